@@ -1,0 +1,203 @@
+"""Oracle restatement of the reference policy/value nets (PyTorch-CPU, fp32/fp64).
+
+TEST INFRASTRUCTURE — see ``oracle/__init__.py``.  **PARITY UNPINNED** at the
+MXNet boundary: the arithmetic of the reference lives in MXNet
+(``requirements.txt:8`` -> mxnet==1.6.0; graph file written by 1.5.1), which is
+not present in ``/root/reference`` nor installable here.  This module restates
+the documented MXNet-1.x operator semantics the reference call sites rely on:
+
+* ``Convolution`` : NCHW cross-correlation, weight (O,I,kh,kw), bias on,
+  pad = k//2 (``policy_value_net_mxnet_simple.py:39-46``)
+* ``BatchNorm``   : eps=1e-3, inference uses moving mean/var,
+  ``fix_gamma=True`` by default (gamma treated as 1) -- the ``conv_act`` BNs
+  (``..._simple.py:47-53``); ``fix_gamma=False`` for ``bnA*/bnB*``
+  (``policy_value_net_mxnet.py:77-81``)
+* ``Flatten`` -> (N, C*H*W); ``Dropout`` identity at inference;
+  ``FullyConnected`` y = x W^T + b with W (out,in);
+  ``SoftmaxActivation`` = softmax over the S logits (probabilities).
+
+Graphs: simple = ``policy_value_net_mxnet_simple.py:68-92``;
+residual = ``policy_value_net_mxnet.py:70-102``.
+Parameter names/shapes are the reference's (``policy_value_net_mxnet.py:125-138``).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-3
+SIMPLE_TRUNK = (("conv1", 64), ("conv2", 64), ("conv3", 128), ("conv4", 128),
+                ("conv5", 256), ("conv_final", 256))
+
+
+def trunk_spec(arch, n_blocks=10, n_filter=128):
+    """[(kind, names..., cin, cout)] for the 3x3 trunk."""
+    if arch == "simple":
+        spec, cin = [], 9
+        for name, cout in SIMPLE_TRUNK:
+            spec.append(("conv_act", name, cin, cout))
+            cin = cout
+        return spec, cin
+    if arch == "resnet":
+        spec = [("conv_act", "res_conv1", 9, 128)]
+        cin = 128
+        for i in range(1, n_blocks + 1):
+            spec.append(("res_block", i, cin, n_filter))
+            cin = n_filter
+        return spec, cin
+    raise ValueError(arch)
+
+
+def param_shapes(arch, width, height, n_blocks=10, n_filter=128):
+    """OrderedDict name -> shape, arg params then aux params (is_aux flag)."""
+    S = width * height
+    arg, aux = OrderedDict(), OrderedDict()
+
+    def conv_act(name, cin, cout, k):
+        arg[name + "_weight"] = (cout, cin, k, k)
+        arg[name + "_bias"] = (cout,)
+        arg[name + "_gamma"] = (cout,)
+        arg[name + "_beta"] = (cout,)
+        aux[name + "_mean"] = (cout,)
+        aux[name + "_var"] = (cout,)
+
+    spec, cfin = trunk_spec(arch, n_blocks, n_filter)
+    for item in spec:
+        if item[0] == "conv_act":
+            conv_act(item[1], item[2], item[3], 3)
+        else:
+            _, i, cin, cout = item
+            for tag, ci in (("A", cin), ("B", cout)):
+                arg["conv%s%d_weight" % (tag, i)] = (cout, ci, 3, 3)
+                arg["conv%s%d_bias" % (tag, i)] = (cout,)
+                arg["bn%s%d_gamma" % (tag, i)] = (cout,)
+                arg["bn%s%d_beta" % (tag, i)] = (cout,)
+                aux["bn%s%d_moving_mean" % (tag, i)] = (cout,)
+                aux["bn%s%d_moving_var" % (tag, i)] = (cout,)
+    conv_act("conv3_1_1", cfin, 4, 1)
+    arg["fc_3_1_1_weight"] = (S, 4 * S)
+    arg["fc_3_1_1_bias"] = (S,)
+    conv_act("conv3_2_1", cfin, 2, 1)
+    arg["fc_3_2_1_weight"] = (1, 2 * S)
+    arg["fc_3_2_1_bias"] = (1,)
+    return arg, aux
+
+
+def init_params(arch, width, height, seed=0, n_blocks=10, n_filter=128, synthetic_stats=True):
+    """Xavier(uniform, avg, magnitude 3) weights, zero biases, gamma 1, beta 0
+    (MXNet ``mx.init.Xavier()`` defaults, ``..._simple.py:148``).  With
+    ``synthetic_stats`` the moving stats are mu~N(0,0.1), var~U(0.5,1.5) and
+    beta~N(0,0.1), biases~N(0,0.05) so BN folding is actually exercised
+    (SURVEY 8(d) synthetic weights)."""
+    g = torch.Generator().manual_seed(seed)
+    arg_s, aux_s = param_shapes(arch, width, height, n_blocks, n_filter)
+    arg, aux = OrderedDict(), OrderedDict()
+    for name, shp in arg_s.items():
+        if name.endswith("_weight"):
+            hw = int(np.prod(shp[2:])) if len(shp) > 2 else 1
+            fan_in, fan_out = shp[1] * hw, shp[0] * hw
+            scale = math.sqrt(3.0 / ((fan_in + fan_out) / 2.0))
+            t = (torch.rand(shp, generator=g, dtype=torch.float32) * 2 - 1) * scale
+        elif name.endswith("_gamma"):
+            t = torch.ones(shp)
+            if synthetic_stats and name.startswith("bn"):
+                t = 0.5 + torch.rand(shp, generator=g)
+        elif name.endswith("_beta"):
+            t = torch.randn(shp, generator=g) * 0.1 if synthetic_stats else torch.zeros(shp)
+        else:  # bias
+            t = torch.randn(shp, generator=g) * 0.05 if synthetic_stats else torch.zeros(shp)
+        arg[name] = t.numpy().astype(np.float32)
+    for name, shp in aux_s.items():
+        if name.endswith("mean"):
+            t = torch.randn(shp, generator=g) * 0.1 if synthetic_stats else torch.zeros(shp)
+        else:
+            t = 0.5 + torch.rand(shp, generator=g) if synthetic_stats else torch.ones(shp)
+        aux[name] = t.numpy().astype(np.float32)
+    return arg, aux
+
+
+def _bn(x, gamma, beta, mean, var, fix_gamma):
+    inv = 1.0 / torch.sqrt(var + BN_EPS)
+    y = (x - mean[None, :, None, None]) * inv[None, :, None, None]
+    if not fix_gamma:
+        y = y * gamma[None, :, None, None]
+    return y + beta[None, :, None, None]
+
+
+def forward(arg, aux, states, arch, n_blocks=10, n_filter=128, dtype=torch.float32,
+            return_logits=False):
+    """states: (B, 9, H, W) array-like -> (probs (B,S), values (B,1)) numpy."""
+    P = {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in list(arg.items()) + list(aux.items())}
+    x = torch.as_tensor(np.ascontiguousarray(states)).to(dtype)
+
+    def conv_act(x, name, k):
+        y = F.conv2d(x, P[name + "_weight"], P[name + "_bias"], padding=k // 2)
+        y = _bn(y, P[name + "_gamma"], P[name + "_beta"], P[name + "_mean"], P[name + "_var"], True)
+        return F.relu(y)
+
+    spec, _ = trunk_spec(arch, n_blocks, n_filter)
+    for item in spec:
+        if item[0] == "conv_act":
+            x = conv_act(x, item[1], 3)
+        else:
+            i = item[1]
+            idn = x
+            y = F.conv2d(x, P["convA%d_weight" % i], P["convA%d_bias" % i], padding=1)
+            y = F.relu(_bn(y, P["bnA%d_gamma" % i], P["bnA%d_beta" % i],
+                           P["bnA%d_moving_mean" % i], P["bnA%d_moving_var" % i], False))
+            y = F.conv2d(y, P["convB%d_weight" % i], P["convB%d_bias" % i], padding=1)
+            y = _bn(y, P["bnB%d_gamma" % i], P["bnB%d_beta" % i],
+                    P["bnB%d_moving_mean" % i], P["bnB%d_moving_var" % i], False)
+            x = F.relu(y + idn)
+    B = x.shape[0]
+    p = conv_act(x, "conv3_1_1", 1).reshape(B, -1)
+    logits = p @ P["fc_3_1_1_weight"].t() + P["fc_3_1_1_bias"]
+    probs = torch.softmax(logits, dim=1)
+    v = conv_act(x, "conv3_2_1", 1).reshape(B, -1)
+    val = torch.tanh(v @ P["fc_3_2_1_weight"].t() + P["fc_3_2_1_bias"])
+    if return_logits:
+        return probs.numpy(), val.numpy(), logits.numpy()
+    return probs.numpy(), val.numpy()
+
+
+class ONet(object):
+    """Oracle-side ``PolicyValueNet`` inference face (``..._simple.py:178-226``)."""
+
+    def __init__(self, board_width, board_height, arch="simple", params=None, seed=0,
+                 n_blocks=10, n_filter=128, dtype=torch.float32):
+        self.board_width, self.board_height = board_width, board_height
+        self.arch, self.n_blocks, self.n_filter, self.dtype = arch, n_blocks, n_filter, dtype
+        self.arg, self.aux = params if params is not None else init_params(
+            arch, board_width, board_height, seed, n_blocks, n_filter)
+
+    def policy_value(self, state_batch):
+        with torch.no_grad():
+            return forward(self.arg, self.aux, np.asarray(state_batch), self.arch,
+                           self.n_blocks, self.n_filter, self.dtype)
+
+    def policy_value_fn(self, board):
+        legal = board.availables
+        st = np.ascontiguousarray(board.current_state()).reshape(
+            1, 9, self.board_height, self.board_width)
+        probs, values = self.policy_value(st)
+        return zip(legal, probs[0][legal]), values[0]
+
+
+FLOP_PER_LEAF = {  # 2*MAC of convs + FCs
+    ("simple", 15): 517682700, ("simple", 8): 147169536, ("resnet", 15): 1332521100,
+}
+
+
+def flop_per_leaf(arch, width, height, n_blocks=10, n_filter=128):
+    S = width * height
+    spec, cfin = trunk_spec(arch, n_blocks, n_filter)
+    mac = 0
+    for item in spec:
+        if item[0] == "conv_act":
+            mac += 9 * item[2] * item[3] * S
+        else:
+            mac += 9 * item[2] * item[3] * S + 9 * item[3] * item[3] * S
+    mac += cfin * 6 * S + 4 * S * S + 2 * S
+    return 2 * mac

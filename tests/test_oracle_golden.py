@@ -1,0 +1,129 @@
+"""CPU: the oracle restatement reproduces the golden vectors that
+tests/golden/make_golden.py wrote from the unmodified reference."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle.board import OBoard
+from oracle.evaluators import EVALUATORS, position_key
+from oracle.mcts import OMCTSPlayer, OPureMCTS, pure_policy_value_fn
+from oracle import selfplay as osp
+
+from conftest import GOLDEN
+
+
+def _packed_state(b):
+    return np.packbits(np.ascontiguousarray(b.current_state()).astype(np.uint8).ravel())
+
+
+@pytest.mark.parametrize("name", ["boards_8x8", "boards_15x15", "boards_6x6_4", "boards_5x5"])
+def test_board_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    W, H, n, G = [int(x) for x in z["meta"]]
+    ties = 0
+    for g in range(G):
+        b = OBoard(W, H, n)
+        b.init_board(int(z["start_player"][g]))
+        for k in range(W * H):
+            m = int(z["moves"][g, k])
+            if m < 0:
+                break
+            assert np.array_equal(_packed_state(b), z["feats"][g, k][: (9 * W * H + 7) // 8])
+            b.do_move(m)
+            end, winner = b.game_end()
+            assert int(end) == int(z["ends"][g, k])
+            assert int(winner) == int(z["winners"][g, k])
+            ties += int(end and winner == -1)
+    if name == "boards_5x5":
+        assert ties > 0  # the tie branch (game.py:164-165) is covered
+
+
+def test_board_errors():
+    b = OBoard(4, 8, 5)
+    with pytest.raises(Exception):
+        b.init_board()
+    b = OBoard(8, 8, 5)
+    b.init_board()
+    b.do_move(3)
+    with pytest.raises(ValueError):
+        b.do_move(3)
+
+
+def _run_tree_case(meta, arrs, Board=OBoard, Player=OMCTSPlayer):
+    W, H, n = meta["W"], meta["H"], meta["n"]
+    b = Board(width=W, height=H, n_in_row=n)
+    b.init_board(0)
+    for m in meta["start_moves"]:
+        b.do_move(m)
+    player = Player(EVALUATORS[meta["evaluator"]], c_puct=meta["c_puct"],
+                    n_playout=meta["n_playout"], is_selfplay=meta["selfplay"])
+    np.random.seed(meta["seed"])
+    for ply in range(meta["n_plies"]):
+        move, pi = player.get_action(b, temp=meta["temp"], return_prob=1)
+        assert np.array_equal(pi, arrs["pi"][ply]), "pi differs at ply %d" % ply
+        assert int(move) == int(arrs["chosen"][ply])
+        b.do_move(int(move))
+
+
+def test_tree_golden():
+    metas = json.load(open(os.path.join(GOLDEN, "tree_cases.json")))
+    z = np.load(os.path.join(GOLDEN, "tree_cases.npz"))
+    for i, meta in enumerate(metas):
+        arrs = {k: z["c%d_%s" % (i, k)] for k in ("visits", "q", "pi", "root_n", "chosen")}
+        _run_tree_case(meta, arrs)
+
+
+def hash_rollout(state):
+    player = state.get_current_player()
+    end, winner = state.game_end()
+    if not end:
+        return int(position_key(state) % 3) - 1
+    if winner == -1:
+        return 0
+    return 1 if winner == player else -1
+
+
+def test_pure_golden():
+    metas = json.load(open(os.path.join(GOLDEN, "pure_cases.json")))
+    z = np.load(os.path.join(GOLDEN, "pure_cases.npz"))
+    for i, meta in enumerate(metas):
+        b = OBoard(meta["W"], meta["H"], meta["n"])
+        b.init_board(0)
+        for m in meta["start_moves"]:
+            b.do_move(m)
+        mcts = OPureMCTS(pure_policy_value_fn, meta["c_puct"], meta["n_playout"], rollout_fn=hash_rollout)
+        move = mcts.get_move(b)
+        assert move == meta["move"]
+        assert mcts.root.N == meta["root_n"]
+        S = meta["W"] * meta["H"]
+        visits = np.zeros(S, np.int32)
+        qs = np.zeros(S)
+        for a, node in mcts.root.children.items():
+            visits[a], qs[a] = node.N, node.Q
+        assert np.array_equal(visits, z["p%d_visits" % i])
+        assert np.array_equal(qs, z["p%d_q" % i])
+
+
+def test_selfplay_golden():
+    metas = json.load(open(os.path.join(GOLDEN, "selfplay_cases.json")))
+    z = np.load(os.path.join(GOLDEN, "selfplay_cases.npz"))
+    for i, meta in enumerate(metas):
+        b = OBoard(meta["W"], meta["H"], meta["n"])
+        player = OMCTSPlayer(EVALUATORS[meta["evaluator"]], c_puct=5, n_playout=meta["n_playout"], is_selfplay=1)
+        np.random.seed(meta["seed"])
+        random.seed(meta["seed"])
+        orig = osp.random.random
+        osp.random.random = lambda: 0.5
+        try:
+            winner, data = osp.start_self_play(b, player, temp=meta["temp"])
+        finally:
+            osp.random.random = orig
+        assert winner == meta["winner"]
+        assert [m for m, _ in b.history] == list(z["s%d_moves" % i])
+        assert np.array_equal(np.stack([p for _, p, _ in data]), z["s%d_pi" % i])
+        assert np.array_equal(np.array([zz for _, _, zz in data]), z["s%d_z" % i])
+        st = np.stack([np.packbits(np.ascontiguousarray(s).astype(np.uint8).ravel()) for s, _, _ in data])
+        assert np.array_equal(st, z["s%d_states" % i])
