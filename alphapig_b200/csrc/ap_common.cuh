@@ -1,0 +1,120 @@
+// Shared definitions for libalphapig_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/alphapig_b200.h"
+
+#define AP_MAX_S 256
+#define AP_ROWS 16
+#define AP_FULL 0xffffffffu
+
+// Per-game board meta (16 B).  hist[0] is the most recent move, -1 = none.
+struct BoardMeta {
+  int16_t hist[4];
+  int16_t n_stones;
+  int16_t last_move;
+  int8_t cur;    // player to move: 1 or 2
+  int8_t start;  // start_player index given to init_board
+  int16_t pad;
+};
+
+// Geometry + constants passed by value to kernels.
+struct Geo {
+  int W, H, S, n_in_row;
+  int G;
+  int cap;  // node capacity per game
+  double c_puct;
+};
+
+// SoA node pools: index = g*cap + i.  32 B / node.
+struct Pools {
+  double* P;
+  double* Q;
+  int32_t* N;
+  int32_t* child_start;  // -1 = leaf
+  int32_t* parent;       // -1 = root
+  uint16_t* child_count;
+  int16_t* move;
+  int32_t* alloc;  // [G] nodes in use
+};
+
+// Per-game leaf record written by select, read by features / expand / backup.
+struct Leaves {
+  uint32_t* rows;   // [G][16]
+  BoardMeta* meta;  // [G]
+  int32_t* node;    // [G]
+  int8_t* terminal; // [G] 0/1
+  int8_t* winner;   // [G] winner at the leaf (1,2,-1) when terminal
+  int32_t* depth;   // [G]
+  int16_t* path;    // [G][S]
+};
+
+struct NetState;  // net.cu
+
+struct ap_engine {
+  ap_config cfg;
+  Geo geo;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  uint64_t bytes = 0;
+  std::vector<void*> allocs;
+  // boards
+  uint32_t* rows = nullptr;  // [G][16]  lo16 = player 1 stones of board row h, hi16 = player 2
+  BoardMeta* meta = nullptr; // [G]
+  Pools pools{};
+  Leaves leaves{};
+  int32_t* errflag = nullptr;     // [G] device error codes (sticky until read)
+  unsigned long long* stats = nullptr;  // [8] device counters
+  // scratch for compaction
+  void* scratch = nullptr;
+  int scratch_slots = 0;
+  // staging
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  void* h_stage = nullptr;  // pinned
+  size_t h_stage_bytes = 0;
+  int32_t* d_ids = nullptr;  // [G]
+  // net
+  NetState* net = nullptr;
+  float* d_probs = nullptr;   // [G][S] fp32
+  float* d_values = nullptr;  // [G]
+  float last_total_ms = 0.f, last_net_ms = 0.f;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define AP_CUDA(e, call)                                                                  \
+  do {                                                                                    \
+    cudaError_t _st = (call);                                                             \
+    if (_st != cudaSuccess) {                                                             \
+      (e)->err = std::string(#call) + ": " + cudaGetErrorString(_st);                     \
+      return AP_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define AP_LAUNCH_CHECK(e)                                                                \
+  do {                                                                                    \
+    (e)->launches++;                                                                      \
+    cudaError_t _st = cudaGetLastError();                                                 \
+    if (_st != cudaSuccess) {                                                             \
+      (e)->err = std::string("kernel launch: ") + cudaGetErrorString(_st) + " at " +      \
+                 __FILE__ + ":" + std::to_string(__LINE__);                               \
+      return AP_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+// helpers implemented in engine.cu
+int ap_fail(ap_engine* e, int code, const std::string& msg);
+int ap_stage(ap_engine* e, size_t dbytes, size_t hbytes);
+int ap_ids(ap_engine* e, const int32_t* game_ids, int32_t n);  // uploads ids (or iota) into e->d_ids
+
+// net.cu
+int net_destroy(ap_engine* e);
+int net_forward_leaves(ap_engine* e, int precise);
+int net_emit_features_launch(ap_engine* e);
+int net_check_err(ap_engine* e);

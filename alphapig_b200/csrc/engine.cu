@@ -1,0 +1,484 @@
+// C-ABI of libalphapig_b200.so: handle lifecycle, staging, and the host side of every entry point.
+#include <string.h>
+
+#include <algorithm>
+
+#include "kernels.h"
+#include "net.h"
+
+int ap_fail(ap_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg;
+  return code;
+}
+
+static int dev_alloc(ap_engine* e, void** p, size_t bytes, bool zero = true) {
+  AP_CUDA(e, cudaMalloc(p, bytes));
+  e->allocs.push_back(*p);
+  e->bytes += bytes;
+  if (zero) AP_CUDA(e, cudaMemsetAsync(*p, 0, bytes, e->stream));
+  return AP_OK;
+}
+#define AP_TRY(x)            \
+  do {                       \
+    int _r = (x);            \
+    if (_r != AP_OK) return _r; \
+  } while (0)
+
+// grow-only device + pinned host staging buffers
+int ap_stage(ap_engine* e, size_t dbytes, size_t hbytes) {
+  if (dbytes > e->stage_bytes) {
+    if (e->d_stage) cudaFree(e->d_stage);
+    e->d_stage = nullptr;
+    size_t nb = std::max(dbytes, e->stage_bytes * 2);
+    AP_CUDA(e, cudaMalloc(&e->d_stage, nb));
+    e->stage_bytes = nb;
+  }
+  if (hbytes > e->h_stage_bytes) {
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    e->h_stage = nullptr;
+    size_t nb = std::max(hbytes, e->h_stage_bytes * 2);
+    AP_CUDA(e, cudaMallocHost(&e->h_stage, nb));
+    e->h_stage_bytes = nb;
+  }
+  return AP_OK;
+}
+
+int ap_ids(ap_engine* e, const int32_t* game_ids, int32_t n) {
+  if (n < 0 || n > e->geo.G) return ap_fail(e, AP_ERR_BAD_ARG, "n out of range");
+  std::vector<int32_t> ids(n);
+  for (int i = 0; i < n; ++i) {
+    ids[i] = game_ids ? game_ids[i] : i;
+    if (ids[i] < 0 || ids[i] >= e->geo.G) return ap_fail(e, AP_ERR_BAD_ARG, "game id out of range");
+  }
+  AP_CUDA(e, cudaMemcpyAsync(e->d_ids, ids.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));  // ids vector dies at return
+  return AP_OK;
+}
+
+static int h2d(ap_engine* e, void* d, const void* h, size_t bytes) {
+  AP_CUDA(e, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream));
+  return AP_OK;
+}
+static int d2h_sync(ap_engine* e, void* h, const void* d, size_t bytes) {
+  AP_CUDA(e, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  return AP_OK;
+}
+
+static int check_errflags(ap_engine* e) {
+  // sticky per-game device error codes -> first one reported
+  std::vector<int32_t> f(e->geo.G);
+  AP_TRY(d2h_sync(e, f.data(), e->errflag, sizeof(int32_t) * e->geo.G));
+  for (int g = 0; g < e->geo.G; ++g)
+    if (f[g] != 0) {
+      int code = f[g];
+      cudaMemsetAsync(e->errflag, 0, sizeof(int32_t) * e->geo.G, e->stream);
+      return ap_fail(e, code, "game " + std::to_string(g) + ": " +
+                                  (code == AP_ERR_POOL_EXHAUSTED ? "node pool exhausted (raise node_capacity)"
+                                                                 : "device error"));
+    }
+  return AP_OK;
+}
+
+extern "C" {
+
+const char* ap_version(void) { return "alphapig_b200 0.1 (sm_100a)"; }
+
+const char* ap_last_error(const ap_engine* e) { return e ? e->err.c_str() : "bad handle"; }
+
+int ap_engine_create(const ap_config* cfg, ap_engine** out) {
+  if (!cfg || !out) return AP_ERR_BAD_ARG;
+  *out = nullptr;
+  // game.py:36-38: width/height must be >= n_in_row
+  if (cfg->width < cfg->n_in_row || cfg->height < cfg->n_in_row || cfg->width > 16 || cfg->height > 16 ||
+      cfg->n_in_row < 2 || cfg->n_games < 1)
+    return AP_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return AP_ERR_CUDA;
+  ap_engine* e = new ap_engine();
+  e->cfg = *cfg;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) {
+    delete e;
+    return AP_ERR_CUDA;
+  }
+  Geo& g = e->geo;
+  g.W = cfg->width;
+  g.H = cfg->height;
+  g.S = g.W * g.H;
+  g.n_in_row = cfg->n_in_row;
+  g.G = cfg->n_games;
+  g.c_puct = cfg->c_puct;
+  int cap = cfg->node_capacity;
+  if (cap <= 0) {
+    // every playout adds at most S children; a re-rooted subtree can retain about one search's worth
+    long long want = 2ll * std::max(cfg->n_playout_hint, 1) * g.S + g.S + 2;
+    cap = (int)std::min<long long>(want, 1 << 20);
+  }
+  g.cap = cap;
+  int rc = AP_OK;
+  auto fail = [&](int code) {
+    e->err += " (engine_create)";
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    static std::string last;
+    last = e->err;
+    delete e;
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(AP_ERR_CUDA);
+  const size_t G = g.G, N = G * (size_t)cap;
+#define ALLOC(ptr, bytes) \
+  if ((rc = dev_alloc(e, (void**)&(ptr), (bytes))) != AP_OK) return fail(rc)
+  ALLOC(e->rows, G * AP_ROWS * 4);
+  ALLOC(e->meta, G * sizeof(BoardMeta));
+  ALLOC(e->pools.P, N * 8);
+  ALLOC(e->pools.Q, N * 8);
+  ALLOC(e->pools.N, N * 4);
+  ALLOC(e->pools.child_start, N * 4);
+  ALLOC(e->pools.parent, N * 4);
+  ALLOC(e->pools.child_count, N * 2);
+  ALLOC(e->pools.move, N * 2);
+  ALLOC(e->pools.alloc, G * 4);
+  ALLOC(e->leaves.rows, G * AP_ROWS * 4);
+  ALLOC(e->leaves.meta, G * sizeof(BoardMeta));
+  ALLOC(e->leaves.node, G * 4);
+  ALLOC(e->leaves.terminal, G);
+  ALLOC(e->leaves.winner, G);
+  ALLOC(e->leaves.depth, G * 4);
+  ALLOC(e->leaves.path, G * (size_t)g.S * 2);
+  ALLOC(e->errflag, G * 4);
+  ALLOC(e->stats, 8 * 8);
+  ALLOC(e->d_ids, G * 4);
+  ALLOC(e->d_probs, G * (size_t)g.S * 4);
+  ALLOC(e->d_values, G * 4);
+  e->scratch_slots = (int)std::min<size_t>(G, 296);
+  ALLOC(e->scratch, (size_t)e->scratch_slots * scratch_bytes_per_slot(cap));
+#undef ALLOC
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+  // all boards empty with player 1 to move, all trees a fresh root
+  std::vector<int32_t> ids(G);
+  for (size_t i = 0; i < G; ++i) ids[i] = (int32_t)i;
+  cudaMemcpyAsync(e->d_ids, ids.data(), G * 4, cudaMemcpyHostToDevice, e->stream);
+  launch_boards_reset(e, g.G, nullptr);
+  launch_tree_reset_all(e);
+  e->launches += 2;
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    e->err = "initial reset kernels failed (is this an sm_100a device?)";
+    return fail(AP_ERR_CUDA);
+  }
+  *out = e;
+  return AP_OK;
+}
+
+int ap_engine_destroy(ap_engine* e) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  net_destroy(e);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->d_stage) cudaFree(e->d_stage);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return AP_OK;
+}
+
+int ap_sync(ap_engine* e) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  return AP_OK;
+}
+
+int ap_engine_memory(const ap_engine* e, uint64_t* out_bytes) {
+  if (!e || !out_bytes) return AP_ERR_BAD_HANDLE;
+  *out_bytes = e->bytes;
+  return AP_OK;
+}
+
+int ap_launch_count(const ap_engine* e, uint64_t* out) {
+  if (!e || !out) return AP_ERR_BAD_HANDLE;
+  *out = e->launches;
+  return AP_OK;
+}
+
+// ---- boards -------------------------------------------------------------------------------
+
+int ap_boards_reset(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* start_player) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  int32_t* d_start = nullptr;
+  if (start_player) {
+    for (int i = 0; i < n; ++i)
+      if (start_player[i] != 0 && start_player[i] != 1)
+        return ap_fail(e, AP_ERR_BAD_ARG, "start_player should be either 0 or 1");  // game.py:206-208
+    AP_TRY(ap_stage(e, sizeof(int32_t) * n, 0));
+    d_start = (int32_t*)e->d_stage;
+    AP_TRY(h2d(e, d_start, start_player, sizeof(int32_t) * n));
+  }
+  launch_boards_reset(e, n, d_start);
+  AP_LAUNCH_CHECK(e);
+  return ap_sync(e);
+}
+
+int ap_boards_do_move(ap_engine* e, const int32_t* game_ids, const int32_t* moves, int32_t n, int32_t* out_status) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  AP_TRY(ap_stage(e, sizeof(int32_t) * 2 * n, 0));
+  int32_t* d_moves = (int32_t*)e->d_stage;
+  int32_t* d_status = d_moves + n;
+  AP_TRY(h2d(e, d_moves, moves, sizeof(int32_t) * n));
+  launch_boards_do_move(e, n, d_moves, d_status);
+  AP_LAUNCH_CHECK(e);
+  std::vector<int32_t> st(n);
+  AP_TRY(d2h_sync(e, st.data(), d_status, sizeof(int32_t) * n));
+  int rc = AP_OK;
+  for (int i = 0; i < n; ++i) {
+    if (out_status) out_status[i] = st[i];
+    if (st[i] != AP_OK && rc == AP_OK) {
+      rc = st[i];
+      e->err = "illegal move " + std::to_string(moves[i]) + " for game " + std::to_string(game_ids ? game_ids[i] : i);
+    }
+  }
+  return rc;
+}
+
+int ap_boards_status(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* out_end, int8_t* out_winner) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  AP_TRY(ap_stage(e, 2 * (size_t)n, 0));
+  uint8_t* d_end = (uint8_t*)e->d_stage;
+  int8_t* d_win = (int8_t*)e->d_stage + n;
+  launch_boards_status(e, e->rows, e->meta, e->d_ids, n, d_end, d_win);
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaMemcpyAsync(out_end, d_end, n, cudaMemcpyDeviceToHost, e->stream));
+  return d2h_sync(e, out_winner, d_win, n);
+}
+
+int ap_boards_legal(ap_engine* e, const int32_t* game_ids, int32_t n, uint32_t* out_mask) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  AP_TRY(ap_stage(e, 32 * (size_t)n, 0));
+  launch_boards_legal(e, e->d_ids, n, (uint32_t*)e->d_stage);
+  AP_LAUNCH_CHECK(e);
+  return d2h_sync(e, out_mask, e->d_stage, 32 * (size_t)n);
+}
+
+int ap_boards_features(ap_engine* e, const int32_t* game_ids, int32_t n, float* out) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  size_t bytes = (size_t)n * 9 * e->geo.S * 4;
+  AP_TRY(ap_stage(e, bytes, 0));
+  launch_boards_features(e, e->rows, e->meta, e->d_ids, n, (float*)e->d_stage);
+  e->launches++;
+  AP_LAUNCH_CHECK(e);
+  return d2h_sync(e, out, e->d_stage, bytes);
+}
+
+static int export_common(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
+                         int8_t* out_cells, int32_t* out_meta) {
+  size_t cb = ((size_t)n * e->geo.S + 15) & ~(size_t)15, mb = (size_t)n * AP_META_INTS * 4;
+  AP_TRY(ap_stage(e, cb + mb, 0));
+  int8_t* d_cells = (int8_t*)e->d_stage;
+  int32_t* d_meta = (int32_t*)((char*)e->d_stage + cb);
+  launch_boards_export(e, rows, meta, d_ids, n, d_cells, d_meta);
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaMemcpyAsync(out_cells, d_cells, (size_t)n * e->geo.S, cudaMemcpyDeviceToHost, e->stream));
+  return d2h_sync(e, out_meta, d_meta, mb);
+}
+
+int ap_boards_export(ap_engine* e, const int32_t* game_ids, int32_t n, int8_t* out_cells, int32_t* out_meta) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  return export_common(e, e->rows, e->meta, e->d_ids, n, out_cells, out_meta);
+}
+
+int ap_boards_import(ap_engine* e, const int32_t* game_ids, int32_t n, const int8_t* cells, const int32_t* meta) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  size_t cb = ((size_t)n * e->geo.S + 15) & ~(size_t)15, mb = (size_t)n * AP_META_INTS * 4;
+  AP_TRY(ap_stage(e, cb + mb, 0));
+  int8_t* d_cells = (int8_t*)e->d_stage;
+  int32_t* d_meta = (int32_t*)((char*)e->d_stage + cb);
+  AP_TRY(h2d(e, d_cells, cells, (size_t)n * e->geo.S));
+  AP_TRY(h2d(e, d_meta, meta, mb));
+  launch_boards_import(e, n, d_cells, d_meta);
+  AP_LAUNCH_CHECK(e);
+  return ap_sync(e);
+}
+
+// ---- search -------------------------------------------------------------------------------
+
+int ap_search_select(ap_engine* e, uint8_t* out_terminal, int32_t* out_depth, int16_t* out_path) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  launch_select(e);
+  AP_LAUNCH_CHECK(e);
+  const int G = e->geo.G;
+  if (out_terminal) AP_CUDA(e, cudaMemcpyAsync(out_terminal, e->leaves.terminal, G, cudaMemcpyDeviceToHost, e->stream));
+  if (out_depth) AP_CUDA(e, cudaMemcpyAsync(out_depth, e->leaves.depth, 4 * (size_t)G, cudaMemcpyDeviceToHost, e->stream));
+  if (out_path)
+    AP_CUDA(e, cudaMemcpyAsync(out_path, e->leaves.path, 2 * (size_t)G * e->geo.S, cudaMemcpyDeviceToHost, e->stream));
+  return ap_sync(e);
+}
+
+int ap_search_leaf_export(ap_engine* e, int8_t* out_cells, int32_t* out_meta) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  return export_common(e, e->leaves.rows, e->leaves.meta, nullptr, e->geo.G, out_cells, out_meta);
+}
+
+int ap_search_leaf_features(ap_engine* e, float* out) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  size_t bytes = (size_t)e->geo.G * 9 * e->geo.S * 4;
+  AP_TRY(ap_stage(e, bytes, 0));
+  launch_boards_features(e, e->leaves.rows, e->leaves.meta, nullptr, e->geo.G, (float*)e->d_stage);
+  e->launches++;
+  AP_LAUNCH_CHECK(e);
+  return d2h_sync(e, out, e->d_stage, bytes);
+}
+
+int ap_search_expand_backup(ap_engine* e, const int32_t* counts, const int16_t* acts, const double* priors,
+                            const double* values) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!counts || !acts || !priors || !values) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
+  const size_t G = e->geo.G, S = e->geo.S;
+  for (size_t g = 0; g < G; ++g)
+    if (counts[g] < 0 || counts[g] > (int)S) return ap_fail(e, AP_ERR_BAD_ARG, "counts out of range");
+  size_t o_counts = 0, o_acts = o_counts + ((G * 4 + 15) & ~15ull), o_pri = o_acts + ((G * S * 2 + 15) & ~15ull),
+         o_val = o_pri + G * S * 8, tot = o_val + G * 8;
+  AP_TRY(ap_stage(e, tot, 0));
+  char* d = (char*)e->d_stage;
+  AP_TRY(h2d(e, d + o_counts, counts, G * 4));
+  AP_TRY(h2d(e, d + o_acts, acts, G * S * 2));
+  AP_TRY(h2d(e, d + o_pri, priors, G * S * 8));
+  AP_TRY(h2d(e, d + o_val, values, G * 8));
+  launch_expand_backup(e, (int32_t*)(d + o_counts), (int16_t*)(d + o_acts), (double*)(d + o_pri), (double*)(d + o_val),
+                       nullptr, nullptr);
+  AP_LAUNCH_CHECK(e);
+  return check_errflags(e);
+}
+
+int ap_search_expand_backup_dense(ap_engine* e, const float* priors, const float* values) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!priors || !values) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
+  const size_t G = e->geo.G, S = e->geo.S;
+  AP_TRY(h2d(e, e->d_probs, priors, G * S * 4));
+  AP_TRY(h2d(e, e->d_values, values, G * 4));
+  launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values);
+  AP_LAUNCH_CHECK(e);
+  return check_errflags(e);
+}
+
+int ap_search_run(ap_engine* e, int32_t n_playout) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "ap_search_run: no net loaded (ap_net_load)");
+  AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  for (int it = 0; it < n_playout; ++it) {
+    launch_select(e);
+    AP_LAUNCH_CHECK(e);
+    AP_TRY(net_forward_leaves(e, 0));
+    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values);
+    AP_LAUNCH_CHECK(e);
+  }
+  AP_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  cudaEventElapsedTime(&e->last_total_ms, e->ev0, e->ev1);
+  AP_TRY(net_check_err(e));
+  return check_errflags(e);
+}
+
+int ap_search_timing(ap_engine* e, float* out_total_ms, float* out_net_ms) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (out_total_ms) *out_total_ms = e->last_total_ms;
+  if (out_net_ms) *out_net_ms = e->last_net_ms;
+  return AP_OK;
+}
+
+int ap_search_root(ap_engine* e, const int32_t* game_ids, int32_t n, int32_t* out_count, int16_t* out_acts,
+                   int32_t* out_visits, double* out_q, int32_t* out_root_n) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  const size_t S = e->geo.S, nn = n;
+  size_t o_cnt = 0, o_rn = o_cnt + ((nn * 4 + 15) & ~15ull), o_acts = o_rn + ((nn * 4 + 15) & ~15ull),
+         o_vis = o_acts + ((nn * S * 2 + 15) & ~15ull), o_q = o_vis + nn * S * 4, tot = o_q + nn * S * 8;
+  AP_TRY(ap_stage(e, tot, 0));
+  char* d = (char*)e->d_stage;
+  launch_root(e, e->d_ids, n, (int32_t*)(d + o_cnt), (int16_t*)(d + o_acts), (int32_t*)(d + o_vis),
+              out_q ? (double*)(d + o_q) : nullptr, (int32_t*)(d + o_rn));
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaMemcpyAsync(out_count, d + o_cnt, nn * 4, cudaMemcpyDeviceToHost, e->stream));
+  AP_CUDA(e, cudaMemcpyAsync(out_acts, d + o_acts, nn * S * 2, cudaMemcpyDeviceToHost, e->stream));
+  AP_CUDA(e, cudaMemcpyAsync(out_visits, d + o_vis, nn * S * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (out_q) AP_CUDA(e, cudaMemcpyAsync(out_q, d + o_q, nn * S * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (out_root_n) AP_CUDA(e, cudaMemcpyAsync(out_root_n, d + o_rn, nn * 4, cudaMemcpyDeviceToHost, e->stream));
+  return ap_sync(e);
+}
+
+int ap_search_root_probs(ap_engine* e, double temp, double* out) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!(temp > 0)) return ap_fail(e, AP_ERR_BAD_ARG, "temp must be > 0");
+  size_t bytes = (size_t)e->geo.G * e->geo.S * 8;
+  AP_TRY(ap_stage(e, bytes, 0));
+  launch_root_probs(e, temp, (double*)e->d_stage);
+  AP_LAUNCH_CHECK(e);
+  return d2h_sync(e, out, e->d_stage, bytes);
+}
+
+int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  AP_TRY(ap_stage(e, sizeof(int32_t) * n, 0));
+  AP_TRY(h2d(e, e->d_stage, moves, sizeof(int32_t) * n));
+  launch_advance(e, n, (int32_t*)e->d_stage);
+  AP_LAUNCH_CHECK(e);
+  return ap_sync(e);
+}
+
+int ap_search_stats(ap_engine* e, uint64_t* out5) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  unsigned long long h[8];
+  AP_TRY(d2h_sync(e, h, e->stats, sizeof(h)));
+  for (int i = 0; i < 6; ++i) out5[i] = h[i];
+  AP_CUDA(e, cudaMemsetAsync(e->stats, 0, sizeof(h), e->stream));
+  return ap_sync(e);
+}
+
+// ---- mcts_pure ------------------------------------------------------------------------------
+
+int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_mode, int32_t* out_move) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_stage(e, 4 * (size_t)e->geo.G, 0));
+  AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  launch_pure_run(e, n_playout, seed, rollout_mode, (int32_t*)e->d_stage);
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  AP_TRY(d2h_sync(e, out_move, e->d_stage, 4 * (size_t)e->geo.G));
+  cudaEventElapsedTime(&e->last_total_ms, e->ev0, e->ev1);
+  return check_errflags(e);
+}
+
+int ap_rollout_eval(ap_engine* e, uint64_t seed, int8_t* out_value, int16_t* out_plies) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  const size_t G = e->geo.G;
+  AP_TRY(ap_stage(e, 4 * G, 0));
+  int8_t* d_v = (int8_t*)e->d_stage;
+  int16_t* d_p = (int16_t*)((char*)e->d_stage + ((G + 15) & ~15ull));
+  AP_TRY(ap_stage(e, ((G + 15) & ~15ull) + 2 * G, 0));
+  d_v = (int8_t*)e->d_stage;
+  d_p = (int16_t*)((char*)e->d_stage + ((G + 15) & ~15ull));
+  launch_rollout_eval(e, seed, d_v, d_p);
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaMemcpyAsync(out_value, d_v, G, cudaMemcpyDeviceToHost, e->stream));
+  return d2h_sync(e, out_plies, d_p, 2 * G);
+}
+
+int ap_rollout_hash(ap_engine* e, int8_t* out_value) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_stage(e, e->geo.G, 0));
+  launch_rollout_hash(e, (int8_t*)e->d_stage);
+  AP_LAUNCH_CHECK(e);
+  return d2h_sync(e, out_value, e->d_stage, e->geo.G);
+}
+
+}  // extern "C"

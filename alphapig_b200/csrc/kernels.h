@@ -1,0 +1,31 @@
+// Host-side launch wrappers (each enqueues on e->stream; caller does AP_LAUNCH_CHECK).
+#pragma once
+#include "ap_common.cuh"
+
+// boards.cu
+void launch_boards_reset(ap_engine* e, int n, const int32_t* d_start);
+void launch_boards_do_move(ap_engine* e, int n, const int32_t* d_moves, int32_t* d_status);
+void launch_boards_status(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
+                          uint8_t* d_end, int8_t* d_winner);
+void launch_boards_legal(ap_engine* e, const int32_t* d_ids, int n, uint32_t* d_mask);
+void launch_boards_features(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
+                            float* d_out);
+void launch_boards_export(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
+                          int8_t* d_cells, int32_t* d_meta);
+void launch_boards_import(ap_engine* e, int n, const int8_t* d_cells, const int32_t* d_meta);
+
+// tree.cu
+void launch_tree_reset_all(ap_engine* e);
+void launch_select(ap_engine* e);
+void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* d_acts, const double* d_pri64,
+                          const double* d_val64, const float* d_pri32, const float* d_val32);
+void launch_advance(ap_engine* e, int n, const int32_t* d_moves);
+void launch_root(ap_engine* e, const int32_t* d_ids, int n, int32_t* d_count, int16_t* d_acts, int32_t* d_visits,
+                 double* d_q, int32_t* d_rootn);
+void launch_root_probs(ap_engine* e, double temp, double* d_out);
+size_t scratch_bytes_per_slot(int cap);
+
+// rollout.cu
+void launch_pure_run(ap_engine* e, int n_playout, uint64_t seed, int mode, int32_t* d_move);
+void launch_rollout_eval(ap_engine* e, uint64_t seed, int8_t* d_value, int16_t* d_plies);
+void launch_rollout_hash(ap_engine* e, int8_t* d_value);

@@ -1,0 +1,647 @@
+// Policy/value net: parameter table with the reference's names, BN folding / operand images for the
+// tensor-core trunk (conv_tc.cu), feature emission from bitboards, the fused heads kernel, and an
+// independent fp32 CUDA-core path used as an on-device cross-check.
+// Replaces PolicyValueNet inference (policy_value_net_mxnet_simple.py:68-92,178-226;
+// policy_value_net_mxnet.py:70-102,232-280).
+#include <string.h>
+
+#include "board.cuh"
+#include "kernels.h"
+#include "net.h"
+
+#define BN_EPS 1e-3f
+
+#define AP_TRY(x)               \
+  do {                          \
+    int _r = (x);               \
+    if (_r != AP_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// prep kernels (run at load and after every weight refresh)
+// ------------------------------------------------------------------------------------------
+__global__ void k_prep_conv(const float* __restrict__ master, long long w, long long b, long long gamma, long long beta,
+                            long long mean, long long var, int fix_gamma, int cin, int cin_pad, int cout, int kc,
+                            __half* wimg, float* scale, float* shift) {
+  const long long total = (long long)9 * cin_pad * cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // image order: [kcI][tap][j][n][e]
+    int e = (int)(i & 7);
+    long long r = i >> 3;
+    int n = (int)(r % cout);
+    r /= cout;
+    int j = (int)(r % (kc >> 3));
+    r /= (kc >> 3);
+    int tap = (int)(r % 9);
+    int kcI = (int)(r / 9);
+    int k = kcI * kc + j * 8 + e;
+    float v = (k < cin) ? master[w + ((long long)n * cin + k) * 9 + tap] : 0.f;
+    wimg[i] = __float2half_rn(v);
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < cout; n += gridDim.x * blockDim.x) {
+    float s = 1.f / sqrtf(master[var + n] + BN_EPS);
+    if (!fix_gamma) s *= master[gamma + n];
+    scale[n] = s;
+    shift[n] = (master[b + n] - master[mean + n]) * s + master[beta + n];
+  }
+}
+
+__global__ void k_prep_heads(const float* __restrict__ master, HeadParams h, int S) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < 6 * h.cfin; i += nth) {
+    int o = i / h.cfin, c = i % h.cfin;
+    bool pol = o < 4;
+    int oo = pol ? o : o - 4;
+    float s = 1.f / sqrtf(master[(pol ? h.pvar : h.vvar) + oo] + BN_EPS);  // fix_gamma=True (conv_act)
+    h.w1x1[i] = master[(pol ? h.pw : h.vw) + (long long)oo * h.cfin + c] * s;
+  }
+  for (int o = tid; o < 6; o += nth) {
+    bool pol = o < 4;
+    int oo = pol ? o : o - 4;
+    float s = 1.f / sqrtf(master[(pol ? h.pvar : h.vvar) + oo] + BN_EPS);
+    h.b1x1[o] = (master[(pol ? h.pb : h.vb) + oo] - master[(pol ? h.pmean : h.vmean) + oo]) * s +
+                master[(pol ? h.pbeta : h.vbeta) + oo];
+  }
+  for (long long i = tid; i < (long long)4 * S * S; i += nth) {
+    int s = (int)(i % S);
+    long long k = i / S;
+    h.fcpT[i] = master[h.fcp_w + (long long)s * 4 * S + k];
+  }
+  for (int i = tid; i < S; i += nth) h.fcp_bias[i] = master[h.fcp_b + i];
+  for (int i = tid; i < 2 * S; i += nth) h.fcv[i] = master[h.fcv_w + i];
+  if (tid == 0) h.fcv_bias[0] = master[h.fcv_b];
+}
+
+// ------------------------------------------------------------------------------------------
+// features: leaf bitboards -> fp16 planes [2][mpad][8]  (Board.current_state, game.py:68-94)
+// ------------------------------------------------------------------------------------------
+__global__ void k_emit_features(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, int nb,
+                                __half* feat, long long mpad) {
+  int lane = threadIdx.x & 31;
+  int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= nb) return;
+  WBoard wb = wb_load(rows, meta, b, lane);
+  const int W = geo.W, H = geo.H;
+  uint32_t pl[8];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    pl[6 - 2 * d] = wb_rows_dropped(wb, wb.cur, d, W, lane);
+    pl[7 - 2 * d] = wb_rows_dropped(wb, 3 - wb.cur, d, W, lane);
+  }
+  const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+  const __half p8 = (wb.nst % 2 == 0) ? one : zero;
+  if (lane < H) {
+    const int y = H - 1 - lane;  // axis-1 flip
+    long long row = NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + y * 16;
+    for (int x = 0; x < W; ++x) {
+      uint4 g0, g1;
+      __half* h0 = reinterpret_cast<__half*>(&g0);
+      __half* h1 = reinterpret_cast<__half*>(&g1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        h0[c] = ((pl[c] >> x) & 1u) ? one : zero;
+        h1[c] = zero;
+      }
+      h1[0] = p8;
+      *reinterpret_cast<uint4*>(feat + (row + x) * 8) = g0;
+      *reinterpret_cast<uint4*>(feat + (mpad + row + x) * 8) = g1;
+    }
+  }
+}
+
+// host fp32 states [B][9][H][W] (already on device) -> fp16 planes
+__global__ void k_pack_states(const float* __restrict__ st, int nb, int W, int H, __half* feat, long long mpad) {
+  const int S = W * H;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb * S) return;
+  int b = i / S, p = i % S, y = p / W, x = p % W;
+  long long row = NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + y * 16 + x;
+  uint4 g0, g1;
+  __half* h0 = reinterpret_cast<__half*>(&g0);
+  __half* h1 = reinterpret_cast<__half*>(&g1);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    h0[c] = __float2half_rn(st[((size_t)b * 9 + c) * S + p]);
+    h1[c] = __float2half_rn(0.f);
+  }
+  h1[0] = __float2half_rn(st[((size_t)b * 9 + 8) * S + p]);
+  *reinterpret_cast<uint4*>(feat + row * 8) = g0;
+  *reinterpret_cast<uint4*>(feat + (mpad + row) * 8) = g1;
+}
+
+// ------------------------------------------------------------------------------------------
+// heads: 1x1 convs (+BN+ReLU) -> FC(4S->S)+softmax, FC(2S->1)+tanh   (..._simple.py:78-90)
+// HB boards per CTA so every FC weight read from L2 feeds HB FMAs.
+// ------------------------------------------------------------------------------------------
+#define HB 4
+#define HEAD_THREADS 256
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int d = 16; d >= 1; d >>= 1) {
+    float o = __shfl_xor_sync(AP_FULL, v, d);
+    v = is_max ? fmaxf(v, o) : v + o;
+  }
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < HEAD_THREADS / 32; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS)
+k_heads(const __half* __restrict__ act, long long mpad, int cfin, int W, int H, int nb, HeadParams h,
+        float* __restrict__ probs, float* __restrict__ values) {
+  extern __shared__ float sh[];
+  const int S = W * H;
+  float* s_w = sh;                 // [6][cfin]
+  float* s_h = s_w + 6 * cfin;     // [HB][6][S]
+  float* s_red = s_h + HB * 6 * S; // [8]
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * HB;
+  for (int i = tid; i < 6 * cfin; i += HEAD_THREADS) s_w[i] = h.w1x1[i];
+  __syncthreads();
+  // phase 1: 1x1 convs
+  for (int idx = tid; idx < HB * S; idx += HEAD_THREADS) {
+    int bi = idx / S, p = idx % S;
+    int b = b0 + bi;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (b < nb) {
+      int y = p / W, x = p % W;
+      long long row = NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + y * 16 + x;
+      for (int cg = 0; cg < (cfin >> 3); ++cg) {
+        uint4 v = *reinterpret_cast<const uint4*>(act + ((long long)cg * mpad + row) * 8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 t = __half22float2(hv[k]);
+          int c = cg * 8 + 2 * k;
+#pragma unroll
+          for (int o = 0; o < 6; ++o) acc[o] = fmaf(t.x, s_w[o * cfin + c], fmaf(t.y, s_w[o * cfin + c + 1], acc[o]));
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 6; ++o) s_h[(bi * 6 + o) * S + p] = fmaxf(acc[o] + h.b1x1[o], 0.f);
+  }
+  __syncthreads();
+  // phase 2: policy FC, thread = output move index
+  float logit[HB];
+#pragma unroll
+  for (int bi = 0; bi < HB; ++bi) logit[bi] = 0.f;
+  if (tid < S) {
+    for (int k = 0; k < 4 * S; ++k) {
+      float w = h.fcpT[(long long)k * S + tid];
+#pragma unroll
+      for (int bi = 0; bi < HB; ++bi) logit[bi] = fmaf(w, s_h[bi * 6 * S + k], logit[bi]);
+    }
+    float bb = h.fcp_bias[tid];
+#pragma unroll
+    for (int bi = 0; bi < HB; ++bi) logit[bi] += bb;
+  }
+#pragma unroll
+  for (int bi = 0; bi < HB; ++bi) {
+    float mx = block_reduce(tid < S ? logit[bi] : -INFINITY, s_red, true);
+    float ex = tid < S ? expf(logit[bi] - mx) : 0.f;
+    float sum = block_reduce(ex, s_red, false);
+    if (tid < S && b0 + bi < nb) probs[(size_t)(b0 + bi) * S + tid] = ex / sum;
+  }
+  // phase 3: value FC
+#pragma unroll
+  for (int bi = 0; bi < HB; ++bi) {
+    float part = 0.f;
+    for (int k = tid; k < 2 * S; k += HEAD_THREADS) part = fmaf(h.fcv[k], s_h[(bi * 6 + 4) * S + k], part);
+    float tot = block_reduce(part, s_red, false);
+    if (tid == 0 && b0 + bi < nb) values[b0 + bi] = tanhf(tot + h.fcv_bias[0]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 CUDA-core reference path (independent of the tensor-core path; NCHW dense, unfolded BN)
+// ------------------------------------------------------------------------------------------
+__global__ void k_ref_conv(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ resid,
+                           const float* __restrict__ master, long long w, long long b, long long gamma, long long beta,
+                           long long mean, long long var, int fix_gamma, int relu, int nb, int cin, int cout, int W, int H,
+                           int ksz) {
+  const int S = W * H;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nb * cout * S) return;
+  int p = (int)(i % S);
+  int o = (int)((i / S) % cout);
+  int bb = (int)(i / ((long long)S * cout));
+  int y = p / W, x = p % W;
+  const int r = ksz / 2;
+  float acc = 0.f;
+  for (int c = 0; c < cin; ++c) {
+    const float* ip = in + ((size_t)bb * cin + c) * S;
+    const float* wp = master + w + ((long long)o * cin + c) * ksz * ksz;
+    for (int ty = 0; ty < ksz; ++ty) {
+      int yy = y + ty - r;
+      if (yy < 0 || yy >= H) continue;
+      for (int tx = 0; tx < ksz; ++tx) {
+        int xx = x + tx - r;
+        if (xx < 0 || xx >= W) continue;
+        acc = fmaf(ip[yy * W + xx], wp[ty * ksz + tx], acc);
+      }
+    }
+  }
+  acc += master[b + o];
+  float v = (acc - master[mean + o]) * (1.f / sqrtf(master[var + o] + BN_EPS));
+  if (!fix_gamma) v *= master[gamma + o];
+  v += master[beta + o];
+  if (resid) v += resid[i];
+  if (relu) v = fmaxf(v, 0.f);
+  out[i] = v;
+}
+
+// one block per board: FCs + softmax/tanh on hp [nb][4][S], hv [nb][2][S]
+__global__ void k_ref_heads(const float* __restrict__ hp, const float* __restrict__ hv, const float* __restrict__ master,
+                            long long fcp_w, long long fcp_b, long long fcv_w, long long fcv_b, int S,
+                            float* __restrict__ probs, float* __restrict__ values) {
+  __shared__ float s_red[HEAD_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float logit = -INFINITY;
+  if (tid < S) {
+    float acc = 0.f;
+    for (int k = 0; k < 4 * S; ++k) acc = fmaf(hp[(size_t)b * 4 * S + k], master[fcp_w + (long long)tid * 4 * S + k], acc);
+    logit = acc + master[fcp_b + tid];
+  }
+  float mx = block_reduce(logit, s_red, true);
+  float ex = tid < S ? expf(logit - mx) : 0.f;
+  float sum = block_reduce(ex, s_red, false);
+  if (tid < S) probs[(size_t)b * S + tid] = ex / sum;
+  float part = 0.f;
+  for (int k = tid; k < 2 * S; k += HEAD_THREADS) part = fmaf(hv[(size_t)b * 2 * S + k], master[fcv_w + k], part);
+  float tot = block_reduce(part, s_red, false);
+  if (tid == 0) values[b] = tanhf(tot + master[fcv_b]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int nalloc(ap_engine* e, NetState* n, void** p, size_t bytes) {
+  AP_CUDA(e, cudaMalloc(p, bytes));
+  AP_CUDA(e, cudaMemsetAsync(*p, 0, bytes, e->stream));
+  n->allocs.push_back(*p);
+  e->bytes += bytes;
+  return AP_OK;
+}
+
+static long long off_of(NetState* n, const std::string& name, long long want_numel, std::string* err) {
+  auto it = n->index.find(name);
+  if (it == n->index.end()) {
+    *err = "missing parameter " + name;
+    return -1;
+  }
+  if (want_numel >= 0 && n->numels[it->second] != want_numel) {
+    *err = "parameter " + name + " has " + std::to_string(n->numels[it->second]) + " elements, expected " +
+           std::to_string(want_numel);
+    return -1;
+  }
+  return n->offsets[it->second];
+}
+
+int net_destroy(ap_engine* e) {
+  if (!e->net) return AP_OK;
+  for (void* p : e->net->allocs) cudaFree(p);
+  delete e->net;
+  e->net = nullptr;
+  return AP_OK;
+}
+
+static int net_prep(ap_engine* e) {
+  NetState* n = e->net;
+  for (auto& L : n->trunk) {
+    int kc = L.cin_pad < 64 ? L.cin_pad : 64;
+    k_prep_conv<<<256, 256, 0, e->stream>>>(n->master, L.w, L.b, L.gamma, L.beta, L.mean, L.var, L.fix_gamma, L.cin,
+                                            L.cin_pad, L.cout, kc, L.wimg, L.scale, L.shift);
+    AP_LAUNCH_CHECK(e);
+  }
+  k_prep_heads<<<256, 256, 0, e->stream>>>(n->master, n->head, n->S);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+
+static int conv_bind(ap_engine* e, NetState* n, ConvLayer& L, const std::string& cname, const std::string& bnname,
+                     bool conv_act_style, std::string* err) {
+  const long long wn = (long long)L.cout * L.cin * 9;
+  L.w = off_of(n, cname + "_weight", wn, err);
+  L.b = off_of(n, cname + "_bias", L.cout, err);
+  if (conv_act_style) {
+    L.gamma = off_of(n, cname + "_gamma", L.cout, err);
+    L.beta = off_of(n, cname + "_beta", L.cout, err);
+    L.mean = off_of(n, cname + "_mean", L.cout, err);
+    L.var = off_of(n, cname + "_var", L.cout, err);
+    L.fix_gamma = 1;
+  } else {
+    L.gamma = off_of(n, bnname + "_gamma", L.cout, err);
+    L.beta = off_of(n, bnname + "_beta", L.cout, err);
+    L.mean = off_of(n, bnname + "_moving_mean", L.cout, err);
+    L.var = off_of(n, bnname + "_moving_var", L.cout, err);
+    L.fix_gamma = 0;
+  }
+  if (L.w < 0 || L.b < 0 || L.gamma < 0 || L.beta < 0 || L.mean < 0 || L.var < 0) return AP_ERR_BAD_ARG;
+  L.cin_pad = (L.cin + 15) & ~15;
+  AP_TRY(nalloc(e, n, (void**)&L.wimg, (size_t)9 * L.cin_pad * L.cout * 2));
+  AP_TRY(nalloc(e, n, (void**)&L.scale, (size_t)L.cout * 4));
+  AP_TRY(nalloc(e, n, (void**)&L.shift, (size_t)L.cout * 4));
+  return AP_OK;
+}
+
+extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t n_filter, const ap_tensor* tensors,
+                           int32_t n_tensors) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!tensors || n_tensors <= 0) return ap_fail(e, AP_ERR_BAD_ARG, "no tensors");
+  if (e->geo.W != e->geo.H || e->geo.W > 15)
+    return ap_fail(e, AP_ERR_BAD_ARG, "the net path needs a square board of width <= 15");
+  if (arch != AP_ARCH_SIMPLE && arch != AP_ARCH_RESNET) return ap_fail(e, AP_ERR_BAD_ARG, "unknown arch");
+  net_destroy(e);
+  NetState* n = new NetState();
+  e->net = n;
+  n->arch = arch;
+  n->n_blocks = n_blocks;
+  n->n_filter = n_filter;
+  n->W = e->geo.W;
+  n->H = e->geo.H;
+  n->S = e->geo.S;
+  cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device);
+  long long total = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    n->names.push_back(tensors[i].name);
+    n->offsets.push_back(total);
+    n->numels.push_back(tensors[i].numel);
+    n->index[tensors[i].name] = i;
+    total += (tensors[i].numel + 3) & ~3ll;  // keep every tensor 16-byte aligned
+  }
+  n->master_numel = total;
+  int rc;
+  if ((rc = nalloc(e, n, (void**)&n->master, (size_t)total * 4)) != AP_OK) return rc;
+  for (int i = 0; i < n_tensors; ++i)
+    AP_CUDA(e, cudaMemcpyAsync(n->master + n->offsets[i], tensors[i].data, (size_t)tensors[i].numel * 4,
+                               cudaMemcpyHostToDevice, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+
+  std::string err;
+  auto bad = [&](int code) {
+    std::string m = err.empty() ? e->err : err;
+    net_destroy(e);
+    return ap_fail(e, code, m);
+  };
+  if (arch == AP_ARCH_SIMPLE) {
+    const char* nm[6] = {"conv1", "conv2", "conv3", "conv4", "conv5", "conv_final"};
+    const int co[6] = {64, 64, 128, 128, 256, 256};
+    int cin = 9, buf = -1;
+    for (int i = 0; i < 6; ++i) {
+      ConvLayer L{};
+      L.cin = cin;
+      L.cout = co[i];
+      L.relu = 1;
+      L.in_buf = buf;
+      L.out_buf = (buf == 0) ? 1 : 0;
+      L.resid_buf = -1;
+      if ((rc = conv_bind(e, n, L, nm[i], "", true, &err)) != AP_OK) return bad(rc);
+      n->trunk.push_back(L);
+      cin = co[i];
+      buf = L.out_buf;
+    }
+    n->final_buf = buf;
+    n->head.cfin = cin;
+  } else {
+    if (n_blocks < 0 || n_filter != 128)
+      return bad(ap_fail(e, AP_ERR_BAD_ARG, "resnet: n_filter must be 128 (stem is hard-coded 128, policy_value_net_mxnet.py:73)"));
+    ConvLayer L{};
+    L.cin = 9;
+    L.cout = 128;
+    L.relu = 1;
+    L.in_buf = -1;
+    L.out_buf = 0;
+    L.resid_buf = -1;
+    if ((rc = conv_bind(e, n, L, "res_conv1", "", true, &err)) != AP_OK) return bad(rc);
+    n->trunk.push_back(L);
+    int x = 0;
+    for (int i = 1; i <= n_blocks; ++i) {
+      int t = (x + 1) % 3, y = (x + 2) % 3;
+      ConvLayer A{};
+      A.cin = 128; A.cout = n_filter; A.relu = 1; A.in_buf = x; A.out_buf = t; A.resid_buf = -1;
+      if ((rc = conv_bind(e, n, A, "convA" + std::to_string(i), "bnA" + std::to_string(i), false, &err)) != AP_OK)
+        return bad(rc);
+      n->trunk.push_back(A);
+      ConvLayer B{};
+      B.cin = n_filter; B.cout = n_filter; B.relu = 1; B.in_buf = t; B.out_buf = y; B.resid_buf = x;
+      if ((rc = conv_bind(e, n, B, "convB" + std::to_string(i), "bnB" + std::to_string(i), false, &err)) != AP_OK)
+        return bad(rc);
+      n->trunk.push_back(B);
+      x = y;
+    }
+    n->final_buf = x;
+    n->head.cfin = n_filter;
+  }
+  HeadParams& h = n->head;
+  const int S = n->S;
+  h.pw = off_of(n, "conv3_1_1_weight", 4ll * h.cfin, &err);
+  h.pb = off_of(n, "conv3_1_1_bias", 4, &err);
+  h.pgamma = off_of(n, "conv3_1_1_gamma", 4, &err);
+  h.pbeta = off_of(n, "conv3_1_1_beta", 4, &err);
+  h.pmean = off_of(n, "conv3_1_1_mean", 4, &err);
+  h.pvar = off_of(n, "conv3_1_1_var", 4, &err);
+  h.vw = off_of(n, "conv3_2_1_weight", 2ll * h.cfin, &err);
+  h.vb = off_of(n, "conv3_2_1_bias", 2, &err);
+  h.vgamma = off_of(n, "conv3_2_1_gamma", 2, &err);
+  h.vbeta = off_of(n, "conv3_2_1_beta", 2, &err);
+  h.vmean = off_of(n, "conv3_2_1_mean", 2, &err);
+  h.vvar = off_of(n, "conv3_2_1_var", 2, &err);
+  h.fcp_w = off_of(n, "fc_3_1_1_weight", 4ll * S * S, &err);
+  h.fcp_b = off_of(n, "fc_3_1_1_bias", S, &err);
+  h.fcv_w = off_of(n, "fc_3_2_1_weight", 2ll * S, &err);
+  h.fcv_b = off_of(n, "fc_3_2_1_bias", 1, &err);
+  if (!err.empty()) return bad(AP_ERR_BAD_ARG);
+  if ((rc = nalloc(e, n, (void**)&h.w1x1, 6ull * h.cfin * 4)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&h.b1x1, 6 * 4)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&h.fcpT, 4ull * S * S * 4)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&h.fcp_bias, (size_t)S * 4)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&h.fcv, 2ull * S * 4)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&h.fcv_bias, 4)) != AP_OK) return bad(rc);
+
+  // activation planes for max(G, 256) boards
+  n->bcap = e->geo.G > 256 ? e->geo.G : 256;
+  n->mpad = 2ll * NET_PAD_ROWS + (long long)n->bcap * NET_TILE_ROWS;
+  int maxc = 0;
+  for (auto& L : n->trunk) maxc = L.cout > maxc ? L.cout : maxc;
+  const int nbuf = (arch == AP_ARCH_RESNET) ? 3 : 2;
+  if ((rc = nalloc(e, n, (void**)&n->feat, (size_t)2 * n->mpad * 16)) != AP_OK) return bad(rc);
+  for (int i = 0; i < nbuf; ++i)
+    if ((rc = nalloc(e, n, (void**)&n->act[i], (size_t)(maxc / 8) * n->mpad * 16)) != AP_OK) return bad(rc);
+  n->bcap_ref = 128;
+  const size_t refb = (size_t)n->bcap_ref * 256 * S * 4;
+  if ((rc = nalloc(e, n, (void**)&n->ref_a, refb)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&n->ref_b, refb)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&n->ref_c, refb)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&n->ref_in, (size_t)e->geo.G * 9 * S * 4 > (size_t)n->bcap_ref * 9 * S * 4
+                                                   ? (size_t)e->geo.G * 9 * S * 4
+                                                   : (size_t)n->bcap_ref * 9 * S * 4)) != AP_OK)
+    return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&n->d_err, 4)) != AP_OK) return bad(rc);
+  if ((rc = conv_tc_configure(e)) != AP_OK) return bad(rc);
+  if (cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+    return bad(ap_fail(e, AP_ERR_CUDA, "cudaFuncSetAttribute(k_heads)"));
+  if ((rc = net_prep(e)) != AP_OK) return bad(rc);
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  return AP_OK;
+}
+
+extern "C" int ap_net_refresh(ap_engine* e) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
+  AP_TRY(net_prep(e));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  return AP_OK;
+}
+
+extern "C" int ap_net_weights_ptr(ap_engine* e, void** out_dev_ptr, int64_t* out_numel) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
+  *out_dev_ptr = e->net->master;
+  *out_numel = e->net->master_numel;
+  return AP_OK;
+}
+
+extern "C" int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, int64_t* out_offsets, int64_t* out_numels) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
+  int n = (int)e->net->names.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    out_names[i] = e->net->names[i].c_str();
+    out_offsets[i] = e->net->offsets[i];
+    out_numels[i] = e->net->numels[i];
+  }
+  return n;
+}
+
+// trunk + heads on the first nb boards of the feature planes -> probs/values (device)
+static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values) {
+  NetState* n = e->net;
+  for (auto& L : n->trunk) AP_TRY(conv_tc_launch(e, n, L, nb));
+  const int S = n->S;
+  size_t smem = (size_t)(6 * n->head.cfin + HB * 6 * S + 8) * 4;
+  k_heads<<<(nb + HB - 1) / HB, HEAD_THREADS, smem, e->stream>>>(n->act[n->final_buf], n->mpad, n->head.cfin, n->W, n->H,
+                                                                nb, n->head, d_probs, d_values);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+
+// fp32 path on dense NCHW states (device) for nb <= bcap_ref boards
+static int run_ref(ap_engine* e, const float* d_states, int nb, float* d_probs, float* d_values) {
+  NetState* n = e->net;
+  const int S = n->S, W = n->W, H = n->H;
+  float* bufs[3] = {n->ref_a, n->ref_b, n->ref_c};
+  auto conv = [&](const float* in, float* out, const float* resid, long long w, long long b, long long gamma,
+                  long long beta, long long mean, long long var, int fix_gamma, int relu, int cin, int cout, int ksz) {
+    long long tot = (long long)nb * cout * S;
+    k_ref_conv<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(in, out, resid, n->master, w, b, gamma, beta, mean,
+                                                                    var, fix_gamma, relu, nb, cin, cout, W, H, ksz);
+    e->launches++;
+  };
+  for (auto& L : n->trunk) {
+    const float* in = (L.in_buf < 0) ? d_states : bufs[L.in_buf];
+    conv(in, bufs[L.out_buf], L.resid_buf >= 0 ? bufs[L.resid_buf] : nullptr, L.w, L.b, L.gamma, L.beta, L.mean, L.var,
+         L.fix_gamma, L.relu, L.cin, L.cout, 3);
+  }
+  const float* fin = bufs[n->final_buf];
+  float* hp = bufs[(n->final_buf + 1) % 3];
+  float* hv = hp + (size_t)nb * 4 * S;
+  const HeadParams& h = n->head;
+  conv(fin, hp, nullptr, h.pw, h.pb, h.pgamma, h.pbeta, h.pmean, h.pvar, 1, 1, h.cfin, 4, 1);
+  conv(fin, hv, nullptr, h.vw, h.vb, h.vgamma, h.vbeta, h.vmean, h.vvar, 1, 1, h.cfin, 2, 1);
+  k_ref_heads<<<nb, HEAD_THREADS, 0, e->stream>>>(hp, hv, n->master, h.fcp_w, h.fcp_b, h.fcv_w, h.fcv_b, S, d_probs,
+                                                 d_values);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+
+int net_check_err(ap_engine* e) {
+  int h = 0;
+  AP_CUDA(e, cudaMemcpyAsync(&h, e->net->d_err, 4, cudaMemcpyDeviceToHost, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (h) {
+    cudaMemsetAsync(e->net->d_err, 0, 4, e->stream);
+    return ap_fail(e, AP_ERR_CUDA, "conv kernel: mbarrier wait timed out (pipeline protocol error)");
+  }
+  return AP_OK;
+}
+
+int net_emit_features_launch(ap_engine* e) {
+  NetState* n = e->net;
+  k_emit_features<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->leaves.rows, e->leaves.meta, e->geo.G, n->feat,
+                                                            n->mpad);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+
+// leaves of the last select -> e->d_probs / e->d_values
+int net_forward_leaves(ap_engine* e, int precise) {
+  if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
+  NetState* n = e->net;
+  const int G = e->geo.G;
+  if (!precise) {
+    AP_TRY(net_emit_features_launch(e));
+    return run_fast(e, G, e->d_probs, e->d_values);
+  }
+  launch_boards_features(e, e->leaves.rows, e->leaves.meta, nullptr, G, n->ref_in);
+  e->launches += 2;
+  for (int b0 = 0; b0 < G; b0 += n->bcap_ref) {
+    int nb = (G - b0 < n->bcap_ref) ? G - b0 : n->bcap_ref;
+    AP_TRY(run_ref(e, n->ref_in + (size_t)b0 * 9 * n->S, nb, e->d_probs + (size_t)b0 * n->S, e->d_values + b0));
+  }
+  return AP_OK;
+}
+
+extern "C" int ap_net_forward_leaves(ap_engine* e, int32_t precise, float* out_probs, float* out_values) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(net_forward_leaves(e, precise));
+  const size_t G = e->geo.G, S = e->geo.S;
+  if (out_probs) AP_CUDA(e, cudaMemcpyAsync(out_probs, e->d_probs, G * S * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (out_values) AP_CUDA(e, cudaMemcpyAsync(out_values, e->d_values, G * 4, cudaMemcpyDeviceToHost, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  return net_check_err(e);
+}
+
+// PolicyValueNet.policy_value(state_batch): host fp32 in, host fp32 out.
+// flags via B sign is avoided: precise path is selected with ap_net_forward_precise.
+static int forward_host(ap_engine* e, const float* states, int32_t B, float* out_probs, float* out_values, int precise) {
+  if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
+  if (!states || B <= 0 || !out_probs || !out_values) return ap_fail(e, AP_ERR_BAD_ARG, "bad argument");
+  NetState* n = e->net;
+  const int S = n->S;
+  const int chunk = precise ? n->bcap_ref : n->bcap;
+  const size_t per = (size_t)9 * S * 4;
+  AP_TRY(ap_stage(e, (size_t)chunk * per + (size_t)chunk * (S + 1) * 4, 0));
+  float* d_st = (float*)e->d_stage;
+  float* d_pr = (float*)((char*)e->d_stage + (size_t)chunk * per);
+  float* d_va = d_pr + (size_t)chunk * S;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    int nb = (B - b0 < chunk) ? B - b0 : chunk;
+    AP_CUDA(e, cudaMemcpyAsync(d_st, states + (size_t)b0 * 9 * S, (size_t)nb * per, cudaMemcpyHostToDevice, e->stream));
+    if (precise) {
+      AP_TRY(run_ref(e, d_st, nb, d_pr, d_va));
+    } else {
+      k_pack_states<<<(nb * S + 255) / 256, 256, 0, e->stream>>>(d_st, nb, n->W, n->H, n->feat, n->mpad);
+      AP_LAUNCH_CHECK(e);
+      AP_TRY(run_fast(e, nb, d_pr, d_va));
+    }
+    AP_CUDA(e, cudaMemcpyAsync(out_probs + (size_t)b0 * S, d_pr, (size_t)nb * S * 4, cudaMemcpyDeviceToHost, e->stream));
+    AP_CUDA(e, cudaMemcpyAsync(out_values + b0, d_va, (size_t)nb * 4, cudaMemcpyDeviceToHost, e->stream));
+    AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  }
+  return net_check_err(e);
+}
+
+extern "C" int ap_net_forward(ap_engine* e, const float* states, int32_t B, float* out_probs, float* out_values) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  return forward_host(e, states, B, out_probs, out_values, 0);
+}
+
+extern "C" int ap_net_forward_precise(ap_engine* e, const float* states, int32_t B, float* out_probs, float* out_values) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  return forward_host(e, states, B, out_probs, out_values, 1);
+}

@@ -1,0 +1,66 @@
+// Policy/value net on device (net.cu, conv_tc.cu).
+#pragma once
+#include <map>
+
+#include "ap_common.cuh"
+
+#define NET_PAD_ROWS 32    // zero rows before the first and after the last board
+#define NET_TILE_ROWS 256  // one board = 16x16 padded pixel rows (real pixels x<W, y<H; W,H <= 15)
+#define NET_SLAB_ROWS 290  // 256 + 17 halo rows either side
+
+struct ConvLayer {
+  int cin, cin_pad, cout;
+  int relu;
+  int in_buf, out_buf, resid_buf;  // activation buffer ids (resid_buf < 0: none); in_buf -1 = feature buffer
+  // offsets into the flat fp32 master buffer (-1 = absent)
+  long long w, b, gamma, beta, mean, var;
+  int fix_gamma;
+  // prepared (device)
+  __half* wimg = nullptr;  // [nkc][9][KC/8][cout][8]
+  float* scale = nullptr;  // [cout]
+  float* shift = nullptr;  // [cout]
+};
+
+struct HeadParams {
+  int cfin;  // channels of the trunk output
+  long long pw, pb, pgamma, pbeta, pmean, pvar;  // conv3_1_1 (4 ch)
+  long long vw, vb, vgamma, vbeta, vmean, vvar;  // conv3_2_1 (2 ch)
+  long long fcp_w, fcp_b, fcv_w, fcv_b;
+  float* w1x1 = nullptr;   // [6][cfin] scale-folded
+  float* b1x1 = nullptr;   // [6]
+  float* fcpT = nullptr;   // [4S][S] transposed, k index in tensor-pixel order
+  float* fcp_bias = nullptr;
+  float* fcv = nullptr;    // [2S]
+  float* fcv_bias = nullptr;
+};
+
+struct NetState {
+  int arch = 0, n_blocks = 0, n_filter = 0;
+  int W = 0, H = 0, S = 0;
+  int bcap = 0;         // boards the activation buffers hold
+  long long mpad = 0;   // rows per channel-group plane
+  std::vector<std::string> names;
+  std::vector<long long> offsets, numels;
+  std::map<std::string, int> index;
+  float* master = nullptr;
+  long long master_numel = 0;
+  std::vector<ConvLayer> trunk;
+  HeadParams head;
+  __half* feat = nullptr;      // [2][mpad][8]
+  __half* act[3] = {nullptr, nullptr, nullptr};  // [32][mpad][8]
+  int final_buf = 0;
+  // fp32 CUDA-core reference path
+  float* ref_a = nullptr;  // [bcap_ref][256][S]
+  float* ref_b = nullptr;
+  float* ref_c = nullptr;
+  float* ref_in = nullptr;  // [bcap_ref][9][S]
+  int bcap_ref = 0;
+  int sm_count = 148;
+  int* d_err = nullptr;
+  std::vector<void*> allocs;
+};
+
+// conv_tc.cu
+int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards);
+int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb);
+int conv_tc_configure(ap_engine* e);

@@ -1,0 +1,316 @@
+// Lock-step MCTS kernels for G concurrent games (one warp per game; re-root: one CTA per game).
+// Replaces reference MCTS._playout / get_move_probs / update_with_move (mcts_alphaZero.py:108-167).
+#include "kernels.h"
+#include "tree.cuh"
+
+#define SEL_WARPS 4
+
+__global__ void k_tree_reset_all(Geo geo, Pools pl) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= geo.G) return;
+  tree_write_root(pl, (size_t)g * geo.cap, g);
+}
+
+// MCTS._playout lines 113-121 + the game_end() of :126 for every game.
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, Leaves lv,
+         unsigned long long* stats) {
+  int lane = threadIdx.x & 31;
+  int g = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+  if (g >= geo.G) return;
+  size_t base = (size_t)g * geo.cap;
+  WBoard b = wb_load(rows, meta, g, lane);
+  int node = 0, depth = 0;
+  unsigned long long scanned = 0;
+  while (true) {
+    int cs = pl.child_start[base + node];
+    if (cs < 0) break;
+    int cc = pl.child_count[base + node];
+    int np = pl.N[base + node];
+    int bi = tree_select_child(pl, base, cs, cc, np, geo.c_puct, lane);
+    int mv = pl.move[base + cs + bi];
+    if (lane == 0) lv.path[(size_t)g * geo.S + depth] = (int16_t)mv;
+    wb_do_move(b, mv, geo.W, lane);
+    node = cs + bi;
+    ++depth;
+    scanned += cc;
+  }
+  int winner;
+  bool end = wb_game_end(b, geo.n_in_row, geo.S, winner);
+  wb_store(b, lv.rows, lv.meta, g, lane, 0);
+  if (lane == 0) {
+    lv.node[g] = node;
+    lv.terminal[g] = end ? 1 : 0;
+    lv.winner[g] = (int8_t)winner;
+    lv.depth[g] = depth;
+    atomicAdd(&stats[0], 1ull);
+    atomicAdd(&stats[1], scanned);
+    atomicAdd(&stats[3], (unsigned long long)(depth + 1));
+    if (end) atomicAdd(&stats[4], 1ull);
+  }
+}
+
+// MCTS._playout lines 126-139: expand (unless terminal), terminal value override, update_recursive(-v).
+// Children either from an explicit (acts, priors) list or, dense mode, = legal moves ascending.
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts, const int16_t* __restrict__ acts,
+                const double* __restrict__ pri64, const double* __restrict__ val64, const float* __restrict__ pri32,
+                const float* __restrict__ val32, int32_t* errflag, unsigned long long* stats) {
+  __shared__ int16_t s_list[SEL_WARPS][AP_MAX_S];
+  int lane = threadIdx.x & 31;
+  int w = threadIdx.x >> 5;
+  int g = blockIdx.x * SEL_WARPS + w;
+  if (g >= geo.G) return;
+  size_t base = (size_t)g * geo.cap;
+  int leaf = lv.node[g];
+  double v;
+  if (!lv.terminal[g]) {
+    int A;
+    const size_t row = (size_t)g * geo.S;
+    bool ok;
+    if (acts) {
+      A = counts[g];
+      for (int k = lane; k < A; k += 32) s_list[w][k] = acts[row + k];
+      __syncwarp();
+      ok = tree_expand(pl, base, g, geo.cap, leaf, A, s_list[w],
+                       [&](int k, int mv) { return pri64[row + k]; }, lane);
+    } else {
+      WBoard b = wb_load(lv.rows, lv.meta, g, lane);
+      A = wb_legal_list(b, geo.W, geo.H, lane, s_list[w]);
+      if (pri64)
+        ok = tree_expand(pl, base, g, geo.cap, leaf, A, s_list[w],
+                         [&](int k, int mv) { return pri64[row + mv]; }, lane);
+      else
+        ok = tree_expand(pl, base, g, geo.cap, leaf, A, s_list[w],
+                         [&](int k, int mv) { return (double)pri32[row + mv]; }, lane);
+    }
+    if (!ok && lane == 0) errflag[g] = AP_ERR_POOL_EXHAUSTED;
+    if (ok && lane == 0) atomicAdd(&stats[2], (unsigned long long)A);
+    v = val64 ? val64[g] : (double)val32[g];
+  } else {
+    int winner = lv.winner[g];
+    int cur = lv.meta[g].cur;
+    v = (winner == -1) ? 0.0 : ((winner == cur) ? 1.0 : -1.0);  // mcts_alphaZero.py:131-136
+  }
+  if (lane == 0) tree_backup(pl, base, leaf, -v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MCTS.update_with_move (mcts_alphaZero.py:159-167): re-root on a child keeping its subtree,
+// compacted breadth-first (children blocks stay contiguous and ordered) through a per-CTA
+// scratch slot, or a fresh TreeNode(None, 1.0).
+// ---------------------------------------------------------------------------------------------
+#define ADV_THREADS 256
+
+struct Scratch {
+  double* P;
+  double* Q;
+  int32_t* N;
+  int32_t* child_start;
+  int32_t* parent;
+  int32_t* src;
+  uint16_t* child_count;
+  int16_t* move;
+};
+
+__host__ __device__ inline size_t slot_bytes(int cap) { return (size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 2 + 2); }
+size_t scratch_bytes_per_slot(int cap) { return slot_bytes(cap); }
+
+__device__ __forceinline__ Scratch scratch_slot(void* p, int slot, int cap) {
+  char* b = (char*)p + (size_t)slot * slot_bytes(cap);
+  Scratch s;
+  s.P = (double*)b;            b += (size_t)cap * 8;
+  s.Q = (double*)b;            b += (size_t)cap * 8;
+  s.N = (int32_t*)b;           b += (size_t)cap * 4;
+  s.child_start = (int32_t*)b; b += (size_t)cap * 4;
+  s.parent = (int32_t*)b;      b += (size_t)cap * 4;
+  s.src = (int32_t*)b;         b += (size_t)cap * 4;
+  s.child_count = (uint16_t*)b; b += (size_t)cap * 2;
+  s.move = (int16_t*)b;
+  return s;
+}
+
+__global__ void __launch_bounds__(ADV_THREADS)
+k_advance(Geo geo, Pools pl, const int32_t* __restrict__ ids, const int32_t* __restrict__ moves, int n, void* scratch) {
+  __shared__ int s_scan[ADV_THREADS];
+  __shared__ int s_e_old[ADV_THREADS], s_e_off[ADV_THREADS], s_e_par[ADV_THREADS];
+  __shared__ int s_found, s_count, s_ne, s_total;
+  const int tid = threadIdx.x;
+  Scratch sc = scratch_slot(scratch, blockIdx.x, geo.cap);
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int g = ids[i];
+    const int mv = moves[i];
+    const size_t base = (size_t)g * geo.cap;
+    if (tid == 0) s_found = -1;
+    __syncthreads();
+    const int rcs = pl.child_start[base];
+    const int rcc = (rcs >= 0) ? pl.child_count[base] : 0;
+    if (mv >= 0)
+      for (int k = tid; k < rcc; k += ADV_THREADS)
+        if (pl.move[base + rcs + k] == mv) s_found = rcs + k;
+    __syncthreads();
+    const int r = s_found;
+    if (r < 0) {
+      if (tid == 0) tree_write_root(pl, base, g);
+      __syncthreads();
+      continue;
+    }
+    if (tid == 0) {
+      sc.P[0] = pl.P[base + r];
+      sc.Q[0] = pl.Q[base + r];
+      sc.N[0] = pl.N[base + r];
+      sc.child_start[0] = pl.child_start[base + r];
+      sc.child_count[0] = pl.child_count[base + r];
+      sc.move[0] = pl.move[base + r];
+      sc.parent[0] = -1;  // _root._parent = None
+      sc.src[0] = r;
+      s_count = 1;
+    }
+    __syncthreads();
+    int head = 0;
+    while (true) {
+      const int count = s_count;
+      if (head >= count) break;
+      const int chunk_end = min(head + ADV_THREADS, count);
+      const int me = head + tid;
+      int my_cc = 0, my_ocs = -1;
+      if (me < chunk_end) {
+        int o = sc.src[me];
+        my_ocs = pl.child_start[base + o];
+        my_cc = (my_ocs >= 0) ? (int)pl.child_count[base + o] : 0;
+      }
+      // inclusive scans of (children, has-children) packed in one int: cc < 2^9, count of entries < 2^9
+      int val = (my_cc << 10) | (my_cc > 0 ? 1 : 0);
+      s_scan[tid] = val;
+      __syncthreads();
+      for (int d = 1; d < ADV_THREADS; d <<= 1) {
+        int t = (tid >= d) ? s_scan[tid - d] : 0;
+        __syncthreads();
+        s_scan[tid] += t;
+        __syncthreads();
+      }
+      const int incl = s_scan[tid];
+      const int off = (incl >> 10) - my_cc;
+      const int rank = (incl & 1023) - (my_cc > 0 ? 1 : 0);
+      if (my_cc > 0) {
+        sc.child_start[me] = count + off;
+        s_e_old[rank] = my_ocs;
+        s_e_off[rank] = off;
+        s_e_par[rank] = me;
+      }
+      if (tid == ADV_THREADS - 1) {
+        s_total = incl >> 10;
+        s_ne = incl & 1023;
+      }
+      __syncthreads();
+      const int total = s_total, ne = s_ne;
+      for (int f = tid; f < total; f += ADV_THREADS) {
+        int lo = 0, hi = ne - 1;  // last entry with off <= f
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (s_e_off[mid] <= f) lo = mid; else hi = mid - 1;
+        }
+        const int o = s_e_old[lo] + (f - s_e_off[lo]);
+        const int d = count + f;
+        sc.P[d] = pl.P[base + o];
+        sc.Q[d] = pl.Q[base + o];
+        sc.N[d] = pl.N[base + o];
+        sc.child_start[d] = pl.child_start[base + o];  // fixed up when node d is processed
+        sc.child_count[d] = pl.child_count[base + o];
+        sc.move[d] = pl.move[base + o];
+        sc.parent[d] = s_e_par[lo];
+        sc.src[d] = o;
+      }
+      __syncthreads();
+      if (tid == 0) s_count = count + total;
+      head = chunk_end;
+      __syncthreads();
+    }
+    const int count = s_count;
+    for (int k = tid; k < count; k += ADV_THREADS) {
+      pl.P[base + k] = sc.P[k];
+      pl.Q[base + k] = sc.Q[k];
+      pl.N[base + k] = sc.N[k];
+      pl.child_start[base + k] = sc.child_start[k];
+      pl.child_count[base + k] = sc.child_count[k];
+      pl.move[base + k] = sc.move[k];
+      pl.parent[base + k] = sc.parent[k];
+    }
+    if (tid == 0) pl.alloc[g] = count;
+    __syncthreads();
+  }
+}
+
+// acts / visits / Q of the root's children in insertion order (mcts_alphaZero.py:152-154)
+__global__ void k_root(Geo geo, Pools pl, const int32_t* ids, int n, int32_t* out_count, int16_t* out_acts,
+                       int32_t* out_visits, double* out_q, int32_t* out_rootn) {
+  int lane = threadIdx.x & 31;
+  int i = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+  if (i >= n) return;
+  int g = ids ? ids[i] : i;
+  size_t base = (size_t)g * geo.cap;
+  int cs = pl.child_start[base];
+  int cc = (cs >= 0) ? pl.child_count[base] : 0;
+  for (int k = lane; k < geo.S; k += 32) {
+    bool in = k < cc;
+    out_acts[(size_t)i * geo.S + k] = in ? pl.move[base + cs + k] : (int16_t)-1;
+    out_visits[(size_t)i * geo.S + k] = in ? pl.N[base + cs + k] : 0;
+    if (out_q) out_q[(size_t)i * geo.S + k] = in ? pl.Q[base + cs + k] : 0.0;
+  }
+  if (lane == 0) {
+    out_count[i] = cc;
+    if (out_rootn) out_rootn[i] = pl.N[base];
+  }
+}
+
+// softmax(1/temp * log(visits + 1e-10)) with max subtraction (mcts_alphaZero.py:13-16,155),
+// scattered by move index.  fp64; transcendental ulps may differ from numpy's (the Python shim
+// therefore recomputes pi from the exact visit counts when bit-equality with numpy is wanted).
+__global__ void k_root_probs(Geo geo, Pools pl, double temp, double* out) {
+  int lane = threadIdx.x & 31;
+  int g = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+  if (g >= geo.G) return;
+  size_t base = (size_t)g * geo.cap;
+  int cs = pl.child_start[base];
+  int cc = (cs >= 0) ? pl.child_count[base] : 0;
+  for (int k = lane; k < geo.S; k += 32) out[(size_t)g * geo.S + k] = 0.0;
+  __syncwarp();
+  double inv = 1.0 / temp;
+  double mx = -CUDART_INF;
+  for (int k = lane; k < cc; k += 32) mx = fmax(mx, inv * log((double)pl.N[base + cs + k] + 1e-10));
+  for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(AP_FULL, mx, d));
+  double sum = 0.0;
+  for (int k = lane; k < cc; k += 32) sum += exp(inv * log((double)pl.N[base + cs + k] + 1e-10) - mx);
+  for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(AP_FULL, sum, d);
+  for (int k = lane; k < cc; k += 32) {
+    double p = exp(inv * log((double)pl.N[base + cs + k] + 1e-10) - mx) / sum;
+    out[(size_t)g * geo.S + pl.move[base + cs + k]] = p;
+  }
+}
+
+static inline dim3 sel_grid(int n) { return dim3((n + SEL_WARPS - 1) / SEL_WARPS); }
+
+void launch_tree_reset_all(ap_engine* e) {
+  k_tree_reset_all<<<(e->geo.G + 127) / 128, 128, 0, e->stream>>>(e->geo, e->pools);
+}
+void launch_select(ap_engine* e) {
+  k_select<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, e->leaves, e->stats);
+}
+void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* d_acts, const double* d_pri64,
+                          const double* d_val64, const float* d_pri32, const float* d_val32) {
+  k_expand_backup<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, e->leaves, d_counts, d_acts,
+                                                                       d_pri64, d_val64, d_pri32, d_val32, e->errflag,
+                                                                       e->stats);
+}
+void launch_advance(ap_engine* e, int n, const int32_t* d_moves) {
+  int grid = n < e->scratch_slots ? n : e->scratch_slots;
+  k_advance<<<grid, ADV_THREADS, 0, e->stream>>>(e->geo, e->pools, e->d_ids, d_moves, n, e->scratch);
+}
+void launch_root(ap_engine* e, const int32_t* d_ids, int n, int32_t* d_count, int16_t* d_acts, int32_t* d_visits,
+                 double* d_q, int32_t* d_rootn) {
+  k_root<<<sel_grid(n), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, d_ids, n, d_count, d_acts, d_visits, d_q,
+                                                       d_rootn);
+}
+void launch_root_probs(ap_engine* e, double temp, double* d_out) {
+  k_root_probs<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, temp, d_out);
+}

@@ -1,0 +1,155 @@
+/*
+ * alphapig_b200.h -- C ABI of libalphapig_b200.so (sm_100a only, no CPU fallback).
+ *
+ * The reference (anxingle/AlphaPig) has no FFI: its "operator API" for the
+ * self-play hot path is a set of duck-typed Python call signatures.  Each entry
+ * point below names the reference interface it replaces (file:line relative to
+ * the reference tree).  The Python shims in alphapig_b200/ bind these with
+ * ctypes and re-expose the reference's own class/method names; INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns int: AP_OK (0) or a negative ap_status; the text of
+ *    the last failure on a handle is ap_last_error(e).
+ *  - the library owns all device memory; host pointers are borrowed for the
+ *    duration of the call; calls are synchronous on return unless the name ends
+ *    in _async (then ap_sync()).
+ *  - not re-entrant per handle: one handle per GPU, one host thread per handle.
+ *  - game_ids == NULL means games 0..n-1.
+ *  - a move is h*width + w (reference game.py:46-56); players are 1 and 2.
+ *  - S = width*height <= 256, width,height <= 16.
+ */
+#ifndef ALPHAPIG_B200_H
+#define ALPHAPIG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ap_engine ap_engine;
+
+typedef enum {
+  AP_OK = 0,
+  AP_ERR_BAD_ARG = -1,        /* reference: Exception (game.py:36-38, 206-208)          */
+  AP_ERR_ILLEGAL_MOVE = -2,   /* reference: ValueError from list.remove (game.py:120)   */
+  AP_ERR_POOL_EXHAUSTED = -3, /* node pool of a game is full (no reference analogue)    */
+  AP_ERR_CUDA = -4,
+  AP_ERR_NO_NET = -5,         /* ap_search_run / ap_net_forward before ap_net_load      */
+  AP_ERR_BAD_HANDLE = -6
+} ap_status;
+
+typedef struct {
+  int32_t width, height, n_in_row; /* Board(width,height,n_in_row)      game.py:24-33   */
+  int32_t n_games;                 /* G concurrent games on this GPU                     */
+  int32_t node_capacity;           /* tree nodes per game (0 = pick from n_playout_hint) */
+  int32_t n_playout_hint;          /* MCTS(n_playout)                mcts_alphaZero.py:93 */
+  int32_t device;                  /* CUDA device ordinal                                */
+  int32_t flags;                   /* AP_FLAG_*                                          */
+  double  c_puct;                  /* MCTS(c_puct)                   mcts_alphaZero.py:93 */
+} ap_config;
+
+#define AP_FLAG_NONE 0
+#define AP_META_INTS 8 /* current_player, last_move, n_stones, hist0..3 (most recent first, -1 = none), start_player */
+
+/* ---- lifecycle ------------------------------------------------------------ */
+int ap_engine_create(const ap_config* cfg, ap_engine** out);
+int ap_engine_destroy(ap_engine* e);
+const char* ap_last_error(const ap_engine* e);
+const char* ap_version(void);
+int ap_sync(ap_engine* e);
+/* bytes of device memory held by the handle */
+int ap_engine_memory(const ap_engine* e, uint64_t* out_bytes);
+
+/* ---- boards: replaces game.Board (game.py:21-170) --------------------------- */
+/* Board.init_board(start_player)                                   game.py:35-44 */
+int ap_boards_reset(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* start_player);
+/* Board.do_move(move); out_status[i] = AP_OK / AP_ERR_ILLEGAL_MOVE (board untouched)  game.py:117-125 */
+int ap_boards_do_move(ap_engine* e, const int32_t* game_ids, const int32_t* moves, int32_t n, int32_t* out_status);
+/* Board.game_end() -> (end, winner in {1,2,-1})                  game.py:127-167 */
+int ap_boards_status(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* out_end, int8_t* out_winner);
+/* Board.availables as a bit mask, bit m of out_mask[i][m/32]          game.py:41 */
+int ap_boards_legal(ap_engine* e, const int32_t* game_ids, int32_t n, uint32_t* out_mask /* [n][8] */);
+/* Board.current_state() -> float32 [n][9][width][height], flip included  game.py:68-94 */
+int ap_boards_features(ap_engine* e, const int32_t* game_ids, int32_t n, float* out);
+/* Board.states / history / current_player / last_move                game.py:24-44 */
+int ap_boards_export(ap_engine* e, const int32_t* game_ids, int32_t n, int8_t* out_cells /* [n][S] 0,1,2 */,
+                     int32_t* out_meta /* [n][AP_META_INTS] */);
+int ap_boards_import(ap_engine* e, const int32_t* game_ids, int32_t n, const int8_t* cells, const int32_t* meta);
+
+/* ---- search: replaces mcts_alphaZero.MCTS / TreeNode (mcts_alphaZero.py:19-170) -- */
+/* One lock-step of MCTS._playout up to the evaluator call (:115-124): every game
+ * descends from its root by TreeNode.select (fp64 PUCT, first max) applying
+ * Board.do_move to a scratch copy, and stops at a leaf.
+ *   out_terminal[g] : 1 if game_end() at the leaf (evaluator result is discarded, :126-136)
+ *   out_depth[g]    : plies descended; out_path[g][0..depth) the moves taken        */
+int ap_search_select(ap_engine* e, uint8_t* out_terminal /* [G] or NULL */, int32_t* out_depth /* [G] or NULL */,
+                     int16_t* out_path /* [G][S] or NULL */);
+/* Leaf boards of the last ap_search_select, same layout as ap_boards_export / _features. */
+int ap_search_leaf_export(ap_engine* e, int8_t* out_cells, int32_t* out_meta);
+int ap_search_leaf_features(ap_engine* e, float* out /* [G][9][W][H] */);
+/* Second half of _playout (:126-139): TreeNode.expand with the evaluator's
+ * (action, prior) list in the given order (counts[g] entries of acts/priors row g),
+ * terminal override of the value, then update_recursive(-leaf_value).           */
+int ap_search_expand_backup(ap_engine* e, const int32_t* counts /* [G] */, const int16_t* acts /* [G][S] */,
+                            const double* priors /* [G][S] */, const double* values /* [G] */);
+/* Same, priors given densely by move index; children = legal moves ascending
+ * (what PolicyValueNet.policy_value_fn returns, policy_value_net_mxnet_simple.py:207-226). */
+int ap_search_expand_backup_dense(ap_engine* e, const float* priors /* [G][S] */, const float* values /* [G] */);
+/* MCTS.get_move_probs (:141-157) with the device net as policy_value_fn:
+ * n_playout x (select -> features -> net -> expand/backup), no host round trip. */
+int ap_search_run(ap_engine* e, int32_t n_playout);
+/* Root children in insertion order: acts, visit counts, Q; root's own N.   (:152-154) */
+int ap_search_root(ap_engine* e, const int32_t* game_ids, int32_t n, int32_t* out_count, int16_t* out_acts /* [n][S] */,
+                   int32_t* out_visits /* [n][S] */, double* out_q /* [n][S] or NULL */, int32_t* out_root_n /* [n] or NULL */);
+/* softmax(1/temp * log(visits + 1e-10)) scattered by move index, fp64        (:13-16,155) */
+int ap_search_root_probs(ap_engine* e, double temp, double* out /* [G][S] */);
+/* MCTS.update_with_move(move): re-root on the child (subtree kept) or fresh root (-1 / absent)  (:159-167) */
+int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves);
+/* counters since the last call: playouts, sum of children scanned, children written, path nodes, terminal leaves */
+int ap_search_stats(ap_engine* e, uint64_t* out5);
+
+/* ---- mcts_pure (mcts_pure.py:13-206) ---------------------------------------- */
+/* MCTS.get_move: n_playout x (_playout with uniform priors + random rollout) fully on
+ * device, one CTA per game; out_move[g] = first max by visits (:159-169).
+ * rollout_mode 0 = uniform random legal moves (rollout_policy_fn, :13-17),
+ *              1 = deterministic position hash in {-1,0,1} (bookkeeping-parity tests). */
+int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_mode, int32_t* out_move /* [G] */);
+/* _evaluate_rollout (:138-157) from every root board: winner-from-leaf-player value and plies played */
+int ap_rollout_eval(ap_engine* e, uint64_t seed, int8_t* out_value /* [G] */, int16_t* out_plies /* [G] */);
+/* the deterministic hash used by rollout_mode 1, for the host-side oracle */
+int ap_rollout_hash(ap_engine* e, int8_t* out_value /* [G] */);
+
+/* ---- policy/value net: replaces PolicyValueNet forward (policy_value_net_mxnet{,_simple}.py) -- */
+typedef struct {
+  const char* name;   /* reference parameter name, e.g. "conv1_weight", "bnA3_moving_var" */
+  const float* data;  /* host fp32, reference shape/layout (O,I,kh,kw) / (out,in)         */
+  int64_t numel;
+} ap_tensor;
+#define AP_ARCH_SIMPLE 0 /* policy_value_net_mxnet_simple.py:68-92 */
+#define AP_ARCH_RESNET 1 /* policy_value_net_mxnet.py:70-102       */
+/* set_params(arg_params, aux_params)                 policy_value_net_mxnet_simple.py:33-37 */
+int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t n_filter, const ap_tensor* tensors, int32_t n_tensors);
+/* PolicyValueNet.policy_value(state_batch): host fp32 states [B][9][H][W] -> probs [B][S], values [B]   (:178-188) */
+int ap_net_forward(ap_engine* e, const float* states, int32_t B, float* out_probs, float* out_values);
+/* same through the independent fp32 CUDA-core kernels (slow; on-device cross-check of the tensor-core path) */
+int ap_net_forward_precise(ap_engine* e, const float* states, int32_t B, float* out_probs, float* out_values);
+/* same on the engine's current leaf boards (device resident), results stay on device; precise=1 runs
+ * the fp32 CUDA-core reference kernels instead of the fp16 tensor-core path. */
+int ap_net_forward_leaves(ap_engine* e, int32_t precise, float* out_probs /* [G][S] or NULL */, float* out_values /* [G] or NULL */);
+/* device pointer + element count of the flat fp32 master weights (shared with the PyTorch
+ * train step and the post-train ncclBroadcast); call ap_net_refresh after writing to it. */
+int ap_net_weights_ptr(ap_engine* e, void** out_dev_ptr, int64_t* out_numel);
+int ap_net_refresh(ap_engine* e);
+/* name/offset table of the flat buffer: returns number of tensors; fills up to cap entries */
+int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, int64_t* out_offsets, int64_t* out_numels);
+/* timing of the last ap_search_run in ms (whole loop, net kernels only), measured with CUDA events on the engine stream */
+int ap_search_timing(ap_engine* e, float* out_total_ms, float* out_net_ms);
+/* number of kernels this library launched on the handle since creation */
+int ap_launch_count(const ap_engine* e, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALPHAPIG_B200_H */

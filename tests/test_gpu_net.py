@@ -1,0 +1,114 @@
+"""GPU: policy/value net forward through the C ABI vs the oracle fp32 restatement
+(oracle/net.py; parity unpinned at the MXNet boundary, see its docstring).
+Tolerance (north_star): |d log p| <= 1e-3 and |d v| <= 1e-3 absolute, identical weights."""
+import numpy as np
+import pytest
+
+from helpers import export_oboard, oboard_from, synth_position
+from oracle import net as onet
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _engine(**kw):
+    from alphapig_b200.engine import Engine
+    return Engine(**kw)
+
+
+def _states(W, n_states, seed0, max_pairs):
+    boards = [oboard_from(W, W, 5, synth_position(W, W, 5, seed0 + g, max_pairs)) for g in range(n_states)]
+    return boards, np.stack([np.ascontiguousarray(b.current_state()) for b in boards]).astype(np.float32)
+
+
+def _merged(arg, aux):
+    d = dict(arg)
+    d.update(aux)
+    return d
+
+
+@pytest.mark.parametrize("W,arch,nblk", [(15, "simple", 0), (8, "simple", 0), (15, "resnet", 3)])
+def test_net_forward_vs_oracle(W, arch, nblk):
+    arg, aux = onet.init_params(arch, W, W, seed=0, n_blocks=nblk)
+    boards, st = _states(W, 40, 1234, 31 if W == 15 else 10)
+    ref_p, ref_v = onet.forward(arg, aux, st, arch, n_blocks=nblk)
+    eng = _engine(width=W, height=W, n_in_row=5, n_games=8)
+    eng.net_load(arch, _merged(arg, aux), n_blocks=nblk)
+    # independent fp32 CUDA-core path: fp32 round-off only
+    pp, pv = eng.net_forward_precise(st)
+    assert np.abs(np.log(pp) - np.log(ref_p)).max() < 2e-5
+    assert np.abs(pv - ref_v).max() < 2e-5
+    # tensor-core path (fp16 operands, fp32 accumulate in TMEM)
+    p, v = eng.net_forward(st)
+    dlp = np.abs(np.log(p) - np.log(ref_p)).max()
+    dv = np.abs(v - ref_v).max()
+    print("arch %s W %d: max|dlogp| %.3e max|dv| %.3e" % (arch, W, dlp, dv))
+    assert np.allclose(p.sum(1), 1.0, atol=1e-5)
+    assert dlp <= TOL and dv <= TOL
+    eng.close()
+
+
+def test_net_on_leaf_boards_and_policy_value_fn_order():
+    """Features emitted on device from bitboards feed the net: same result as the host-state path,
+    and probabilities line up with move indices (policy_value_net_mxnet_simple.py:207-226)."""
+    W = 15
+    G = 24
+    arg, aux = onet.init_params("simple", W, W, seed=3)
+    eng = _engine(width=W, height=W, n_in_row=5, n_games=G)
+    eng.net_load("simple", _merged(arg, aux))
+    boards, st = _states(W, G, 77, 31)
+    cm = [export_oboard(b) for b in boards]
+    eng.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+    term, depth, _ = eng.search_select()  # fresh trees: every leaf is its root
+    assert not term.any() and not depth.any()
+    assert np.array_equal(eng.search_leaf_features(), st)
+    p_leaf, v_leaf = eng.net_forward_leaves(precise=False)
+    p_host, v_host = eng.net_forward(st)
+    assert np.array_equal(p_leaf, p_host) and np.array_equal(v_leaf, v_host[:, 0])
+    pp, pv = eng.net_forward_leaves(precise=True)
+    ref_p, ref_v = onet.forward(arg, aux, st, "simple")
+    assert np.abs(np.log(pp) - np.log(ref_p)).max() < 2e-5
+    assert np.abs(np.log(p_leaf) - np.log(ref_p)).max() <= TOL
+    assert np.abs(v_leaf - ref_v[:, 0]).max() <= TOL
+    eng.close()
+
+
+def test_net_weight_refresh_and_layout():
+    W = 8
+    arg, aux = onet.init_params("simple", W, W, seed=1)
+    eng = _engine(width=W, height=W, n_in_row=5, n_games=2)
+    eng.net_load("simple", _merged(arg, aux))
+    lay = eng.net_layout()
+    assert [n for n, _, _ in lay] == list(arg.keys()) + list(aux.keys())
+    assert all(sz == int(np.prod(_merged(arg, aux)[n].shape)) for n, _, sz in lay)
+    ptr, numel = eng.net_weights()
+    assert ptr and numel >= sum(sz for _, _, sz in lay)
+    eng.close()
+
+
+def test_search_run_device_net_matches_host_evaluator_path():
+    """ap_search_run (select -> features -> net -> expand/backup on device) must build exactly the
+    tree that the host path builds when fed the same fp32 priors/values."""
+    W = 8
+    G, n_playout = 6, 60
+    arg, aux = onet.init_params("simple", W, W, seed=5)
+    roots = [oboard_from(W, W, 5, synth_position(W, W, 5, 40 + g, 8)) for g in range(G)]
+    cm = [export_oboard(b) for b in roots]
+    a = _engine(width=W, height=W, n_in_row=5, n_games=G, n_playout=n_playout)
+    b = _engine(width=W, height=W, n_in_row=5, n_games=G, n_playout=n_playout)
+    for e in (a, b):
+        e.net_load("simple", _merged(arg, aux))
+        e.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+    a.search_run(n_playout)
+    for _ in range(n_playout):
+        b.search_select(want_path=False)
+        p, v = b.net_forward_leaves(precise=False)
+        b.search_expand_backup_dense(p, v)
+    ca, aa, va, qa, ra = a.search_root(want_q=True)
+    cb, ab, vb, qb, rb = b.search_root(want_q=True)
+    assert np.array_equal(ca, cb) and np.array_equal(aa, ab) and np.array_equal(va, vb)
+    assert np.array_equal(qa, qb) and np.array_equal(ra, rb)
+    assert ra.min() == n_playout
+    a.close()
+    b.close()

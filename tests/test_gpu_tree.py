@@ -1,0 +1,217 @@
+"""GPU: MCTS kernels (select / expand / backup / re-root) through the C ABI.
+Visit counts, Q, pi and chosen moves must be bit-exact vs the golden vectors written from the
+reference MCTS and vs the oracle, under injected deterministic evaluators, Dirichlet noise off."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from helpers import export_oboard, host_playouts, oboard_from, synth_position
+from oracle.evaluators import EVALUATORS, position_key
+from oracle.mcts import OMCTS, OPureMCTS, pure_policy_value_fn, softmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(**kw):
+    from alphapig_b200.engine import Engine
+    return Engine(**kw)
+
+
+def _root_arrays(eng, g=0):
+    count, acts, visits, q, rootn = eng.search_root(want_q=True)
+    S = eng.S
+    v = np.zeros(S, np.int32)
+    qq = np.zeros(S, np.float64)
+    a = acts[g, :count[g]]
+    v[a] = visits[g, :count[g]]
+    qq[a] = q[g, :count[g]]
+    return a, visits[g, :count[g]], v, qq, int(rootn[g])
+
+
+def test_tree_golden_cases():
+    metas = json.load(open(os.path.join(GOLDEN, "tree_cases.json")))
+    z = np.load(os.path.join(GOLDEN, "tree_cases.npz"))
+    for i, meta in enumerate(metas):
+        W, H, n = meta["W"], meta["H"], meta["n"]
+        eng = _engine(width=W, height=H, n_in_row=n, n_games=1, c_puct=meta["c_puct"], n_playout=meta["n_playout"])
+        root = oboard_from(W, H, n, meta["start_moves"])
+        c, m = export_oboard(root)
+        eng.boards_import(c[None], m[None])
+        for ply in range(meta["n_plies"]):
+            host_playouts(eng, [root], EVALUATORS[meta["evaluator"]], meta["n_playout"])
+            acts, vis_list, visits, q, rootn = _root_arrays(eng)
+            assert np.array_equal(visits, z["c%d_visits" % i][ply]), "case %d ply %d visits" % (i, ply)
+            assert np.array_equal(q, z["c%d_q" % i][ply]), "case %d ply %d Q" % (i, ply)
+            assert rootn == z["c%d_root_n" % i][ply]
+            # acts are the legal moves ascending = child insertion order
+            assert list(acts) == list(root.availables)
+            pi = np.zeros(W * H)
+            pi[acts] = softmax(1.0 / meta["temp"] * np.log(np.array(vis_list) + 1e-10))
+            assert np.array_equal(pi, z["c%d_pi" % i][ply])
+            dev_pi = eng.search_root_probs(meta["temp"])[0]
+            assert np.allclose(dev_pi, pi, rtol=0, atol=1e-12)
+            move = int(z["c%d_chosen" % i][ply])
+            eng.search_advance([move if meta["selfplay"] else -1])
+            eng.boards_do_move([move])
+            root.do_move(move)
+        eng.close()
+
+
+def test_tree_lockstep_many_games_vs_oracle():
+    """32 different 8x8 positions searched concurrently, 3 plies with tree reuse, vs the oracle MCTS."""
+    W = H = 8
+    G, n_playout, plies = 32, 150, 3
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, c_puct=5, n_playout=n_playout)
+    roots, oracles = [], []
+    for g in range(G):
+        roots.append(oboard_from(W, H, 5, synth_position(W, H, 5, 900 + g, 10)))
+        oracles.append(OMCTS(EVALUATORS["e2" if g % 2 else "e3"], 5, n_playout))
+    cm = [export_oboard(b) for b in roots]
+    eng.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+    for ply in range(plies):
+        # drive the engine with a per-game evaluator
+        for _ in range(n_playout):
+            term, depth, path = eng.search_select()
+            counts = np.zeros(G, np.int32)
+            acts = np.zeros((G, W * H), np.int16)
+            pri = np.zeros((G, W * H))
+            vals = np.zeros(G)
+            for g in range(G):
+                leaf = roots[g].clone()
+                for m in path[g, :depth[g]]:
+                    leaf.do_move(int(m))
+                ap, v = EVALUATORS["e2" if g % 2 else "e3"](leaf)
+                ap = list(ap)
+                counts[g] = len(ap)
+                acts[g, :len(ap)] = [a for a, _ in ap]
+                pri[g, :len(ap)] = [p for _, p in ap]
+                vals[g] = v
+            eng.search_expand_backup(counts, acts, pri, vals)
+        count, acts, visits, q, rootn = eng.search_root(want_q=True)
+        moves = np.zeros(G, np.int32)
+        for g in range(G):
+            o_acts, o_probs = oracles[g].get_move_probs(roots[g], 1.0)
+            o_vis = [nd.N for nd in oracles[g].root.children.values()]
+            o_q = [float(nd.Q) for nd in oracles[g].root.children.values()]
+            assert list(acts[g, :count[g]]) == list(o_acts)
+            assert list(visits[g, :count[g]]) == o_vis, "game %d ply %d" % (g, ply)
+            assert list(q[g, :count[g]]) == o_q
+            assert rootn[g] == oracles[g].root.N
+            # most-visited child (first max) as the move; every 4th game resets its tree instead of reusing it
+            moves[g] = o_acts[int(np.argmax(o_vis))]
+        adv = np.where(np.arange(G) % 4 == 3, -1, moves).astype(np.int32)
+        eng.search_advance(adv)
+        eng.boards_do_move(moves)
+        for g in range(G):
+            oracles[g].update_with_move(int(adv[g]))
+            roots[g].do_move(int(moves[g]))
+    eng.close()
+
+
+def test_pure_bookkeeping_golden():
+    """mcts_pure tree bookkeeping (uniform priors, injected rollout result) vs the golden vectors
+    written from the reference mcts_pure.MCTS."""
+    metas = json.load(open(os.path.join(GOLDEN, "pure_cases.json")))
+    z = np.load(os.path.join(GOLDEN, "pure_cases.npz"))
+
+    def policy(leaf):
+        ap, _ = pure_policy_value_fn(leaf)
+        # value the reference would back up: _evaluate_rollout with the random play replaced by a hash
+        return ap, float(int(position_key(leaf) % 3) - 1)
+
+    for i, meta in enumerate(metas):
+        W, H, n = meta["W"], meta["H"], meta["n"]
+        eng = _engine(width=W, height=H, n_in_row=n, n_games=1, c_puct=meta["c_puct"], n_playout=meta["n_playout"])
+        root = oboard_from(W, H, n, meta["start_moves"])
+        c, m = export_oboard(root)
+        eng.boards_import(c[None], m[None])
+        host_playouts(eng, [root], policy, meta["n_playout"])
+        acts, vis_list, visits, q, rootn = _root_arrays(eng)
+        assert np.array_equal(visits, z["p%d_visits" % i])
+        assert np.array_equal(q, z["p%d_q" % i])
+        assert rootn == meta["root_n"]
+        assert int(acts[int(np.argmax(vis_list))]) == meta["move"]
+        eng.close()
+
+
+def test_pure_fused_kernel_vs_oracle():
+    """The fused one-CTA-per-game mcts_pure kernel with the deterministic rollout hash must give the
+    oracle's visit counts and move exactly."""
+    from alphapig_b200.engine import rollout_hash_host
+    W = H = 8
+    G, n_playout = 16, 600
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, c_puct=5, n_playout=n_playout)
+    roots = [oboard_from(W, H, 5, synth_position(W, H, 5, 500 + g, 10)) for g in range(G)]
+    cm = [export_oboard(b) for b in roots]
+    eng.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+
+    def rollout(state):
+        player = state.get_current_player()
+        end, winner = state.game_end()
+        if not end:
+            c, _ = export_oboard(state)
+            return rollout_hash_host(c, state.current_player, W, H)
+        if winner == -1:
+            return 0
+        return 1 if winner == player else -1
+
+    # the device hash agrees with its host twin on the roots
+    dev = eng.rollout_hash()
+    assert list(dev) == [rollout(b) for b in roots]
+    moves = eng.pure_run(n_playout, seed=1, rollout_mode=1)
+    count, acts, visits, q, rootn = eng.search_root(want_q=True)
+    for g in range(G):
+        o = OPureMCTS(pure_policy_value_fn, 5, n_playout, rollout_fn=rollout)
+        mv = o.get_move(roots[g])
+        assert mv == moves[g]
+        assert list(visits[g, :count[g]]) == [nd.N for nd in o.root.children.values()]
+        assert list(q[g, :count[g]]) == [float(nd.Q) for nd in o.root.children.values()]
+    eng.close()
+
+
+def test_rollout_distribution():
+    """Random rollouts (uniform legal moves) from the empty 15x15 board: game length and result
+    distribution vs the oracle's rollout (mcts_pure.py:138-157) on >= 10^4 rollouts."""
+    from oracle.board import OBoard
+    W = H = 15
+    G = 16384
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, n_playout=1, node_capacity=4)
+    v, plies = eng.rollout_eval(seed=123)
+    assert plies.min() >= 9 and plies.max() <= 225
+    # oracle sample (slow): 200 rollouts
+    rs = np.random.RandomState(5)
+    o_plies, o_v = [], []
+    for _ in range(200):
+        b = OBoard(W, H, 5)
+        b.init_board(0)
+        while not b.game_end()[0]:
+            b.do_move(int(b.availables[rs.randint(len(b.availables))]))
+        o_plies.append(len(b.states))
+        w = b.game_end()[1]
+        o_v.append(0 if w == -1 else (1 if w == 1 else -1))
+    # means agree within 4 standard errors of the small oracle sample
+    se = np.std(o_plies) / np.sqrt(len(o_plies))
+    assert abs(plies.mean() - np.mean(o_plies)) < 4 * se + 0.5
+    se_v = np.std(o_v) / np.sqrt(len(o_v))
+    assert abs(v.mean() - np.mean(o_v)) < 4 * se_v + 0.02
+    # first player (to move at the root) wins slightly more often than the second; ties are rare
+    assert (v == 0).mean() < 0.02
+    # different seeds give different streams, same seed is reproducible
+    v2, p2 = eng.rollout_eval(seed=123)
+    assert np.array_equal(plies, p2) and np.array_equal(v, v2)
+    v3, p3 = eng.rollout_eval(seed=124)
+    assert not np.array_equal(plies, p3)
+    eng.close()
+
+
+def test_pool_exhaustion_is_reported():
+    from alphapig_b200._lib import EngineError
+    eng = _engine(width=8, height=8, n_in_row=5, n_games=1, node_capacity=100)
+    root = oboard_from(8, 8, 5, [])
+    with pytest.raises(EngineError) as ei:
+        host_playouts(eng, [root], EVALUATORS["e1"], 5)
+    assert ei.value.code == -3
+    eng.close()
