@@ -401,7 +401,7 @@ int ap_search_root(ap_engine* e, const int32_t* game_ids, int32_t n, int32_t* ou
   AP_TRY(ap_ids(e, game_ids, n));
   const size_t S = e->geo.S, nn = n;
   size_t o_cnt = 0, o_rn = o_cnt + ((nn * 4 + 15) & ~15ull), o_acts = o_rn + ((nn * 4 + 15) & ~15ull),
-         o_vis = o_acts + ((nn * S * 2 + 15) & ~15ull), o_q = o_vis + nn * S * 4, tot = o_q + nn * S * 8;
+         o_vis = o_acts + ((nn * S * 2 + 15) & ~15ull), o_q = o_vis + ((nn * S * 4 + 15) & ~15ull), tot = o_q + nn * S * 8;
   AP_TRY(ap_stage(e, tot, 0));
   char* d = (char*)e->d_stage;
   launch_root(e, e->d_ids, n, (int32_t*)(d + o_cnt), (int16_t*)(d + o_acts), (int32_t*)(d + o_vis),

@@ -27,6 +27,20 @@ def _service(width, height, n_in_row):
     return eng
 
 
+def export_board_state(board):
+    """Any object with the reference Board protocol -> (cells int8[S], meta int32[8]) in the C-ABI format."""
+    S = board.width * board.height
+    cells = np.zeros(S, np.int8)
+    for m, p in board.states.items():
+        if 0 <= m < S:
+            cells[m] = p
+    hist = [m for m, _ in board.history[-1:-5:-1]]
+    hist += [-1] * (4 - len(hist))
+    meta = np.array([board.current_player, board.last_move, len(board.states)] + hist +
+                    [getattr(board, '_start', 0)], np.int32)
+    return cells, meta
+
+
 class Board(object):
     """board for the game (reference game.py:21-170)"""
 
@@ -80,16 +94,7 @@ class Board(object):
     # ---- device side ------------------------------------------------------
     def export_state(self):
         """(cells int8[S], meta int32[8]) in the C-ABI board format."""
-        S = self.width * self.height
-        cells = np.zeros(S, np.int8)
-        for m, p in self.states.items():
-            if 0 <= m < S:
-                cells[m] = p
-        hist = [m for m, _ in self.history[-1:-5:-1]]
-        hist += [-1] * (4 - len(hist))
-        meta = np.array([self.current_player, self.last_move, len(self.states)] + hist +
-                        [getattr(self, '_start', 0)], np.int32)
-        return cells, meta
+        return export_board_state(self)
 
     def _upload(self):
         eng = _service(self.width, self.height, self.n_in_row)
