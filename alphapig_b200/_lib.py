@@ -69,6 +69,7 @@ SIGNATURES = {
     "ap_net_refresh": (C.c_int, [_P]),
     "ap_net_layout": (C.c_int, [_P, _I, _P, _P, _P]),
     "ap_search_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "ap_search_profile": (C.c_int, [_P, _I, _P, _I]),
     "ap_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
 }
 

@@ -86,6 +86,11 @@ struct ap_engine {
   float* d_values = nullptr;  // [G]
   float last_total_ms = 0.f, last_net_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // optional per-phase timing of ap_search_run (ap_search_profile): events after every phase of every lock-step
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<float> prof_ms;  // accumulated ms per phase of the last ap_search_run
+  int prof_cursor = 0;
 };
 
 #define AP_CUDA(e, call)                                                                  \
@@ -118,3 +123,5 @@ int net_destroy(ap_engine* e);
 int net_forward_leaves(ap_engine* e, int precise);
 int net_emit_features_launch(ap_engine* e);
 int net_check_err(ap_engine* e);
+int net_phase_count(ap_engine* e);
+void prof_mark(ap_engine* e);

@@ -80,6 +80,11 @@ static int check_errflags(ap_engine* e) {
   return AP_OK;
 }
 
+void prof_mark(ap_engine* e) {
+  if (!e->profile) return;
+  if ((size_t)e->prof_cursor < e->prof_events.size()) cudaEventRecord(e->prof_events[e->prof_cursor++], e->stream);
+}
+
 extern "C" {
 
 const char* ap_version(void) { return "alphapig_b200 0.1 (sm_100a)"; }
@@ -179,6 +184,7 @@ int ap_engine_destroy(ap_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_stage) cudaFree(e->d_stage);
   if (e->h_stage) cudaFreeHost(e->h_stage);
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->stream);
@@ -373,19 +379,51 @@ int ap_search_expand_backup_dense(ap_engine* e, const float* priors, const float
 int ap_search_run(ap_engine* e, int32_t n_playout) {
   if (!e) return AP_ERR_BAD_HANDLE;
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "ap_search_run: no net loaded (ap_net_load)");
+  // phases per lock-step: select, features, one per trunk conv, heads, expand/backup
+  const int phases = net_phase_count(e) + 2;
+  if (e->profile) {
+    size_t need = (size_t)n_playout * phases + 1;
+    while (e->prof_events.size() < need) {
+      cudaEvent_t ev;
+      AP_CUDA(e, cudaEventCreate(&ev));
+      e->prof_events.push_back(ev);
+    }
+    e->prof_cursor = 0;
+  }
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  prof_mark(e);
   for (int it = 0; it < n_playout; ++it) {
     launch_select(e);
     AP_LAUNCH_CHECK(e);
+    prof_mark(e);
     AP_TRY(net_forward_leaves(e, 0));
     launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values);
     AP_LAUNCH_CHECK(e);
+    prof_mark(e);
   }
   AP_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   AP_CUDA(e, cudaStreamSynchronize(e->stream));
   cudaEventElapsedTime(&e->last_total_ms, e->ev0, e->ev1);
+  if (e->profile) {
+    e->prof_ms.assign(phases, 0.f);
+    for (int it = 0; it < n_playout; ++it)
+      for (int ph = 0; ph < phases; ++ph) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->prof_events[(size_t)it * phases + ph], e->prof_events[(size_t)it * phases + ph + 1]);
+        e->prof_ms[ph] += ms;
+      }
+  }
   AP_TRY(net_check_err(e));
   return check_errflags(e);
+}
+
+int ap_search_profile(ap_engine* e, int32_t enable, float* out_ms, int32_t cap) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  e->profile = enable;
+  int n = (int)e->prof_ms.size();
+  if (out_ms)
+    for (int i = 0; i < n && i < cap; ++i) out_ms[i] = e->prof_ms[i];
+  return n;
 }
 
 int ap_search_timing(ap_engine* e, float* out_total_ms, float* out_net_ms) {

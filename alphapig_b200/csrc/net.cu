@@ -519,9 +519,14 @@ extern "C" int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, 
 }
 
 // trunk + heads on the first nb boards of the feature planes -> probs/values (device)
+int net_phase_count(ap_engine* e) { return e->net ? (int)e->net->trunk.size() + 2 : 0; }
+
 static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values) {
   NetState* n = e->net;
-  for (auto& L : n->trunk) AP_TRY(conv_tc_launch(e, n, L, nb));
+  for (auto& L : n->trunk) {
+    AP_TRY(conv_tc_launch(e, n, L, nb));
+    prof_mark(e);
+  }
   const int S = n->S;
   size_t smem = (size_t)(6 * n->head.cfin + HB * 6 * S + 8) * 4;
   k_heads<<<(nb + HB - 1) / HB, HEAD_THREADS, smem, e->stream>>>(n->act[n->final_buf], n->mpad, n->head.cfin, n->W, n->H,
@@ -585,7 +590,10 @@ int net_forward_leaves(ap_engine* e, int precise) {
   const int G = e->geo.G;
   if (!precise) {
     AP_TRY(net_emit_features_launch(e));
-    return run_fast(e, G, e->d_probs, e->d_values);
+    prof_mark(e);
+    AP_TRY(run_fast(e, G, e->d_probs, e->d_values));
+    prof_mark(e);
+    return AP_OK;
   }
   launch_boards_features(e, e->leaves.rows, e->leaves.meta, nullptr, G, n->ref_in);
   e->launches += 2;

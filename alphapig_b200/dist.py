@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing: one process per GPU, games sharded per rank, ZERO traffic during search.
+
+Only two exchanges exist, both outside the search loop, both ``torch.distributed``
+(NCCL over NVLink on GPUs; gloo in the CPU tests):
+
+* ``broadcast_weights``  - after ``train_step`` on the trainer rank, ONE broadcast of the flat fp32
+  master-weight buffer (5.4 MB simple / 12.7 MB res-10) straight from/into the engine-owned device
+  memory, then a local rebuild of the fp16 operand images.  The reference's analogue is the
+  in-process train->predict parameter copy (policy_value_net_mxnet.py:295-297).
+* ``gather_replay``      - finished-game records as fixed-size packed rows
+  (bit-packed 9xS planes | pi fp32[S] | z fp32) gathered to every rank (or used on the trainer);
+  the reference's analogue is ``data_buffer.extend`` (train_mxnet.py:153,180).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_games(n_total, rank, world):
+    """Contiguous block of games for this rank: (first, count)."""
+    base, rem = divmod(n_total, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def broadcast_weights(net, src=0):
+    flat, _ = net._views()
+    dist.broadcast(flat, src=src)
+    net.sync_replicas()
+
+
+def record_width(S):
+    """bytes per packed record: ceil(9S/8) state bits padded to 4, S fp32 pi, 1 fp32 z"""
+    return ((9 * S + 7) // 8 + 3) // 4 * 4 + 4 * S + 4
+
+
+def pack_records(states_bits, pis, zs, S):
+    """states_bits uint8[n][ceil(9S/8)], pis float[n][S], zs float[n] -> uint8[n][record_width]"""
+    n = len(zs)
+    w = record_width(S)
+    sb = (9 * S + 7) // 8
+    out = np.zeros((n, w), np.uint8)
+    if n:
+        out[:, :sb] = states_bits
+        off = w - 4 * S - 4
+        out[:, off:off + 4 * S] = np.ascontiguousarray(pis, dtype=np.float32).view(np.uint8).reshape(n, 4 * S)
+        out[:, off + 4 * S:] = np.ascontiguousarray(zs, dtype=np.float32).reshape(n, 1).view(np.uint8)
+    return out
+
+
+def unpack_records(packed, S, width, height):
+    """-> (states float32[n][9][width][height], pis float32[n][S], zs float32[n])"""
+    n = packed.shape[0]
+    w = record_width(S)
+    sb = (9 * S + 7) // 8
+    off = w - 4 * S - 4
+    bits = np.unpackbits(np.ascontiguousarray(packed[:, :sb]), axis=1)[:, :9 * S]
+    states = bits.reshape(n, 9, width, height).astype(np.float32)
+    pis = np.ascontiguousarray(packed[:, off:off + 4 * S]).view(np.float32).reshape(n, S)
+    zs = np.ascontiguousarray(packed[:, off + 4 * S:]).view(np.float32).reshape(n)
+    return states, pis, zs
+
+
+def gather_replay(packed, device=None):
+    """All-gather variable numbers of packed records from every rank.  Returns uint8[N_total][width]."""
+    world = dist.get_world_size()
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend() == "nccl" else torch.device("cpu"))
+    n = torch.tensor([packed.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    width = packed.shape[1]
+    mx = max(counts + [1])
+    buf = torch.zeros((mx, width), dtype=torch.uint8, device=dev)
+    if packed.shape[0]:
+        buf[:packed.shape[0]] = torch.from_numpy(packed).to(dev)
+    outs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return np.concatenate([o[:c].cpu().numpy() for o, c in zip(outs, counts)], axis=0)

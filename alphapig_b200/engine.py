@@ -177,6 +177,13 @@ class Engine(object):
         self._check(self.lib.ap_search_timing(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def search_profile(self, enable=True):
+        """Toggle per-phase timing; returns the per-phase ms of the last search_run
+        (select, features, trunk convs..., heads, expand/backup)."""
+        out = np.zeros(64, np.float32)
+        n = self.lib.ap_search_profile(self.h, int(bool(enable)), _ptr(out), 64)
+        return out[:max(n, 0)].copy()
+
     def search_root(self, game_ids=None, want_q=False):
         ids = _ids(game_ids)
         n = self._n(ids)

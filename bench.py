@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the self-play hot path (BASELINE.json metric: MCTS playouts/s, 15x15, 400 playouts).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one full MCTS move search (n_playout lock-steps of select -> features -> net ->
+expand/backup) for every one of the G concurrent games of a rank, from the synthetic positions of
+SURVEY 8(d), on a fresh tree.  Prints ONE JSON line (see the prompt's contract / DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 15
+N_IN_ROW = 5
+N_PLAYOUT = 400
+C_PUCT = 5
+G_PER_GPU = 4096
+ARCH = "simple"
+METRIC = "mcts_playouts_per_s"
+UNIT = "playouts/s"
+
+
+def workload_name(G):
+    return ("15x15 five-in-a-row batched MCTS move search, policy_value_net_mxnet_simple (6-conv net), "
+            "%d concurrent games per GPU, n_playout=%d, c_puct=%d" % (G, N_PLAYOUT, C_PUCT))
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic inputs: k = 2*randint(0,31) uniformly random legal plies per game
+# ------------------------------------------------------------------------------------------
+def draw_position(rs):
+    S = W * H
+    k = 2 * rs.randint(0, 31)
+    perm = rs.permutation(S)[:k]
+    cells = np.zeros(S, np.int8)
+    cells[perm[0::2]] = 1
+    cells[perm[1::2]] = 2
+    hist = [int(m) for m in perm[::-1][:4]] + [-1] * max(0, 4 - k)
+    meta = np.array([1, int(perm[-1]) if k else -1, k] + hist[:4] + [0], np.int32)
+    return cells, meta
+
+
+def synthetic_positions(eng, G, seed0=1234):
+    """A position whose random play already ended the game is redrawn (checked on the device)."""
+    S = W * H
+    rss = [np.random.RandomState(seed0 + g) for g in range(G)]
+    cells = np.zeros((G, S), np.int8)
+    meta = np.zeros((G, 8), np.int32)
+    todo = np.arange(G)
+    while len(todo):
+        for g in todo:
+            cells[g], meta[g] = draw_position(rss[g])
+        eng.boards_import(cells[todo], meta[todo], todo.astype(np.int32))
+        end, _ = eng.boards_status(todo.astype(np.int32))
+        todo = todo[end]
+    return cells, meta
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One process: oracle MCTS + oracle net (PyTorch-CPU fp32, 1 thread), n_moves move searches."""
+    seed, n_moves, n_playout, params = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle.board import OBoard
+    from oracle.mcts import OMCTSPlayer
+    from oracle.net import ONet
+    net = ONet(W, H, arch=ARCH, params=params)
+    rs = np.random.RandomState(seed)
+    b = OBoard(W, H, N_IN_ROW)
+    b.init_board(0)
+    for m in rs.permutation(W * H)[:2 * rs.randint(0, 8)]:
+        b.do_move(int(m))
+    player = OMCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=n_playout, is_selfplay=1)
+    np.random.seed(seed)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(n_moves):
+        if b.game_end()[0]:
+            break
+        mv = player.get_action(b, temp=1.0)
+        b.do_move(int(mv))
+        done += 1
+    return done * n_playout, time.perf_counter() - t0
+
+
+def cpu_baseline_single(params, n_moves=2):
+    """Faithful single-process reference-style path: Python tree + batch-1 net forward with all
+    host threads given to the net (what the reference's MXNet-CPU engine would use)."""
+    import torch
+    from oracle.board import OBoard
+    from oracle.mcts import OMCTSPlayer
+    from oracle.net import ONet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    net = ONet(W, H, arch=ARCH, params=params)
+    b = OBoard(W, H, N_IN_ROW)
+    b.init_board(0)
+    player = OMCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=N_PLAYOUT, is_selfplay=1)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    for _ in range(n_moves):
+        b.do_move(int(player.get_action(b, temp=1.0)))
+    dt = time.perf_counter() - t0
+    return {"value": n_moves * N_PLAYOUT / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "oracle port (Python MCTS + PyTorch-CPU fp32 stand-in for MXNet, batch 1): 1 game, %d moves x %d "
+                      "playouts on 15x15, %.1f s" % (n_moves, N_PLAYOUT, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: MXNet absent, reference Python cannot
+    travel to the GPU box) saturating the host: one process per core, one game each."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from alphapig_b200.params import init_params
+    arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
+    params = (arg, aux)
+    procs = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    per_step = []
+    with ctx.Pool(procs) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(1000 * step + p, 1, N_PLAYOUT, params) for p in range(procs)])
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                per_step.append((sum(r[0] for r in res), dt))
+    playouts = sum(p for p, _ in per_step)
+    secs = sum(t for _, t in per_step)
+    value = playouts / secs
+    sample = ("%d processes x 1 game x 1 move x %d playouts per step (host-saturated, 1 torch thread each)"
+              % (procs, N_PLAYOUT))
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(1, len(per_step)),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(G_PER_GPU), "l2": "n/a (CPU)"},
+           "moves_per_s": value / N_PLAYOUT,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from alphapig_b200.params import flop_per_leaf, init_params
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    from alphapig_b200 import dist as apdist
+
+    G = args.games
+    arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
+    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=local)
+    cap = N_PLAYOUT * W * H + 2
+    eng = net.search_engine(n_in_row=N_IN_ROW, c_puct=C_PUCT, n_playout=N_PLAYOUT, n_games=G, node_capacity=cap)
+    if world > 1:
+        # the one collective of the path: post-train weight broadcast from the trainer rank (NCCL over NVLink)
+        apdist.broadcast_weights(net, src=0)
+    cells, meta = synthetic_positions(eng, G, seed0=1234 + rank * G)
+    pin_cells = torch.from_numpy(cells).pin_memory().numpy()
+    pin_meta = torch.from_numpy(meta).pin_memory().numpy()
+    eng.boards_import(pin_cells, pin_meta)
+    eng.search_profile(True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        eng.search_advance(-1)
+        eng.search_run(N_PLAYOUT)
+        return eng.search_timing()[0]
+
+    for _ in range(args.warmup):
+        resident_step()
+    eng.search_stats()
+    clocks = ClockSampler(local)
+    sync_all()
+    clocks.start()
+    l0 = eng.launch_count()
+    dev_ms, phase_ms = 0.0, None
+    for _ in range(args.steps):
+        dev_ms += resident_step()
+        ph = eng.search_profile(True)
+        phase_ms = ph if phase_ms is None else phase_ms + ph
+    sync_all()
+    launches = eng.launch_count() - l0
+    clk = clocks.stop()
+    stats = eng.search_stats()
+
+    # end to end through the public API with host buffers: H2D positions, search, D2H visit counts
+    e2e_s = 0.0
+    sync_all()
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        eng.boards_import(pin_cells, pin_meta)
+        eng.search_advance(-1)
+        eng.search_run(N_PLAYOUT)
+        count, acts, visits, _, rootn = eng.search_root()
+        if i >= args.warmup:
+            e2e_s += time.perf_counter() - t0
+    assert int(rootn.min()) == N_PLAYOUT and int(visits.sum()) == G * (N_PLAYOUT - 1)
+    sync_all()
+    h2d = pin_cells.nbytes + pin_meta.nbytes + 4 * G * 3
+    d2h = count.nbytes + acts.nbytes + visits.nbytes + rootn.nbytes
+
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_max = float(t[0]), float(t[1])
+    total_playouts = world * G * N_PLAYOUT * args.steps
+    value = total_playouts / (dev_ms_max / 1000.0)
+    e2e_value = total_playouts / e2e_max
+
+    if rank == 0:
+        peaks = {}
+        pk_src = "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            pk_src = "measured (sustained)"
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        n_conv = len(phase_ms) - 4
+        conv_ms = float(phase_ms[2:2 + n_conv].sum())
+        conv_flop_leaf = 2 * sum(9 * ci * co for ci, co in ((9, 64), (64, 64), (64, 128), (128, 128), (128, 256),
+                                                          (256, 256))) * W * H
+        lockstep = args.steps * N_PLAYOUT
+        conv_launches = lockstep * n_conv
+        achieved = conv_flop_leaf * G * lockstep / (conv_ms / 1000.0) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_conv3x3_tc (6 launches per lock-step, all trunk layers)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_source": pk_src, "traffic": None,
+                "avg_launch_ms": conv_ms / conv_launches,
+                "algorithmic_flop_per_launch_avg": conv_flop_leaf * G / n_conv,
+                "phase_ms_per_lockstep": {"select": float(phase_ms[0]) / lockstep, "features": float(phase_ms[1]) / lockstep,
+                                          "trunk_convs": [float(x) / lockstep for x in phase_ms[2:2 + n_conv]],
+                                          "heads": float(phase_ms[2 + n_conv]) / lockstep,
+                                          "expand_backup": float(phase_ms[3 + n_conv]) / lockstep}}
+        # tree kernels against the HBM roofline (they are latency bound; reported for honesty)
+        tree_bytes = 20 * stats["children_scanned"] + 20 * stats["children_written"] + 24 * stats["path_nodes"] + \
+            128 * stats["playouts"]
+        tree_ms = float(phase_ms[0] + phase_ms[3 + n_conv])
+        roof["tree_kernels"] = {"bound": "hbm", "achieved_gbs": tree_bytes / (tree_ms / 1000.0) / 1e9,
+                                "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)),
+                                "frac": tree_bytes / (tree_ms / 1000.0) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
+                                "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
+                                "terminal_leaf_frac": stats["terminal_leaves"] / max(1, stats["playouts"])}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline_single((arg, aux), n_moves=2)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+               "config": {"workload": workload_name(G), "games_per_gpu": G, "n_playout": N_PLAYOUT,
+                          "net": "policy_value_net_mxnet_simple", "flop_per_leaf": flop_per_leaf(ARCH, W, H),
+                          "arithmetic": "fp16 operands, fp32 TMEM accumulate (net); fp64 (tree)",
+                          "l2": "working set (node pools + activation planes, >10 GB) is larger than L2; no flush needed",
+                          "timing": "CUDA events on the engine stream around each ap_search_run, summed over steps, max over ranks"},
+               "moves_per_s": value / N_PLAYOUT,
+               "clocks": clk,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "timing": "wall clock around boards_import + search_advance + search_run + search_root"},
+               "gpu_launches": int(launches),
+               "roofline": roof}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--games", type=int, default=G_PER_GPU, help="concurrent games per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -146,6 +146,9 @@ int ap_net_refresh(ap_engine* e);
 int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, int64_t* out_offsets, int64_t* out_numels);
 /* timing of the last ap_search_run in ms (whole loop, net kernels only), measured with CUDA events on the engine stream */
 int ap_search_timing(ap_engine* e, float* out_total_ms, float* out_net_ms);
+/* enable/disable per-phase CUDA-event timing of ap_search_run and fetch the accumulated ms of the last run;
+ * phases per lock-step: select, features, one per trunk conv layer, heads, expand/backup.  Returns #phases. */
+int ap_search_profile(ap_engine* e, int32_t enable, float* out_ms, int32_t cap);
 /* number of kernels this library launched on the handle since creation */
 int ap_launch_count(const ap_engine* e, uint64_t* out);
 
