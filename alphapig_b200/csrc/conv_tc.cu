@@ -15,6 +15,7 @@
 //   B operand    = per (K-chunk, tap) image [KC/8][Cout][8] prepared by net.cu.
 #include "kernels.h"
 #include "net.h"
+#include "ptx.cuh"
 
 namespace {
 
@@ -22,91 +23,18 @@ constexpr int kThreads = 256;
 constexpr int kSlabRows = NET_SLAB_ROWS;
 constexpr int kSlabGroupBytes = kSlabRows * 16;  // one 8-channel group of the slab
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU box.  ~2 s at 2 GHz.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* errflag) {
-  if (mbar_try(bar, parity)) return true;
-  long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      atomicExch(errflag, 1);
-      return false;
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, no swizzle: rows 16 B apart inside an 8-row core matrix, SBO between 8-row groups,
-// LBO between the two 16-byte K halves of one K=16 MMA.  version=1 (Blackwell), layout_type=0.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 struct ConvParams {
   const __half* in;
   __half* out;
   const __half* resid;
   const __half* wimg;
-  const float* scale;
-  const float* shift;
+  const float* bias;  // folded BN shift; the BN scale is folded into the fp16 weights
   long long mpad;
   int cout, kc, nkc, relu;
   int n_tiles, W, H;
   int nb;         // B-tile ring depth
-  int tmem_cols;  // power of two >= 2*cout
+  int tmem_cols;  // power of two >= acc_stages*2*cout
+  int acc_stages; // 2 when two tiles' accumulators fit in TMEM (cout <= 128): epilogue overlaps the next tile
   int* errflag;
 };
 
@@ -125,9 +53,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
   uint64_t* slab_empty = bars + 2;
   uint64_t* b_full = bars + 4;
   uint64_t* b_empty = bars + 4 + p.nb;
-  uint64_t* tmem_full = bars + 4 + 2 * p.nb;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
+  uint64_t* tmem_full = bars + 4 + 2 * p.nb;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* s_bias = (float*)(tmem_slot + 4);     // [cout]
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -138,8 +67,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
       mbar_init(smem_u32(&b_full[i]), 1);
       mbar_init(smem_u32(&b_empty[i]), 1);
     }
-    mbar_init(smem_u32(tmem_full), 1);
-    mbar_init(smem_u32(tmem_empty), 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full[i]), 1);
+      mbar_init(smem_u32(&tmem_empty[i]), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -148,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -183,12 +115,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | ((uint32_t)(p.cout >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t b_lbo = (uint32_t)p.cout * 16;
-    int sl = 0, slph = 0, bs = 0, bph = 0, tph = 0;
+    int sl = 0, slph = 0, bs = 0, bph = 0, as = 0, aph = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
-      ok = mbar_wait(smem_u32(tmem_empty), tph ^ 1, p.errflag);
+      ok = mbar_wait(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag);
       if (!ok) break;
       tc_fence_after();
+      const uint32_t acc_base = tmem_base + (uint32_t)(as * 2 * p.cout);
       for (int kc = 0; kc < p.nkc && ok; ++kc) {
         ok = mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag);
         if (!ok) break;
@@ -204,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
             for (int j = 0; j < (p.kc >> 4); ++j) {
               const uint64_t ad = make_desc(arow + (uint32_t)(2 * j) * kSlabGroupBytes, kSlabGroupBytes, 128);
               const uint64_t bd = make_desc(bbase + (uint32_t)(2 * j) * b_lbo, b_lbo, 128);
-              tc_mma_f16(tmem_base + (uint32_t)(half * p.cout), ad, bd, idesc, (kc | tap | j) != 0);
+              tc_mma_f16(acc_base + (uint32_t)(half * p.cout), ad, bd, idesc, (kc | tap | j) != 0);
             }
           }
           tc_commit(smem_u32(&b_empty[bs]));
@@ -213,34 +146,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
         tc_commit(smem_u32(&slab_empty[sl]));
         if (++sl == 2) { sl = 0; slph ^= 1; }
       }
-      tc_commit(smem_u32(tmem_full));
-      tph ^= 1;
+      tc_commit(smem_u32(&tmem_full[as]));
+      if (++as == p.acc_stages) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> regs -> scale/shift (+resid) -> ReLU -> fp16 -> global =====
     const int q = warp & 3;
-    int tph = 0;
+    int as = 0, aph = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
-      ok = mbar_wait(smem_u32(tmem_full), tph, p.errflag);
+      ok = mbar_wait(smem_u32(&tmem_full[as]), aph, p.errflag);
       ok = __all_sync(AP_FULL, ok);
       if (!ok) break;
       tc_fence_after();
+      const uint32_t acc_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * p.cout);
       for (int half = 0; half < 2; ++half) {
         const int r = half * 128 + q * 32 + lane;
         const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
         const long long grow = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + r;
         for (int c0 = 0; c0 < p.cout; c0 += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * p.cout + c0), v);
+          tmem_ld32(acc_base + (uint32_t)(half * p.cout + c0), v);
           tmem_ld_wait();
 #pragma unroll
           for (int gi = 0; gi < 4; ++gi) {
             const int c = c0 + gi * 8;
             const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
             float f[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[gi * 8 + k]), p.scale[c + k], p.shift[c + k]);
+            f[0] = __uint_as_float(v[gi * 8 + 0]) + b0.x;
+            f[1] = __uint_as_float(v[gi * 8 + 1]) + b0.y;
+            f[2] = __uint_as_float(v[gi * 8 + 2]) + b0.z;
+            f[3] = __uint_as_float(v[gi * 8 + 3]) + b0.w;
+            f[4] = __uint_as_float(v[gi * 8 + 4]) + b1.x;
+            f[5] = __uint_as_float(v[gi * 8 + 5]) + b1.y;
+            f[6] = __uint_as_float(v[gi * 8 + 6]) + b1.z;
+            f[7] = __uint_as_float(v[gi * 8 + 7]) + b1.w;
             if (p.resid) {
               uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
               const __half2* rh = reinterpret_cast<const __half2*>(&rv);
@@ -268,8 +210,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(tmem_empty));
-      tph ^= 1;
+      mbar_arrive(smem_u32(&tmem_empty[as]));
+      if (++as == p.acc_stages) { as = 0; aph ^= 1; }
     }
   }
   tc_fence_before();
@@ -288,11 +230,11 @@ static int smem_layout(const ConvLayer& L, int* nb_out) {
   const int slab = (((kc >> 3) * kSlabGroupBytes) + 127) & ~127;
   const int btile = kc * L.cout * 2;
   const int budget = 220 * 1024;
-  int nb = (budget - 2 * slab - 512) / btile;
+  int nb = (budget - 2 * slab - 2048) / btile;
   if (nb > 9) nb = 9;
   if (nb < 2) nb = 2;
   *nb_out = nb;
-  return 2 * slab + nb * btile + (4 + 2 * nb + 2) * 8 + 16;
+  return 2 * slab + nb * btile + (4 + 2 * nb + 4) * 8 + 16 + L.cout * 4;
 }
 
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb) { return smem_layout(L, out_nb); }
@@ -309,8 +251,7 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards) 
   p.out = n->act[L.out_buf];
   p.resid = (L.resid_buf >= 0) ? n->act[L.resid_buf] : nullptr;
   p.wimg = L.wimg;
-  p.scale = L.scale;
-  p.shift = L.shift;
+  p.bias = L.shift;
   p.mpad = n->mpad;
   p.cout = L.cout;
   p.kc = L.cin_pad < 64 ? L.cin_pad : 64;
@@ -319,8 +260,9 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards) 
   p.n_tiles = n_boards;
   p.W = n->W;
   p.H = n->H;
+  p.acc_stages = (4 * L.cout <= 512) ? 2 : 1;
   int cols = 32;
-  while (cols < 2 * L.cout) cols <<= 1;
+  while (cols < p.acc_stages * 2 * L.cout) cols <<= 1;
   p.tmem_cols = cols;
   p.errflag = n->d_err;
   int nb;

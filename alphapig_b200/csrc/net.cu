@@ -8,6 +8,7 @@
 #include "board.cuh"
 #include "kernels.h"
 #include "net.h"
+#include "ptx.cuh"
 
 #define BN_EPS 1e-3f
 
@@ -35,7 +36,9 @@ __global__ void k_prep_conv(const float* __restrict__ master, long long w, long 
     int tap = (int)(r % 9);
     int kcI = (int)(r / 9);
     int k = kcI * kc + j * 8 + e;
-    float v = (k < cin) ? master[w + ((long long)n * cin + k) * 9 + tap] : 0.f;
+    float sc = 1.f / sqrtf(master[var + n] + BN_EPS);
+    if (!fix_gamma) sc *= master[gamma + n];
+    float v = (k < cin) ? master[w + ((long long)n * cin + k) * 9 + tap] * sc : 0.f;  // BN scale folded in fp32
     wimg[i] = __float2half_rn(v);
   }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < cout; n += gridDim.x * blockDim.x) {
@@ -62,10 +65,10 @@ __global__ void k_prep_heads(const float* __restrict__ master, HeadParams h, int
     h.b1x1[o] = (master[(pol ? h.pb : h.vb) + oo] - master[(pol ? h.pmean : h.vmean) + oo]) * s +
                 master[(pol ? h.pbeta : h.vbeta) + oo];
   }
-  for (long long i = tid; i < (long long)4 * S * S; i += nth) {
-    int s = (int)(i % S);
-    long long k = i / S;
-    h.fcpT[i] = master[h.fcp_w + (long long)s * 4 * S + k];
+  for (long long i = tid; i < (long long)4 * S * 232; i += nth) {  // [4S][FC_NPAD], zero padded columns
+    int s = (int)(i % 232);
+    long long k = i / 232;
+    h.fcpT[i] = (s < S) ? master[h.fcp_w + (long long)s * 4 * S + k] : 0.f;
   }
   for (int i = tid; i < S; i += nth) h.fcp_bias[i] = master[h.fcp_b + i];
   for (int i = tid; i < 2 * S; i += nth) h.fcv[i] = master[h.fcv_w + i];
@@ -133,8 +136,11 @@ __global__ void k_pack_states(const float* __restrict__ st, int nb, int W, int H
 // heads: 1x1 convs (+BN+ReLU) -> FC(4S->S)+softmax, FC(2S->1)+tanh   (..._simple.py:78-90)
 // HB boards per CTA so every FC weight read from L2 feeds HB FMAs.
 // ------------------------------------------------------------------------------------------
-#define HB 4
 #define HEAD_THREADS 256
+#define FC_HB 16         // boards per CTA of the FC kernel
+#define FC_THREADS 128   // 4 board groups (4 boards each) x 29 output groups (8 outputs each) = 116 active
+#define FC_KC 36         // K chunk of the policy FC staged in shared memory (4S = 900 = 25 * 36 on 15x15)
+#define FC_NPAD 232      // S <= 225 outputs padded to 29 groups of 8
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -150,70 +156,149 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
-__global__ void __launch_bounds__(HEAD_THREADS)
-k_heads(const __half* __restrict__ act, long long mpad, int cfin, int W, int H, int nb, HeadParams h,
-        float* __restrict__ probs, float* __restrict__ values) {
-  extern __shared__ float sh[];
-  const int S = W * H;
-  float* s_w = sh;                 // [6][cfin]
-  float* s_h = s_w + 6 * cfin;     // [HB][6][S]
-  float* s_red = s_h + HB * 6 * S; // [8]
-  const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * HB;
-  for (int i = tid; i < 6 * cfin; i += HEAD_THREADS) s_w[i] = h.w1x1[i];
+// (A) the two 1x1 convs (+ folded BN + ReLU): one CTA per board, thread = padded pixel row.
+// HBM-bound: reads the trunk output once (coalesced 512 B per warp per channel group).
+// hbuf [nb][6][S] fp32, pixel index p = y*W + x in tensor coordinates (Flatten order C,H,W).
+__global__ void __launch_bounds__(256)
+k_head_conv(const __half* __restrict__ act, long long mpad, int cfin, int W, int H, HeadParams h,
+            float* __restrict__ hbuf) {
+  extern __shared__ __align__(16) float sh[];
+  float* s_w = sh;  // [6][cfin]
+  const int tid = threadIdx.x, b = blockIdx.x, S = W * H;
+  for (int i = tid; i < 6 * cfin; i += 256) s_w[i] = h.w1x1[i];
   __syncthreads();
-  // phase 1: 1x1 convs
-  for (int idx = tid; idx < HB * S; idx += HEAD_THREADS) {
-    int bi = idx / S, p = idx % S;
-    int b = b0 + bi;
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (b < nb) {
-      int y = p / W, x = p % W;
-      long long row = NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + y * 16 + x;
-      for (int cg = 0; cg < (cfin >> 3); ++cg) {
-        uint4 v = *reinterpret_cast<const uint4*>(act + ((long long)cg * mpad + row) * 8);
-        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+  const int y = tid >> 4, x = tid & 15;
+  if (x >= W || y >= H) return;
+  const long long row = NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + tid;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int ncg = cfin >> 3;
+  for (int cg0 = 0; cg0 < ncg; cg0 += 8) {
+    uint4 v[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float2 t = __half22float2(hv[k]);
-          int c = cg * 8 + 2 * k;
+    for (int u = 0; u < 8; ++u)
+      v[u] = *reinterpret_cast<const uint4*>(act + ((long long)(cg0 + u) * mpad + row) * 8);
 #pragma unroll
-          for (int o = 0; o < 6; ++o) acc[o] = fmaf(t.x, s_w[o * cfin + c], fmaf(t.y, s_w[o * cfin + c + 1], acc[o]));
+    for (int u = 0; u < 8; ++u) {
+      const __half2* hv = reinterpret_cast<const __half2*>(&v[u]);
+      float a[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 t = __half22float2(hv[k]);
+        a[2 * k] = t.x;
+        a[2 * k + 1] = t.y;
+      }
+#pragma unroll
+      for (int o = 0; o < 6; ++o) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + o * cfin + (cg0 + u) * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_w + o * cfin + (cg0 + u) * 8 + 4);
+        acc[o] = fmaf(a[0], w0.x, fmaf(a[1], w0.y, fmaf(a[2], w0.z, fmaf(a[3], w0.w, acc[o]))));
+        acc[o] = fmaf(a[4], w1.x, fmaf(a[5], w1.y, fmaf(a[6], w1.z, fmaf(a[7], w1.w, acc[o]))));
+      }
+    }
+  }
+  const int p = y * W + x;
+#pragma unroll
+  for (int o = 0; o < 6; ++o) hbuf[((size_t)b * 6 + o) * S + p] = fmaxf(acc[o] + h.b1x1[o], 0.f);
+}
+
+// (B) FC(4S->S)+softmax and FC(2S->1)+tanh for FC_HB boards per CTA.  The policy FC is a
+// register-tiled fp32 GEMM [16 x 4S] x [4S x S] (thread = 4 boards x 8 outputs); the weight matrix
+// streams through shared memory in K chunks by TMA bulk copies, double buffered on two mbarriers.
+// smem: s_h [FC_HB][6S] | s_wc [2][FC_KC][FC_NPAD] | s_lg [FC_HB][FC_NPAD] | 2 mbarriers
+__global__ void __launch_bounds__(FC_THREADS)
+k_head_fc(const float* __restrict__ hbuf, int S, int nb, HeadParams h, float* __restrict__ probs,
+          float* __restrict__ values) {
+  extern __shared__ __align__(128) float sh[];
+  const int K = 4 * S;
+  float* s_wc = sh;                                   // 2 * FC_KC * FC_NPAD (16-byte aligned for TMA)
+  float* s_h = s_wc + 2 * FC_KC * FC_NPAD;            // FC_HB * 6S
+  float* s_lg = s_h + FC_HB * 6 * S;                  // FC_HB * FC_NPAD
+  uint64_t* bars = (uint64_t*)(s_lg + FC_HB * FC_NPAD);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b0 = blockIdx.x * FC_HB;
+  const int nchunks = (K + FC_KC - 1) / FC_KC;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int c) {  // one thread: TMA bulk copy of weight chunk c into buffer c&1
+    const int kn = min(FC_KC, K - c * FC_KC);
+    const uint32_t bytes = (uint32_t)kn * FC_NPAD * 4;
+    const uint32_t bar = smem_u32(&bars[c & 1]);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(s_wc + (c & 1) * FC_KC * FC_NPAD), h.fcpT + (size_t)c * FC_KC * FC_NPAD, bytes, bar);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (nchunks > 1) issue(1);
+  }
+  for (int i = tid; i < FC_HB * 6 * S; i += FC_THREADS) {
+    const int bi = i / (6 * S);
+    s_h[i] = (b0 + bi < nb) ? hbuf[(size_t)b0 * 6 * S + i] : 0.f;
+  }
+  __syncthreads();
+  const int og = tid % (FC_NPAD / 8), bg = tid / (FC_NPAD / 8);
+  const bool fc_thread = bg < FC_HB / 4;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const int kn = min(FC_KC, K - c * FC_KC);
+    // parity of the (c/2)-th completion of barrier c&1
+    while (!mbar_try(smem_u32(&bars[c & 1]), (c >> 1) & 1)) {
+    }
+    if (fc_thread) {
+      const float* wc = s_wc + (c & 1) * FC_KC * FC_NPAD + og * 8;
+      const float* hp = s_h + (4 * bg) * 6 * S + c * FC_KC;
+#pragma unroll 4
+      for (int kk = 0; kk < kn; ++kk) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wc + kk * FC_NPAD);
+        const float4 w1 = *reinterpret_cast<const float4*>(wc + kk * FC_NPAD + 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xv = hp[i * 6 * S + kk];
+          acc[i][0] = fmaf(xv, w0.x, acc[i][0]); acc[i][1] = fmaf(xv, w0.y, acc[i][1]);
+          acc[i][2] = fmaf(xv, w0.z, acc[i][2]); acc[i][3] = fmaf(xv, w0.w, acc[i][3]);
+          acc[i][4] = fmaf(xv, w1.x, acc[i][4]); acc[i][5] = fmaf(xv, w1.y, acc[i][5]);
+          acc[i][6] = fmaf(xv, w1.z, acc[i][6]); acc[i][7] = fmaf(xv, w1.w, acc[i][7]);
         }
       }
     }
+    __syncthreads();  // buffer c&1 fully consumed
+    if (tid == 0 && c + 2 < nchunks) issue(c + 2);
+  }
+  if (fc_thread) {
 #pragma unroll
-    for (int o = 0; o < 6; ++o) s_h[(bi * 6 + o) * S + p] = fmaxf(acc[o] + h.b1x1[o], 0.f);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int sidx = og * 8 + j;
+        s_lg[(4 * bg + i) * FC_NPAD + sidx] = (sidx < S) ? acc[i][j] + h.fcp_bias[sidx] : -INFINITY;
+      }
   }
   __syncthreads();
-  // phase 2: policy FC, thread = output move index
-  float logit[HB];
-#pragma unroll
-  for (int bi = 0; bi < HB; ++bi) logit[bi] = 0.f;
-  if (tid < S) {
-    for (int k = 0; k < 4 * S; ++k) {
-      float w = h.fcpT[(long long)k * S + tid];
-#pragma unroll
-      for (int bi = 0; bi < HB; ++bi) logit[bi] = fmaf(w, s_h[bi * 6 * S + k], logit[bi]);
-    }
-    float bb = h.fcp_bias[tid];
-#pragma unroll
-    for (int bi = 0; bi < HB; ++bi) logit[bi] += bb;
-  }
-#pragma unroll
-  for (int bi = 0; bi < HB; ++bi) {
-    float mx = block_reduce(tid < S ? logit[bi] : -INFINITY, s_red, true);
-    float ex = tid < S ? expf(logit[bi] - mx) : 0.f;
-    float sum = block_reduce(ex, s_red, false);
-    if (tid < S && b0 + bi < nb) probs[(size_t)(b0 + bi) * S + tid] = ex / sum;
-  }
-  // phase 3: value FC
-#pragma unroll
-  for (int bi = 0; bi < HB; ++bi) {
+  // softmax (SoftmaxActivation over the S logits) and the value head: one warp per board
+  for (int bi = warp; bi < FC_HB; bi += FC_THREADS / 32) {
+    const int b = b0 + bi;
+    if (b >= nb) continue;
+    const float* lg = s_lg + bi * FC_NPAD;
+    float mx = -INFINITY;
+    for (int i = lane; i < S; i += 32) mx = fmaxf(mx, lg[i]);
+    for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(AP_FULL, mx, d));
+    float sum = 0.f;
+    for (int i = lane; i < S; i += 32) sum += expf(lg[i] - mx);
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(AP_FULL, sum, d);
+    const float inv = 1.f / sum;
+    for (int i = lane; i < S; i += 32) probs[(size_t)b * S + i] = expf(lg[i] - mx) * inv;
     float part = 0.f;
-    for (int k = tid; k < 2 * S; k += HEAD_THREADS) part = fmaf(h.fcv[k], s_h[(bi * 6 + 4) * S + k], part);
-    float tot = block_reduce(part, s_red, false);
-    if (tid == 0 && b0 + bi < nb) values[b0 + bi] = tanhf(tot + h.fcv_bias[0]);
+    const float* hv = s_h + (bi * 6 + 4) * S;
+    for (int k = lane; k < 2 * S; k += 32) part = fmaf(h.fcv[k], hv[k], part);
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(AP_FULL, part, d);
+    if (lane == 0) values[b] = tanhf(part + h.fcv_bias[0]);
   }
 }
 
@@ -458,7 +543,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if (!err.empty()) return bad(AP_ERR_BAD_ARG);
   if ((rc = nalloc(e, n, (void**)&h.w1x1, 6ull * h.cfin * 4)) != AP_OK) return bad(rc);
   if ((rc = nalloc(e, n, (void**)&h.b1x1, 6 * 4)) != AP_OK) return bad(rc);
-  if ((rc = nalloc(e, n, (void**)&h.fcpT, 4ull * S * S * 4)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&h.fcpT, 4ull * S * 232 * 4)) != AP_OK) return bad(rc);
   if ((rc = nalloc(e, n, (void**)&h.fcp_bias, (size_t)S * 4)) != AP_OK) return bad(rc);
   if ((rc = nalloc(e, n, (void**)&h.fcv, 2ull * S * 4)) != AP_OK) return bad(rc);
   if ((rc = nalloc(e, n, (void**)&h.fcv_bias, 4)) != AP_OK) return bad(rc);
@@ -483,8 +568,9 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
     return bad(rc);
   if ((rc = nalloc(e, n, (void**)&n->d_err, 4)) != AP_OK) return bad(rc);
   if ((rc = conv_tc_configure(e)) != AP_OK) return bad(rc);
-  if (cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
-    return bad(ap_fail(e, AP_ERR_CUDA, "cudaFuncSetAttribute(k_heads)"));
+  if (cudaFuncSetAttribute(k_head_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    return bad(ap_fail(e, AP_ERR_CUDA, "cudaFuncSetAttribute(k_head_fc)"));
+  if ((rc = nalloc(e, n, (void**)&n->hbuf, (size_t)n->bcap * 6 * S * 4)) != AP_OK) return bad(rc);
   if ((rc = net_prep(e)) != AP_OK) return bad(rc);
   AP_CUDA(e, cudaStreamSynchronize(e->stream));
   return AP_OK;
@@ -528,9 +614,11 @@ static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values) {
     prof_mark(e);
   }
   const int S = n->S;
-  size_t smem = (size_t)(6 * n->head.cfin + HB * 6 * S + 8) * 4;
-  k_heads<<<(nb + HB - 1) / HB, HEAD_THREADS, smem, e->stream>>>(n->act[n->final_buf], n->mpad, n->head.cfin, n->W, n->H,
-                                                                nb, n->head, d_probs, d_values);
+  k_head_conv<<<nb, 256, (size_t)6 * n->head.cfin * 4, e->stream>>>(n->act[n->final_buf], n->mpad, n->head.cfin, n->W,
+                                                                  n->H, n->head, n->hbuf);
+  AP_LAUNCH_CHECK(e);
+  size_t smem = (size_t)(2 * FC_KC * FC_NPAD + FC_HB * 6 * S + FC_HB * FC_NPAD) * 4 + 16;
+  k_head_fc<<<(nb + FC_HB - 1) / FC_HB, FC_THREADS, smem, e->stream>>>(n->hbuf, S, nb, n->head, d_probs, d_values);
   AP_LAUNCH_CHECK(e);
   return AP_OK;
 }

@@ -28,7 +28,7 @@ struct HeadParams {
   long long fcp_w, fcp_b, fcv_w, fcv_b;
   float* w1x1 = nullptr;   // [6][cfin] scale-folded
   float* b1x1 = nullptr;   // [6]
-  float* fcpT = nullptr;   // [4S][S] transposed, k index in tensor-pixel order
+  float* fcpT = nullptr;   // [4S][232] transposed + zero padded, k index in tensor-pixel order
   float* fcp_bias = nullptr;
   float* fcv = nullptr;    // [2S]
   float* fcv_bias = nullptr;
@@ -49,6 +49,7 @@ struct NetState {
   __half* feat = nullptr;      // [2][mpad][8]
   __half* act[3] = {nullptr, nullptr, nullptr};  // [32][mpad][8]
   int final_buf = 0;
+  float* hbuf = nullptr;  // [bcap][6][S] fp32 outputs of the two 1x1 head convs
   // fp32 CUDA-core reference path
   float* ref_a = nullptr;  // [bcap_ref][256][S]
   float* ref_b = nullptr;
