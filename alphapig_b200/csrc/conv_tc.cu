@@ -12,16 +12,27 @@
 //   A operand    = a 290-row slab of KC<=64 channels ([KC/8][290][8]: K-major, no swizzle, 8x16B core
 //                matrices; any start row is a legal descriptor base) loaded ONCE per K-chunk and reused
 //                by all 9 taps through descriptor start offsets.
-//   B operand    = per (K-chunk, tap) image [KC/8][Cout][8] prepared by net.cu.
+//   B operand    = per (K-chunk, tap) image [KC/8][Cout][8] prepared by net.cu; TPS consecutive taps
+//                travel as one bulk copy / one ring stage.  When the whole layer fits in the ring
+//                (conv1..conv3, the residual stem) it is loaded once per CTA and stays resident.
+//
+// Issue-rate notes (tools/mma_probe.cu, measured on B200): an M=128 MMA executes in 128/64/48 cycles
+// for N=256/128/64 (N=64 is bound by the 128 B/cycle shared-memory operand read), and rebuilding both
+// descriptors per instruction costs ~64-70 issue cycles - more than the N<=128 instruction itself.
+// The issuer below therefore keeps COUT/KC compile-time, unrolls all taps and only adds constants to
+// pre-built descriptor words.
 #include "kernels.h"
 #include "net.h"
 #include "ptx.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kCtrlWarps = 4;                       // TMA producer, MMA issuer, TMEM allocator, spare
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, each owning half of the columns
+constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
 constexpr int kSlabRows = NET_SLAB_ROWS;
-constexpr int kSlabGroupBytes = kSlabRows * 16;  // one 8-channel group of the slab
+constexpr int kSlabGroupBytes = kSlabRows * 16;     // one 8-channel group of the slab
+constexpr int kMaxSlabs = 4, kMaxStages = 9;
 
 struct ConvParams {
   const __half* in;
@@ -30,56 +41,84 @@ struct ConvParams {
   const __half* wimg;
   const float* bias;  // folded BN shift; the BN scale is folded into the fp16 weights
   long long mpad;
-  int cout, kc, nkc, relu;
+  int nkc, relu;
   int n_tiles, W, H;
-  int nb;         // B-tile ring depth
-  int tmem_cols;  // power of two >= acc_stages*2*cout
-  int acc_stages; // 2 when two tiles' accumulators fit in TMEM (cout <= 128): epilogue overlaps the next tile
+  const int* n_tiles_dev;  // when non-null the tile count is read from device memory (compacted leaf batches)
+  int ns;                  // slab ring depth
+  int nb;                  // B ring depth (stages of TPS taps)
   int* errflag;
 };
 
+template <int COUT>
+struct ConvCfg {
+  static constexpr int TPS = (COUT == 256) ? 1 : 3;          // taps per B stage
+  static constexpr int ACC_STAGES = (COUT <= 128) ? 2 : 1;   // accumulator double buffering when TMEM allows
+  static constexpr int TMEM_COLS = (ACC_STAGES * 2 * COUT <= 256) ? 256 : 512;
+};
+
+// wait for every outstanding tcgen05.ld and tie the destination registers to the wait
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+template <int COUT, int KC, bool RESID>
 __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
+  using Cfg = ConvCfg<COUT>;
+  constexpr int TPS = Cfg::TPS;
+  constexpr int STAGES_PER_KC = 9 / TPS;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+  constexpr int KG = KC / 8;                              // 8-channel groups per K-chunk
+  constexpr uint32_t SLAB_BYTES = KG * kSlabGroupBytes;   // multiple of 16
+  constexpr uint32_t SLAB_STRIDE = (SLAB_BYTES + 127u) & ~127u;
+  constexpr uint32_t TAP_BYTES = (uint32_t)KC * COUT * 2;
+  constexpr uint32_t STAGE_BYTES = TPS * TAP_BYTES;
+
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kg = p.kc >> 3;                         // 8-channel groups per K-chunk
-  const uint32_t slab_bytes = kg * kSlabGroupBytes;  // multiple of 16
-  const uint32_t slab_stride = (slab_bytes + 127u) & ~127u;
-  const uint32_t btile_bytes = (uint32_t)p.kc * p.cout * 2;
   uint8_t* slab0 = smem;
-  uint8_t* btile0 = smem + 2 * slab_stride;
-  uint64_t* bars = (uint64_t*)(btile0 + (size_t)p.nb * btile_bytes);
-  // barrier map: [0,2) slab_full, [2,4) slab_empty, [4,4+nb) b_full, [4+nb,4+2nb) b_empty, then tmem_full, tmem_empty
+  uint8_t* bstage0 = smem + (size_t)p.ns * SLAB_STRIDE;
+  uint64_t* bars = (uint64_t*)(bstage0 + (size_t)p.nb * STAGE_BYTES);
   uint64_t* slab_full = bars;
-  uint64_t* slab_empty = bars + 2;
-  uint64_t* b_full = bars + 4;
-  uint64_t* b_empty = bars + 4 + p.nb;
-  uint64_t* tmem_full = bars + 4 + 2 * p.nb;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint64_t* slab_empty = slab_full + kMaxSlabs;
+  uint64_t* b_full = slab_empty + kMaxSlabs;
+  uint64_t* b_empty = b_full + kMaxStages;
+  uint64_t* tmem_full = b_empty + kMaxStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
-  float* s_bias = (float*)(tmem_slot + 4);     // [cout]
+  float* s_bias = (float*)(tmem_slot + 4);      // [COUT]
+
+  const int n_tiles = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
+  // the whole layer's weights fit in the ring: load them once, never release
+  const bool resident = p.nkc * STAGES_PER_KC <= p.nb;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxSlabs; ++i) {
       mbar_init(smem_u32(&slab_full[i]), 1);
       mbar_init(smem_u32(&slab_empty[i]), 1);
     }
-    for (int i = 0; i < p.nb; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(smem_u32(&b_full[i]), 1);
       mbar_init(smem_u32(&b_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full[i]), 1);
-      mbar_init(smem_u32(&tmem_empty[i]), 128);
+      mbar_init(smem_u32(&tmem_empty[i]), 32 * kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)p.tmem_cols)
+                 "r"((uint32_t)Cfg::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -88,164 +127,239 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     int sl = 0, slph = 0, bs = 0, bph = 0;
-    bool ok = true;
-    for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+    bool ok = true, first = true;
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       const long long row0 = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS - 17;
       for (int kc = 0; kc < p.nkc && ok; ++kc) {
         ok = mbar_wait(smem_u32(&slab_empty[sl]), slph ^ 1, p.errflag);
         if (!ok) break;
         const uint32_t fb = smem_u32(&slab_full[sl]);
-        mbar_expect_tx(fb, slab_bytes);
-        for (int j = 0; j < kg; ++j)
-          bulk_g2s(smem_u32(slab0 + sl * slab_stride + j * kSlabGroupBytes),
-                   p.in + ((long long)(kc * kg + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
-        for (int tap = 0; tap < 9; ++tap) {
-          ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag);
-          if (!ok) break;
+        mbar_expect_tx(fb, SLAB_BYTES);
+#pragma unroll
+        for (int j = 0; j < KG; ++j)
+          bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
+                   p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
+        if (resident && !first) continue;
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          if (!resident) {
+            ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag);
+            if (!ok) break;
+          }
           const uint32_t bb = smem_u32(&b_full[bs]);
-          mbar_expect_tx(bb, btile_bytes);
-          bulk_g2s(smem_u32(btile0 + (size_t)bs * btile_bytes),
-                   p.wimg + (size_t)(kc * 9 + tap) * ((size_t)p.kc * p.cout), btile_bytes, bb);
+          mbar_expect_tx(bb, STAGE_BYTES);
+          bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES),
+                   p.wimg + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_BYTES, bb);
           if (++bs == p.nb) { bs = 0; bph ^= 1; }
         }
-        if (++sl == 2) { sl = 0; slph ^= 1; }
       }
+      first = false;
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.cout >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t b_lbo = (uint32_t)p.cout * 16;
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+    // descriptor words: lo = addr>>4 | LBO>>4 << 16, hi = SBO>>4 | version 1 (bit 46); advancing a
+    // K-major no-swizzle operand by rows / K-groups only adds to the 14-bit address field
+    constexpr uint64_t DESC_HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    constexpr uint32_t A_LBO = (uint32_t)kSlabGroupBytes >> 4;   // 290
+    constexpr uint32_t B_LBO = (uint32_t)COUT;                   // COUT*16 >> 4
     int sl = 0, slph = 0, bs = 0, bph = 0, as = 0, aph = 0;
-    bool ok = true;
-    for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+    bool ok = true, first = true;
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       ok = mbar_wait(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t acc_base = tmem_base + (uint32_t)(as * 2 * p.cout);
+      const uint32_t acc_base = tmem_base + (uint32_t)(as * 2 * COUT);
       for (int kc = 0; kc < p.nkc && ok; ++kc) {
         ok = mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag);
         if (!ok) break;
-        const uint32_t sbase = smem_u32(slab0 + sl * slab_stride);
-        for (int tap = 0; tap < 9; ++tap) {
-          ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.errflag);
-          if (!ok) break;
+        const uint32_t a_lo = (smem_u32(slab0 + sl * SLAB_STRIDE) >> 4) | (A_LBO << 16);
+#pragma unroll
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          const int stage = resident ? kc * STAGES_PER_KC + ts : bs;
+          if (!resident || first) {
+            ok = mbar_wait(smem_u32(&b_full[stage]), resident ? 0 : bph, p.errflag);
+            if (!ok) break;
+          }
           tc_fence_after();
-          const int off = (tap / 3 - 1) * 16 + (tap % 3 - 1);
-          const uint32_t bbase = smem_u32(btile0 + (size_t)bs * btile_bytes);
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t arow = sbase + (uint32_t)(17 + off + half * 128) * 16;
-            for (int j = 0; j < (p.kc >> 4); ++j) {
-              const uint64_t ad = make_desc(arow + (uint32_t)(2 * j) * kSlabGroupBytes, kSlabGroupBytes, 128);
-              const uint64_t bd = make_desc(bbase + (uint32_t)(2 * j) * b_lbo, b_lbo, 128);
-              tc_mma_f16(acc_base + (uint32_t)(half * p.cout), ad, bd, idesc, (kc | tap | j) != 0);
+          const uint32_t b_lo = (smem_u32(bstage0 + (size_t)stage * STAGE_BYTES) >> 4) | (B_LBO << 16);
+#pragma unroll
+          for (int t = 0; t < TPS; ++t) {
+            const int tap = ts * TPS + t;
+            const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+              for (int j = 0; j < KC / 16; ++j) {
+                const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
+                const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
+                tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad, bd, IDESC, (kc | tap | j) != 0);
+              }
             }
           }
-          tc_commit(smem_u32(&b_empty[bs]));
-          if (++bs == p.nb) { bs = 0; bph ^= 1; }
+          if (!resident) {
+            tc_commit(smem_u32(&b_empty[bs]));
+            if (++bs == p.nb) { bs = 0; bph ^= 1; }
+          }
         }
         tc_commit(smem_u32(&slab_empty[sl]));
-        if (++sl == 2) { sl = 0; slph ^= 1; }
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
       }
       tc_commit(smem_u32(&tmem_full[as]));
-      if (++as == p.acc_stages) { as = 0; aph ^= 1; }
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+      first = false;
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> regs -> scale/shift (+resid) -> ReLU -> fp16 -> global =====
+  } else if (warp >= kCtrlWarps) {
+    // ===== epilogue: TMEM -> regs -> +shift (+resid) -> ReLU -> fp16 -> global =====
+    // warp w reads TMEM lanes 32*(w&3)..+31 (hardware restriction) and the column half (w-4)>>2
+    constexpr int COLS_PER_WARP = COUT / 2;
+    constexpr int CHUNKS = COLS_PER_WARP / 32;   // 32-column chunks per accumulator half: 1 / 2 / 4
+    constexpr int NCH = 2 * CHUNKS;              // chunks per tile and warp
     const int q = warp & 3;
+    const int cbase = ((warp - kCtrlWarps) >> 2) * COLS_PER_WARP;
     int as = 0, aph = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       ok = mbar_wait(smem_u32(&tmem_full[as]), aph, p.errflag);
       ok = __all_sync(AP_FULL, ok);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t acc_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * p.cout);
-      for (int half = 0; half < 2; ++half) {
+      const uint32_t acc_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * COUT + cbase);
+      const long long grow0 = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + q * 32 + lane;
+      uint32_t v[2][32];
+      tmem_ld32(acc_base, v[0]);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int half = i / CHUNKS, c0 = cbase + (i % CHUNKS) * 32;
+        tmem_ld_wait_regs(v[i & 1]);
+        if (i + 1 < NCH)
+          tmem_ld32(acc_base + (uint32_t)(((i + 1) / CHUNKS) * COUT + ((i + 1) % CHUNKS) * 32), v[(i + 1) & 1]);
         const int r = half * 128 + q * 32 + lane;
         const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
-        const long long grow = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + r;
-        for (int c0 = 0; c0 < p.cout; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(acc_base + (uint32_t)(half * p.cout + c0), v);
-          tmem_ld_wait();
+        const long long grow = grow0 + half * 128;
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            const int c = c0 + gi * 8;
-            const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
-            float f[8];
-            f[0] = __uint_as_float(v[gi * 8 + 0]) + b0.x;
-            f[1] = __uint_as_float(v[gi * 8 + 1]) + b0.y;
-            f[2] = __uint_as_float(v[gi * 8 + 2]) + b0.z;
-            f[3] = __uint_as_float(v[gi * 8 + 3]) + b0.w;
-            f[4] = __uint_as_float(v[gi * 8 + 4]) + b1.x;
-            f[5] = __uint_as_float(v[gi * 8 + 5]) + b1.y;
-            f[6] = __uint_as_float(v[gi * 8 + 6]) + b1.z;
-            f[7] = __uint_as_float(v[gi * 8 + 7]) + b1.w;
-            if (p.resid) {
-              uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float2 t = __half22float2(rh[k]);
-                f[2 * k] += t.x;
-                f[2 * k + 1] += t.y;
-              }
-            }
-            uint4 ov;
-            __half2* oh = reinterpret_cast<__half2*>(&ov);
+        for (int gi = 0; gi < 4; ++gi) {
+          const int c = c0 + gi * 8;
+          const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+          float f[8];
+          f[0] = __uint_as_float(v[i & 1][gi * 8 + 0]) + b0.x;
+          f[1] = __uint_as_float(v[i & 1][gi * 8 + 1]) + b0.y;
+          f[2] = __uint_as_float(v[i & 1][gi * 8 + 2]) + b0.z;
+          f[3] = __uint_as_float(v[i & 1][gi * 8 + 3]) + b0.w;
+          f[4] = __uint_as_float(v[i & 1][gi * 8 + 4]) + b1.x;
+          f[5] = __uint_as_float(v[i & 1][gi * 8 + 5]) + b1.y;
+          f[6] = __uint_as_float(v[i & 1][gi * 8 + 6]) + b1.z;
+          f[7] = __uint_as_float(v[i & 1][gi * 8 + 7]) + b1.w;
+          if (RESID) {
+            uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              float a = f[2 * k], b = f[2 * k + 1];
-              if (p.relu) {
-                a = fmaxf(a, 0.f);
-                b = fmaxf(b, 0.f);
-              }
-              if (!valid) a = b = 0.f;
-              oh[k] = __floats2half2_rn(a, b);
+              float2 t = __half22float2(rh[k]);
+              f[2 * k] += t.x;
+              f[2 * k + 1] += t.y;
             }
-            *reinterpret_cast<uint4*>(p.out + idx) = ov;
           }
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+            if (p.relu) h = __hmax2(h, zero2);
+            oh[k] = h;
+          }
+          if (!valid) ov = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(p.out + idx) = ov;
         }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tmem_empty[as]));
-      if (++as == p.acc_stages) { as = 0; aph ^= 1; }
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
                  : "memory");
   }
 }
 
-}  // namespace
+struct SmemPlan {
+  int ns, nb, bytes;
+};
 
-static int smem_layout(const ConvLayer& L, int* nb_out) {
-  const int kc = L.cin_pad < 64 ? L.cin_pad : 64;
+// slabs + B ring + barriers + TMEM slot + bias inside the 227 KB opt-in limit
+SmemPlan plan_smem(int cout, int kc, int nkc) {
+  const int tps = (cout == 256) ? 1 : 3;
   const int slab = (((kc >> 3) * kSlabGroupBytes) + 127) & ~127;
-  const int btile = kc * L.cout * 2;
-  const int budget = 220 * 1024;
-  int nb = (budget - 2 * slab - 2048) / btile;
-  if (nb > 9) nb = 9;
-  if (nb < 2) nb = 2;
-  *nb_out = nb;
-  return 2 * slab + nb * btile + (4 + 2 * nb + 4) * 8 + 16 + L.cout * 4;
+  const int stage = tps * kc * cout * 2;
+  const int fixed = (2 * kMaxSlabs + 2 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128;
+  const int budget = 227 * 1024 - fixed;
+  const int all = nkc * (9 / tps);  // stages that hold the whole layer
+  SmemPlan s;
+  if (all <= kMaxStages && 2 * slab + all * stage <= budget) {
+    s.nb = all;  // resident weights; spend what is left on a deeper slab ring
+    s.ns = (budget - all * stage) / slab;
+    if (s.ns > kMaxSlabs) s.ns = kMaxSlabs;
+  } else {
+    s.ns = 2;
+    s.nb = (budget - 2 * slab) / stage;
+    if (s.nb > kMaxStages) s.nb = kMaxStages;
+    if (s.nb >= all) s.nb = all - 1;  // never "resident" by accident with a ring smaller than planned
+  }
+  s.bytes = s.ns * slab + s.nb * stage + fixed;
+  return s;
 }
 
-int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb) { return smem_layout(L, out_nb); }
-
-// per-device opt-in to > 48 KB dynamic shared memory (called from ap_net_load)
-int conv_tc_configure(ap_engine* e) {
-  AP_CUDA(e, cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+template <int COUT, int KC>
+int launch_t(ap_engine* e, const ConvParams& p, bool resid, int grid, int smem) {
+  if (resid)
+    k_conv3x3_tc<COUT, KC, true><<<grid, kThreads, smem, e->stream>>>(p);
+  else
+    k_conv3x3_tc<COUT, KC, false><<<grid, kThreads, smem, e->stream>>>(p);
+  AP_LAUNCH_CHECK(e);
   return AP_OK;
 }
 
-int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards) {
+template <int COUT, int KC>
+cudaError_t optin_t() {
+  cudaError_t a = cudaFuncSetAttribute(k_conv3x3_tc<COUT, KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t b = cudaFuncSetAttribute(k_conv3x3_tc<COUT, KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return a != cudaSuccess ? a : b;
+}
+
+}  // namespace
+
+int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb) {
+  const int kc = L.cin_pad < 64 ? L.cin_pad : 64;
+  SmemPlan s = plan_smem(L.cout, kc, L.cin_pad / kc);
+  if (out_nb) *out_nb = s.nb;
+  return s.bytes;
+}
+
+bool conv_tc_supported(int cin_pad, int cout) {
+  const int kc = cin_pad < 64 ? cin_pad : 64;
+  return (cout == 64 || cout == 128 || cout == 256) && (kc == 16 || kc == 64) && cin_pad % kc == 0;
+}
+
+// per-device opt-in to > 48 KB dynamic shared memory for every instantiation (called from ap_net_load)
+int conv_tc_configure(ap_engine* e) {
+  AP_CUDA(e, (optin_t<64, 16>()));
+  AP_CUDA(e, (optin_t<64, 64>()));
+  AP_CUDA(e, (optin_t<128, 16>()));
+  AP_CUDA(e, (optin_t<128, 64>()));
+  AP_CUDA(e, (optin_t<256, 16>()));
+  AP_CUDA(e, (optin_t<256, 64>()));
+  return AP_OK;
+}
+
+int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev) {
   ConvParams p;
   p.in = (L.in_buf < 0) ? n->feat : n->act[L.in_buf];
   p.out = n->act[L.out_buf];
@@ -253,23 +367,27 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards) 
   p.wimg = L.wimg;
   p.bias = L.shift;
   p.mpad = n->mpad;
-  p.cout = L.cout;
-  p.kc = L.cin_pad < 64 ? L.cin_pad : 64;
-  p.nkc = L.cin_pad / p.kc;
+  const int kc = L.cin_pad < 64 ? L.cin_pad : 64;
+  p.nkc = L.cin_pad / kc;
   p.relu = L.relu;
   p.n_tiles = n_boards;
+  p.n_tiles_dev = n_boards_dev;
   p.W = n->W;
   p.H = n->H;
-  p.acc_stages = (4 * L.cout <= 512) ? 2 : 1;
-  int cols = 32;
-  while (cols < p.acc_stages * 2 * L.cout) cols <<= 1;
-  p.tmem_cols = cols;
   p.errflag = n->d_err;
-  int nb;
-  int smem = smem_layout(L, &nb);
-  p.nb = nb;
-  int grid = n_boards < n->sm_count ? n_boards : n->sm_count;
-  k_conv3x3_tc<<<grid, kThreads, smem, e->stream>>>(p);
-  AP_LAUNCH_CHECK(e);
-  return AP_OK;
+  if (!conv_tc_supported(L.cin_pad, L.cout)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
+  const SmemPlan s = plan_smem(L.cout, kc, p.nkc);
+  p.ns = s.ns;
+  p.nb = s.nb;
+  const int grid = n_boards < n->sm_count ? n_boards : n->sm_count;
+  const bool resid = p.resid != nullptr;
+  switch (L.cout * 100 + kc) {
+    case 64 * 100 + 16: return launch_t<64, 16>(e, p, resid, grid, s.bytes);
+    case 64 * 100 + 64: return launch_t<64, 64>(e, p, resid, grid, s.bytes);
+    case 128 * 100 + 16: return launch_t<128, 16>(e, p, resid, grid, s.bytes);
+    case 128 * 100 + 64: return launch_t<128, 64>(e, p, resid, grid, s.bytes);
+    case 256 * 100 + 16: return launch_t<256, 16>(e, p, resid, grid, s.bytes);
+    case 256 * 100 + 64: return launch_t<256, 64>(e, p, resid, grid, s.bytes);
+  }
+  return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
 }

@@ -62,6 +62,7 @@ struct NetState {
 };
 
 // conv_tc.cu
-int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards);
+int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev = nullptr);
+bool conv_tc_supported(int cin_pad, int cout);
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb);
 int conv_tc_configure(ap_engine* e);
