@@ -47,7 +47,24 @@ struct ConvParams {
   int ns;                  // slab ring depth
   int nb;                  // B ring depth (stages of TPS taps)
   int* errflag;
+#ifdef AP_CONV_TRACE
+  long long* trace;
+#endif
 };
+
+#ifdef AP_CONV_TRACE
+// development build only (tools/conv_bench.cu): per-role clock64 stamps of the first tiles of CTAs 0 and 1
+static long long* g_conv_trace = nullptr;
+#define CTRACE(role, it, slot)                                                                      \
+  do {                                                                                              \
+    if (p.trace && blockIdx.x < 2 && (it) < 64 && (threadIdx.x & 31) == 0)                          \
+      p.trace[((blockIdx.x * 4 + (role)) * 64 + (it)) * 8 + (slot)] = clock64();                    \
+  } while (0)
+#else
+#define CTRACE(role, it, slot) \
+  do {                         \
+  } while (0)
+#endif
 
 template <int COUT>
 struct ConvCfg {
@@ -80,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
   constexpr uint32_t STAGE_BYTES = TPS * TAP_BYTES;
 
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(AP_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint8_t* slab0 = smem;
   uint8_t* bstage0 = smem + (size_t)p.ns * SLAB_STRIDE;
   uint64_t* bars = (uint64_t*)(bstage0 + (size_t)p.nb * STAGE_BYTES);
@@ -91,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
   uint64_t* tmem_full = b_empty + kMaxStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
-  float* s_bias = (float*)(tmem_slot + 4);      // [COUT]
+  float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [COUT], float4 reads
 
   const int n_tiles = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
   // the whole layer's weights fit in the ring: load them once, never release
@@ -124,88 +141,105 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
-    int sl = 0, slph = 0, bs = 0, bph = 0;
+  if (warp == 0) {
+    // ===== TMA producer (whole warp loops, one elected lane issues) =====
+    int sl = 0, slph = 0, bs = 0, bph = 0, titer = 0;
     bool ok = true, first = true;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+      const int it = titer++;
       const long long row0 = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS - 17;
       for (int kc = 0; kc < p.nkc && ok; ++kc) {
-        ok = mbar_wait(smem_u32(&slab_empty[sl]), slph ^ 1, p.errflag);
+        if (kc == 0) CTRACE(0, it, 0);
+        ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&slab_empty[sl]), slph ^ 1, p.errflag));
         if (!ok) break;
+        if (kc == 0) CTRACE(0, it, 1);
         const uint32_t fb = smem_u32(&slab_full[sl]);
-        mbar_expect_tx(fb, SLAB_BYTES);
+        if (elect_one()) {
+          mbar_expect_tx(fb, SLAB_BYTES);
 #pragma unroll
-        for (int j = 0; j < KG; ++j)
-          bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
-                   p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+          for (int j = 0; j < KG; ++j)
+            bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
+                     p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+        }
+        __syncwarp();
         if (++sl == p.ns) { sl = 0; slph ^= 1; }
         if (resident && !first) continue;
         for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
           if (!resident) {
-            ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag);
+            ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag));
             if (!ok) break;
           }
           const uint32_t bb = smem_u32(&b_full[bs]);
-          mbar_expect_tx(bb, STAGE_BYTES);
-          bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES),
-                   p.wimg + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_BYTES, bb);
+          if (elect_one()) {
+            mbar_expect_tx(bb, STAGE_BYTES);
+            bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES),
+                     p.wimg + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_BYTES, bb);
+          }
+          __syncwarp();
           if (++bs == p.nb) { bs = 0; bph ^= 1; }
         }
       }
       first = false;
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
     // descriptor words: lo = addr>>4 | LBO>>4 << 16, hi = SBO>>4 | version 1 (bit 46); advancing a
     // K-major no-swizzle operand by rows / K-groups only adds to the 14-bit address field
     constexpr uint64_t DESC_HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
     constexpr uint32_t A_LBO = (uint32_t)kSlabGroupBytes >> 4;   // 290
     constexpr uint32_t B_LBO = (uint32_t)COUT;                   // COUT*16 >> 4
-    int sl = 0, slph = 0, bs = 0, bph = 0, as = 0, aph = 0;
+    int sl = 0, slph = 0, bs = 0, bph = 0, as = 0, aph = 0, titer = 0;
     bool ok = true, first = true;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-      ok = mbar_wait(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag);
+      const int it = titer++;
+      CTRACE(1, it, 0);
+      ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag));
       if (!ok) break;
+      CTRACE(1, it, 1);
       tc_fence_after();
       const uint32_t acc_base = tmem_base + (uint32_t)(as * 2 * COUT);
       for (int kc = 0; kc < p.nkc && ok; ++kc) {
-        ok = mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag);
+        ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag));
         if (!ok) break;
+        if (kc == 0) CTRACE(1, it, 2);
         const uint32_t a_lo = (smem_u32(slab0 + sl * SLAB_STRIDE) >> 4) | (A_LBO << 16);
 #pragma unroll
         for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
           const int stage = resident ? kc * STAGES_PER_KC + ts : bs;
           if (!resident || first) {
-            ok = mbar_wait(smem_u32(&b_full[stage]), resident ? 0 : bph, p.errflag);
+            ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&b_full[stage]), resident ? 0 : bph, p.errflag));
             if (!ok) break;
           }
           tc_fence_after();
           const uint32_t b_lo = (smem_u32(bstage0 + (size_t)stage * STAGE_BYTES) >> 4) | (B_LBO << 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int t = 0; t < TPS; ++t) {
-            const int tap = ts * TPS + t;
-            const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
+            for (int t = 0; t < TPS; ++t) {
+              const int tap = ts * TPS + t;
+              const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+              for (int half = 0; half < 2; ++half) {
 #pragma unroll
-              for (int j = 0; j < KC / 16; ++j) {
-                const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
-                const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
-                tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad, bd, IDESC, (kc | tap | j) != 0);
+                for (int j = 0; j < KC / 16; ++j) {
+                  const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
+                  const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
+                  tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad, bd, IDESC, (kc | tap | j) != 0);
+                }
               }
             }
+            if (!resident) tc_commit(smem_u32(&b_empty[bs]));
+            if (ts == STAGES_PER_KC - 1) {
+              tc_commit(smem_u32(&slab_empty[sl]));
+              if (kc == p.nkc - 1) tc_commit(smem_u32(&tmem_full[as]));
+            }
           }
-          if (!resident) {
-            tc_commit(smem_u32(&b_empty[bs]));
-            if (++bs == p.nb) { bs = 0; bph ^= 1; }
-          }
+          __syncwarp();
+          if (!resident && ++bs == p.nb) { bs = 0; bph ^= 1; }
         }
-        tc_commit(smem_u32(&slab_empty[sl]));
         if (++sl == p.ns) { sl = 0; slph ^= 1; }
       }
-      tc_commit(smem_u32(&tmem_full[as]));
+      CTRACE(1, it, 3);
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
       first = false;
     }
@@ -217,12 +251,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
     constexpr int NCH = 2 * CHUNKS;              // chunks per tile and warp
     const int q = warp & 3;
     const int cbase = ((warp - kCtrlWarps) >> 2) * COLS_PER_WARP;
-    int as = 0, aph = 0;
+    int as = 0, aph = 0, titer = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+      const int it = titer++;
+      if (warp == kCtrlWarps) CTRACE(2, it, 0);
       ok = mbar_wait(smem_u32(&tmem_full[as]), aph, p.errflag);
       ok = __all_sync(AP_FULL, ok);
       if (!ok) break;
+      if (warp == kCtrlWarps) CTRACE(2, it, 1);
       tc_fence_after();
       const uint32_t acc_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * COUT + cbase);
       const long long grow0 = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + q * 32 + lane;
@@ -232,8 +269,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
       for (int i = 0; i < NCH; ++i) {
         const int half = i / CHUNKS, c0 = cbase + (i % CHUNKS) * 32;
         tmem_ld_wait_regs(v[i & 1]);
-        if (i + 1 < NCH)
+        if (i + 1 < NCH) {
           tmem_ld32(acc_base + (uint32_t)(((i + 1) / CHUNKS) * COUT + ((i + 1) % CHUNKS) * 32), v[(i + 1) & 1]);
+        } else {
+          // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
+          tc_fence_before();
+          mbar_arrive(smem_u32(&tmem_empty[as]));
+          if (warp == kCtrlWarps) CTRACE(2, it, 2);
+        }
         const int r = half * 128 + q * 32 + lane;
         const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
         const long long grow = grow0 + half * 128;
@@ -275,8 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
           *reinterpret_cast<uint4*>(p.out + idx) = ov;
         }
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty[as]));
+      if (warp == kCtrlWarps) CTRACE(2, it, 3);
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
     }
   }
@@ -286,6 +328,296 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2): one board per cluster of two CTAs, UMMA M=256.  CTA r owns board
+// rows [128r, 128r+128): it stages a 162-row slab of them (A) and HALF of the weight tile (B columns
+// [r*COUT/2, (r+1)*COUT/2)); the tensor cores of both SMs read both halves.  Per SM this halves the
+// shared-memory operand traffic and the TMEM footprint, so the accumulator is double buffered for
+// every COUT (the epilogue of tile i hides under the MMAs of tile i+1) and conv4 / the residual
+// blocks keep their whole weight tensor resident in shared memory.
+//   barriers (same offsets in both CTAs):
+//     slab_full / b_full    local TMA completion (tx bytes)
+//     slab_ready / b_ready  used in the leader only, count 2: one relay arrive per CTA after its
+//                           local *_full completed (plain bulk copies cannot signal a peer barrier)
+//     slab_empty / b_empty / tmem_full   tcgen05.commit multicast to both CTAs
+//     tmem_empty            leader only, count 2*kEpiWarps: one arrive per epilogue warp of the pair
+// ---------------------------------------------------------------------------------------------
+constexpr int kSlab2Rows = 128 + 2 * 17;
+constexpr int kSlab2GroupBytes = kSlab2Rows * 16;
+constexpr int kTps2 = 3;  // taps per B stage
+
+template <int COUT, int KC, bool RESID>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3x3_tc2(ConvParams p) {
+  constexpr int TPS = kTps2;
+  constexpr int STAGES_PER_KC = 9 / TPS;
+  constexpr int ACC_STAGES = 2;
+  constexpr int TMEM_COLS = (2 * COUT < 32) ? 32 : 2 * COUT;   // 128 / 256 / 512
+  constexpr int KG = KC / 8;
+  constexpr int NH = COUT / 2;                                 // B columns held by one CTA
+  constexpr uint32_t SLAB_BYTES = KG * kSlab2GroupBytes;
+  constexpr uint32_t SLAB_STRIDE = (SLAB_BYTES + 127u) & ~127u;
+  constexpr uint32_t TAP_BYTES = (uint32_t)KC * NH * 2;
+  constexpr uint32_t STAGE_BYTES = TPS * TAP_BYTES;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(AP_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* slab0 = smem;
+  uint8_t* bstage0 = smem + (size_t)p.ns * SLAB_STRIDE;
+  uint64_t* bars = (uint64_t*)(bstage0 + (size_t)p.nb * STAGE_BYTES);
+  uint64_t* slab_full = bars;
+  uint64_t* slab_ready = slab_full + kMaxSlabs;
+  uint64_t* slab_empty = slab_ready + kMaxSlabs;
+  uint64_t* b_full = slab_empty + kMaxSlabs;
+  uint64_t* b_ready = b_full + kMaxStages;
+  uint64_t* b_empty = b_ready + kMaxStages;
+  uint64_t* tmem_full = b_empty + kMaxStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [COUT], float4 reads
+
+  const int n_tiles = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const bool resident = p.nkc * STAGES_PER_KC <= p.nb;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxSlabs; ++i) {
+      mbar_init(smem_u32(&slab_full[i]), 1);
+      mbar_init(smem_u32(&slab_ready[i]), 2);
+      mbar_init(smem_u32(&slab_empty[i]), 1);
+    }
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(smem_u32(&b_full[i]), 1);
+      mbar_init(smem_u32(&b_ready[i]), 2);
+      mbar_init(smem_u32(&b_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full[i]), 1);
+      mbar_init(smem_u32(&tmem_empty[i]), 2 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: own slab rows + own half of the weight tile =====
+    const __half* wsrc = p.wimg + (size_t)rank * ((size_t)p.nkc * 9 * KC * NH);
+    int sl = 0, slph = 0, bs = 0, bph = 0, titer = 0;
+    bool ok = true, first = true;
+    for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
+      const int it = titer++;
+      const long long row0 = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + 128 * (int)rank - 17;
+      for (int kc = 0; kc < p.nkc && ok; ++kc) {
+        if (kc == 0) CTRACE(0, it, 0);
+        ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&slab_empty[sl]), slph ^ 1, p.errflag));
+        if (!ok) break;
+        if (kc == 0) CTRACE(0, it, 1);
+        const uint32_t fb = smem_u32(&slab_full[sl]);
+        if (elect_one()) {
+          mbar_expect_tx(fb, SLAB_BYTES);
+#pragma unroll
+          for (int j = 0; j < KG; ++j)
+            bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlab2GroupBytes),
+                     p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlab2GroupBytes, fb);
+        }
+        __syncwarp();
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
+        if (resident && !first) continue;
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          if (!resident) {
+            ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag));
+            if (!ok) break;
+          }
+          const uint32_t bb = smem_u32(&b_full[bs]);
+          if (elect_one()) {
+            mbar_expect_tx(bb, STAGE_BYTES);
+            bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES), wsrc + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * NH),
+                     STAGE_BYTES, bb);
+          }
+          __syncwarp();
+          if (++bs == p.nb) { bs = 0; bph ^= 1; }
+        }
+      }
+      first = false;
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===== relay: local TMA completion -> arrive on the leader's *_ready barrier =====
+    int sl = 0, slph = 0, bs = 0, bph = 0, titer = 0;
+    bool ok = true, first = true;
+    for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
+      const int it = titer++;
+      for (int kc = 0; kc < p.nkc && ok; ++kc) {
+        ok = mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag);
+        if (!ok) break;
+        if (kc == 0) CTRACE(3, it, 0);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&slab_ready[sl]), 0));
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
+        if (resident && !first) continue;
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.errflag);
+          if (!ok) break;
+          mbar_arrive_cluster(mapa_u32(smem_u32(&b_ready[bs]), 0));
+          if (++bs == p.nb) { bs = 0; bph ^= 1; }
+        }
+      }
+      first = false;
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA only): the whole warp runs the loop, one elected lane issues =====
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((256u >> 4) << 24);
+    constexpr uint64_t DESC_HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    constexpr uint32_t A_LBO = (uint32_t)kSlab2GroupBytes >> 4;  // 162
+    constexpr uint32_t B_LBO = (uint32_t)NH;                     // NH*16 >> 4
+    int sl = 0, slph = 0, bs = 0, bph = 0, as = 0, aph = 0, titer = 0;
+    bool ok = true, first = true;
+    for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
+      const int it = titer++;
+      CTRACE(1, it, 0);
+      ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag));
+      if (!ok) break;
+      CTRACE(1, it, 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(as * COUT);
+      for (int kc = 0; kc < p.nkc && ok; ++kc) {
+        ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&slab_ready[sl]), slph, p.errflag));
+        if (!ok) break;
+        if (kc == 0) CTRACE(1, it, 2);
+        const uint32_t a_lo = (smem_u32(slab0 + sl * SLAB_STRIDE) >> 4) | (A_LBO << 16);
+#pragma unroll
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          const int stage = resident ? kc * STAGES_PER_KC + ts : bs;
+          if (!resident || first) {
+            ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&b_ready[stage]), resident ? 0 : bph, p.errflag));
+            if (!ok) break;
+          }
+          tc_fence_after();
+          const uint32_t b_lo = (smem_u32(bstage0 + (size_t)stage * STAGE_BYTES) >> 4) | (B_LBO << 16);
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < TPS; ++t) {
+              const int tap = ts * TPS + t;
+              const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
+#pragma unroll
+              for (int j = 0; j < KC / 16; ++j) {
+                const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + 2 * j * (int)A_LBO));
+                const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
+                tc_mma_f16_2cta(acc, ad, bd, IDESC, (kc | tap | j) != 0);
+              }
+            }
+            if (!resident) tc_commit_2cta(smem_u32(&b_empty[bs]));
+            if (ts == STAGES_PER_KC - 1) {
+              tc_commit_2cta(smem_u32(&slab_empty[sl]));
+              if (kc == p.nkc - 1) tc_commit_2cta(smem_u32(&tmem_full[as]));
+            }
+          }
+          __syncwarp();
+          if (!resident && ++bs == p.nb) { bs = 0; bph ^= 1; }
+        }
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
+      }
+      CTRACE(1, it, 3);
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+      first = false;
+    }
+  } else if (warp >= kCtrlWarps) {
+    // ===== epilogue: this CTA's 128 rows; warp w reads TMEM lanes 32*(w&3)..+31, column half (w-4)>>2 =====
+    constexpr int NCH = NH / 32;  // 32-column chunks per warp and tile: 1 / 2 / 4
+    const int q = warp & 3;
+    const int cbase = ((warp - kCtrlWarps) >> 2) * NH;
+    const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    int as = 0, aph = 0, titer = 0;
+    bool ok = true;
+    for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
+      const int it = titer++;
+      if (warp == kCtrlWarps) CTRACE(2, it, 0);
+      ok = mbar_wait(smem_u32(&tmem_full[as]), aph, p.errflag);
+      ok = __all_sync(AP_FULL, ok);
+      if (!ok) break;
+      if (warp == kCtrlWarps) CTRACE(2, it, 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * COUT + cbase);
+      const int r = (int)rank * 128 + q * 32 + lane;
+      const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
+      const long long grow = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + r;
+      uint32_t v[2][32];
+      tmem_ld32(acc, v[0]);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c0 = cbase + i * 32;
+        tmem_ld_wait_regs(v[i & 1]);
+        if (i + 1 < NCH) {
+          tmem_ld32(acc + (uint32_t)((i + 1) * 32), v[(i + 1) & 1]);
+        } else {
+          // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(empty_remote + (uint32_t)(as * 8));
+          if (warp == kCtrlWarps) CTRACE(2, it, 2);
+        }
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const int c = c0 + gi * 8;
+          const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+          float f[8];
+          f[0] = __uint_as_float(v[i & 1][gi * 8 + 0]) + b0.x;
+          f[1] = __uint_as_float(v[i & 1][gi * 8 + 1]) + b0.y;
+          f[2] = __uint_as_float(v[i & 1][gi * 8 + 2]) + b0.z;
+          f[3] = __uint_as_float(v[i & 1][gi * 8 + 3]) + b0.w;
+          f[4] = __uint_as_float(v[i & 1][gi * 8 + 4]) + b1.x;
+          f[5] = __uint_as_float(v[i & 1][gi * 8 + 5]) + b1.y;
+          f[6] = __uint_as_float(v[i & 1][gi * 8 + 6]) + b1.z;
+          f[7] = __uint_as_float(v[i & 1][gi * 8 + 7]) + b1.w;
+          if (RESID) {
+            uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 t = __half22float2(rh[k]);
+              f[2 * k] += t.x;
+              f[2 * k + 1] += t.y;
+            }
+          }
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+            if (p.relu) h = __hmax2(h, zero2);
+            oh[k] = h;
+          }
+          if (!valid) ov = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(p.out + idx) = ov;
+        }
+      }
+      if (warp == kCtrlWarps) CTRACE(2, it, 3);
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits while the peer may still arrive on its barriers / read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
 }
@@ -334,6 +666,45 @@ cudaError_t optin_t() {
   return a != cudaSuccess ? a : b;
 }
 
+
+SmemPlan plan_smem2(int cout, int kc, int nkc) {
+  const int slab = (((kc >> 3) * kSlab2GroupBytes) + 127) & ~127;
+  const int stage = kTps2 * kc * (cout / 2) * 2;
+  const int fixed = (3 * kMaxSlabs + 3 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128;
+  const int budget = 227 * 1024 - fixed;
+  const int all = nkc * (9 / kTps2);
+  SmemPlan s;
+  if (all <= kMaxStages && 2 * slab + all * stage <= budget) {
+    s.nb = all;
+    s.ns = (budget - all * stage) / slab;
+    if (s.ns > kMaxSlabs) s.ns = kMaxSlabs;
+  } else {
+    s.ns = 3;
+    s.nb = (budget - s.ns * slab) / stage;
+    if (s.nb > kMaxStages) s.nb = kMaxStages;
+    if (s.nb >= all) s.nb = all - 1;
+  }
+  s.bytes = s.ns * slab + s.nb * stage + fixed;
+  return s;
+}
+
+template <int COUT, int KC>
+int launch2_t(ap_engine* e, const ConvParams& p, bool resid, int grid, int smem) {
+  if (resid)
+    k_conv3x3_tc2<COUT, KC, true><<<grid, kThreads, smem, e->stream>>>(p);
+  else
+    k_conv3x3_tc2<COUT, KC, false><<<grid, kThreads, smem, e->stream>>>(p);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+
+template <int COUT, int KC>
+cudaError_t optin2_t() {
+  cudaError_t a = cudaFuncSetAttribute(k_conv3x3_tc2<COUT, KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t b = cudaFuncSetAttribute(k_conv3x3_tc2<COUT, KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return a != cudaSuccess ? a : b;
+}
+
 }  // namespace
 
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb) {
@@ -356,6 +727,12 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, (optin_t<128, 64>()));
   AP_CUDA(e, (optin_t<256, 16>()));
   AP_CUDA(e, (optin_t<256, 64>()));
+  AP_CUDA(e, (optin2_t<64, 16>()));
+  AP_CUDA(e, (optin2_t<64, 64>()));
+  AP_CUDA(e, (optin2_t<128, 16>()));
+  AP_CUDA(e, (optin2_t<128, 64>()));
+  AP_CUDA(e, (optin2_t<256, 16>()));
+  AP_CUDA(e, (optin2_t<256, 64>()));
   return AP_OK;
 }
 
@@ -375,12 +752,36 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   p.W = n->W;
   p.H = n->H;
   p.errflag = n->d_err;
+#ifdef AP_CONV_TRACE
+  p.trace = g_conv_trace;
+#endif
   if (!conv_tc_supported(L.cin_pad, L.cout)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
+  const bool resid = p.resid != nullptr;
+  // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks); the
+  // memory-bound small layers and the L2-bound 256->256 layer run the single-CTA kernel
+  const bool pair = n->conv_mode == 2 || (n->conv_mode == 0 && L.cin_pad == 128);
+  if (pair) {
+    // CTA pairs: one board per cluster of two
+    p.wimg = L.wimg2;
+    const SmemPlan s = plan_smem2(L.cout, kc, p.nkc);
+    p.ns = s.ns;
+    p.nb = s.nb;
+    const int pairs = n->sm_count / 2;
+    const int grid = 2 * (n_boards < pairs ? n_boards : pairs);
+    switch (L.cout * 100 + kc) {
+      case 64 * 100 + 16: return launch2_t<64, 16>(e, p, resid, grid, s.bytes);
+      case 64 * 100 + 64: return launch2_t<64, 64>(e, p, resid, grid, s.bytes);
+      case 128 * 100 + 16: return launch2_t<128, 16>(e, p, resid, grid, s.bytes);
+      case 128 * 100 + 64: return launch2_t<128, 64>(e, p, resid, grid, s.bytes);
+      case 256 * 100 + 16: return launch2_t<256, 16>(e, p, resid, grid, s.bytes);
+      case 256 * 100 + 64: return launch2_t<256, 64>(e, p, resid, grid, s.bytes);
+    }
+    return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
+  }
   const SmemPlan s = plan_smem(L.cout, kc, p.nkc);
   p.ns = s.ns;
   p.nb = s.nb;
   const int grid = n_boards < n->sm_count ? n_boards : n->sm_count;
-  const bool resid = p.resid != nullptr;
   switch (L.cout * 100 + kc) {
     case 64 * 100 + 16: return launch_t<64, 16>(e, p, resid, grid, s.bytes);
     case 64 * 100 + 64: return launch_t<64, 64>(e, p, resid, grid, s.bytes);

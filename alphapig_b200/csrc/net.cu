@@ -3,6 +3,7 @@
 // independent fp32 CUDA-core path used as an on-device cross-check.
 // Replaces PolicyValueNet inference (policy_value_net_mxnet_simple.py:68-92,178-226;
 // policy_value_net_mxnet.py:70-102,232-280).
+#include <stdlib.h>
 #include <string.h>
 
 #include "board.cuh"
@@ -23,7 +24,7 @@
 // ------------------------------------------------------------------------------------------
 __global__ void k_prep_conv(const float* __restrict__ master, long long w, long long b, long long gamma, long long beta,
                             long long mean, long long var, int fix_gamma, int cin, int cin_pad, int cout, int kc,
-                            __half* wimg, float* scale, float* shift) {
+                            __half* wimg, __half* wimg2, float* scale, float* shift) {
   const long long total = (long long)9 * cin_pad * cout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     // image order: [kcI][tap][j][n][e]
@@ -40,6 +41,10 @@ __global__ void k_prep_conv(const float* __restrict__ master, long long w, long 
     if (!fix_gamma) sc *= master[gamma + n];
     float v = (k < cin) ? master[w + ((long long)n * cin + k) * 9 + tap] * sc : 0.f;  // BN scale folded in fp32
     wimg[i] = __float2half_rn(v);
+    // CTA-pair image: [r][kcI][tap][j][n'][e], n = r*cout/2 + n'
+    const int nh = cout >> 1, rr = n / nh, np = n - rr * nh;
+    const long long i2 = ((((long long)rr * (cin_pad / kc) + kcI) * 9 + tap) * (kc >> 3) + j) * nh * 8 + (long long)np * 8 + e;
+    wimg2[i2] = __float2half_rn(v);
   }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < cout; n += gridDim.x * blockDim.x) {
     float s = 1.f / sqrtf(master[var + n] + BN_EPS);
@@ -400,7 +405,7 @@ static int net_prep(ap_engine* e) {
   for (auto& L : n->trunk) {
     int kc = L.cin_pad < 64 ? L.cin_pad : 64;
     k_prep_conv<<<256, 256, 0, e->stream>>>(n->master, L.w, L.b, L.gamma, L.beta, L.mean, L.var, L.fix_gamma, L.cin,
-                                            L.cin_pad, L.cout, kc, L.wimg, L.scale, L.shift);
+                                            L.cin_pad, L.cout, kc, L.wimg, L.wimg2, L.scale, L.shift);
     AP_LAUNCH_CHECK(e);
   }
   k_prep_heads<<<256, 256, 0, e->stream>>>(n->master, n->head, n->S);
@@ -429,6 +434,7 @@ static int conv_bind(ap_engine* e, NetState* n, ConvLayer& L, const std::string&
   if (L.w < 0 || L.b < 0 || L.gamma < 0 || L.beta < 0 || L.mean < 0 || L.var < 0) return AP_ERR_BAD_ARG;
   L.cin_pad = (L.cin + 15) & ~15;
   AP_TRY(nalloc(e, n, (void**)&L.wimg, (size_t)9 * L.cin_pad * L.cout * 2));
+  AP_TRY(nalloc(e, n, (void**)&L.wimg2, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.scale, (size_t)L.cout * 4));
   AP_TRY(nalloc(e, n, (void**)&L.shift, (size_t)L.cout * 4));
   return AP_OK;
@@ -451,6 +457,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   n->H = e->geo.H;
   n->S = e->geo.S;
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device);
+  if (const char* m = getenv("AP_CONV_MODE")) n->conv_mode = (m[0] == '1') ? 1 : (m[0] == '2') ? 2 : 0;
   long long total = 0;
   for (int i = 0; i < n_tensors; ++i) {
     n->names.push_back(tensors[i].name);

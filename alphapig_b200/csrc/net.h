@@ -17,6 +17,7 @@ struct ConvLayer {
   int fix_gamma;
   // prepared (device)
   __half* wimg = nullptr;  // [nkc][9][KC/8][cout][8]
+  __half* wimg2 = nullptr; // CTA-pair image [2][nkc][9][KC/8][cout/2][8]: half r holds output channels [r*cout/2, (r+1)*cout/2)
   float* scale = nullptr;  // [cout]
   float* shift = nullptr;  // [cout]
 };
@@ -57,6 +58,7 @@ struct NetState {
   float* ref_in = nullptr;  // [bcap_ref][9][S]
   int bcap_ref = 0;
   int sm_count = 148;
+  int conv_mode = 0;  // 0 = per-layer choice, 1 = single-CTA kernel, 2 = CTA-pair kernel (cta_group::2); AP_CONV_MODE overrides for A/B timing
   int* d_err = nullptr;
   std::vector<void*> allocs;
 };

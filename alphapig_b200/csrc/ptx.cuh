@@ -80,5 +80,81 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- 2-CTA (cta_group::2) helpers: cluster rank, DSMEM barrier arrives, multicast commit --------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// arrive that orders nothing but itself: used to hand a drained TMEM accumulator back to the MMA issuer
+// (the tcgen05.ld results are already in registers; a release here would wait for the epilogue's global stores)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cl(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait with cluster-scope acquire (the arrivals come from the peer CTA)
+__device__ __forceinline__ bool mbar_wait_cl(uint32_t bar, uint32_t parity, int* errflag) {
+  if (mbar_try_cl(bar, parity)) return true;
+  long long t0 = clock64();
+  while (!mbar_try_cl(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      atomicExch(errflag, 1);
+      return false;
+    }
+  }
+  return true;
+}
+// all prior tcgen05.mma of this thread complete -> arrive on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- warp-uniform issue: the whole warp runs the loop, one elected lane executes the instruction -------
+// (a lane==0 branch makes ptxas wrap every uniform-datapath instruction in an ELECT/R2UR loop: ~65 cycles
+// per tcgen05.mma, measured with tools/mma_probe.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t.reg .b32 r;\n\t"
+      "elect.sync r|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 }  // namespace
