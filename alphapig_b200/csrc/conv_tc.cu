@@ -47,6 +47,13 @@ struct ConvParams {
   int ns;                  // slab ring depth
   int nb;                  // B ring depth (stages of TPS taps)
   int* errflag;
+  // HEAD instantiations only: the two 1x1 head convs (+folded BN+ReLU) run in the epilogue and their outputs
+  // go straight into the split-fp16 A operand of the FC GEMM (heads_tc.cu); the trunk output is never stored.
+  // The 1x1 weights travel as a second kernel parameter (HeadArg): they sit in the constant bank and feed the
+  // FFMAs as immediate c[0x0][..] operands - no shared-memory traffic next to the tensor-core operand reads
+  __half* ha;        // [2 (hi,lo)][ha_kg][ha_rows][8]
+  long long ha_rows; // board rows of the A operand (multiple of 128)
+  int ha_kg;         // K groups (of 8) of the A operand
 #ifdef AP_CONV_TRACE
   long long* trace;
 #endif
@@ -84,9 +91,159 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
                : "memory");
 }
 
-template <int COUT, int KC, bool RESID>
-__global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
+
+// ---- epilogue arithmetic shared by both kernels ------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
+
+// second kernel parameter of the HEAD instantiations (empty otherwise)
+template <bool HEAD>
+struct HeadArg {};
+template <>
+struct HeadArg<true> {
+  NetHeadW h;
+};
+
+// one chunk (NG groups of 8 columns) of one accumulator row: +shift (+residual) -> ReLU, then either fp16 store of the
+// activation row (trunk layers) or 6 running dot products with the 1x1 head weights (HEAD; c0 is a compile-time
+// constant after inlining + unrolling, so every weight is an immediate constant-bank operand)
+template <int COUT, bool RESID, bool HEAD, int NG>
+__device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEAD>& hw, const uint32_t (&v)[8 * NG], int c0,
+                                          long long grow, bool valid, uint32_t s_bias, float (&hacc)[6]) {
+#pragma unroll
+  for (int gi = 0; gi < NG; ++gi) {
+    const int c = c0 + gi * 8;
+    const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
+    const float4 b0 = lds128(s_bias + c * 4);
+    const float4 b1 = lds128(s_bias + c * 4 + 16);
+    float f[8];
+    f[0] = __uint_as_float(v[gi * 8 + 0]) + b0.x;
+    f[1] = __uint_as_float(v[gi * 8 + 1]) + b0.y;
+    f[2] = __uint_as_float(v[gi * 8 + 2]) + b0.z;
+    f[3] = __uint_as_float(v[gi * 8 + 3]) + b0.w;
+    f[4] = __uint_as_float(v[gi * 8 + 4]) + b1.x;
+    f[5] = __uint_as_float(v[gi * 8 + 5]) + b1.y;
+    f[6] = __uint_as_float(v[gi * 8 + 6]) + b1.z;
+    f[7] = __uint_as_float(v[gi * 8 + 7]) + b1.w;
+    if (RESID) {
+      uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 t = __half22float2(rh[k]);
+        f[2 * k] += t.x;
+        f[2 * k + 1] += t.y;
+      }
+    }
+    if constexpr (HEAD) {
+      if (p.relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+      }
+#pragma unroll
+      for (int o = 0; o < 6; ++o) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hacc[o] = fmaf(f[k], hw.h.w[o * COUT + c + k], hacc[o]);
+      }
+    } else {
+      uint4 ov;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+      const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+        if (p.relu) h = __hmax2(h, zero2);
+        oh[k] = h;
+      }
+      if (!valid) ov = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(p.out + idx) = ov;
+    }
+  }
+}
+
+// HEAD: the NCG warps that share a TMEM lane quarter (column groups 0..NCG-1) combine their partial dot
+// products through shared memory; the group-0 warp finishes (shift, ReLU) and writes hi/lo fp16 into the
+// FC operand.  NR = accumulator rows per thread (2 in the single-CTA kernel, 1 in the pair kernel).
+template <int NR, int NCG>
+__device__ __forceinline__ void head_finish(const ConvParams& p, const HeadArg<true>& hw, float (&hacc)[NR][6], uint32_t s_hx,
+                                            int bar_id, int q, int lane, int cg, int tile, const int (&rows)[NR]) {
+  if (cg != 0) {
+    const uint32_t slot = s_hx + (uint32_t)(((cg - 1) * 128 + q * 32 + lane) * (NR * 6) * 4);
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int o = 0; o < 6; ++o)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (uint32_t)((r * 6 + o) * 4)), "f"(hacc[r][o]) : "memory");
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NCG) : "memory");
+  if (cg == 0) {
+    const int S = p.W * p.H;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int x = rows[r] & 15, y = rows[r] >> 4;
+      if (x < p.W && y < p.H) {
+        const int pix = y * p.W + x;
+#pragma unroll
+        for (int o = 0; o < 6; ++o) {
+          float a = hacc[r][o];
+#pragma unroll
+          for (int g = 1; g < NCG; ++g) {
+            float t;
+            asm volatile("ld.shared.f32 %0, [%1];"
+                         : "=f"(t)
+                         : "r"(s_hx + (uint32_t)((((g - 1) * 128 + q * 32 + lane) * (NR * 6) + r * 6 + o) * 4))
+                         : "memory");
+            a += t;
+          }
+          const float h = fmaxf(a + hw.h.b[o], 0.f);
+          const __half hi = __float2half_rn(h);
+          const __half lo = __float2half_rn(h - __half2float(hi));
+          const int k = o * S + pix;
+          const long long at = ((long long)(k >> 3) * p.ha_rows + tile) * 8 + (k & 7);
+          p.ha[at] = hi;
+          p.ha[(long long)p.ha_kg * p.ha_rows * 8 + at] = lo;
+        }
+      }
+    }
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NCG) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_regs16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
+// HEAD instantiations run 16 epilogue warps (four per TMEM lane quarter, 16-column chunks): the accumulator of
+// a 256-channel layer cannot be double buffered (512 TMEM columns), so the extra dot-product work of the fused
+// head convs must drain the accumulator as fast as the plain epilogue does
+template <bool HEAD>
+struct EpiCfg {
+  static constexpr int WARPS = HEAD ? 16 : kEpiWarps;
+  static constexpr int THREADS = 32 * (kCtrlWarps + WARPS);
+};
+
+template <int COUT, int KC, bool RESID, bool HEAD>
+__global__ void __launch_bounds__(EpiCfg<HEAD>::THREADS, 1)
+k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadArg<HEAD> hw) {
   using Cfg = ConvCfg<COUT>;
+  constexpr int EPI = EpiCfg<HEAD>::WARPS;
+  constexpr int NTHR = EpiCfg<HEAD>::THREADS;
   constexpr int TPS = Cfg::TPS;
   constexpr int STAGES_PER_KC = 9 / TPS;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
@@ -109,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
   float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [COUT], float4 reads
+  float* s_hx = s_bias + COUT;          // HEAD: [NCG-1][128][NR*6] partial exchange between the warps of a lane quarter
 
   const int n_tiles = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
   // the whole layer's weights fit in the ring: load them once, never release
@@ -125,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full[i]), 1);
-      mbar_init(smem_u32(&tmem_empty[i]), 32 * kEpiWarps);
+      mbar_init(smem_u32(&tmem_empty[i]), 32 * EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -135,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < COUT; i += NTHR) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -244,13 +402,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
       first = false;
     }
   } else if (warp >= kCtrlWarps) {
-    // ===== epilogue: TMEM -> regs -> +shift (+resid) -> ReLU -> fp16 -> global =====
-    // warp w reads TMEM lanes 32*(w&3)..+31 (hardware restriction) and the column half (w-4)>>2
-    constexpr int COLS_PER_WARP = COUT / 2;
-    constexpr int CHUNKS = COLS_PER_WARP / 32;   // 32-column chunks per accumulator half: 1 / 2 / 4
+    // ===== epilogue: TMEM -> regs -> +shift (+resid) -> ReLU -> fp16 -> global (or the fused head convs) =====
+    // warp w reads TMEM lanes 32*(w&3)..+31 (hardware restriction) and column group (w-4)>>2 of EPI/4
+    constexpr int NCG = EPI / 4;                 // warps per lane quarter
+    constexpr int COLS_PER_WARP = COUT / NCG;
+    constexpr int CHUNKS = COLS_PER_WARP / 32;   // 32-column chunks per accumulator half (plain epilogue)
     constexpr int NCH = 2 * CHUNKS;              // chunks per tile and warp
     const int q = warp & 3;
-    const int cbase = ((warp - kCtrlWarps) >> 2) * COLS_PER_WARP;
+    const int cg = (warp - kCtrlWarps) >> 2;
+    const int cbase = cg * COLS_PER_WARP;
     int as = 0, aph = 0, titer = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
@@ -261,61 +421,58 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv3x3_tc(ConvParams p) {
       if (!ok) break;
       if (warp == kCtrlWarps) CTRACE(2, it, 1);
       tc_fence_after();
-      const uint32_t acc_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * COUT + cbase);
+      const uint32_t acc_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * COUT);
       const long long grow0 = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + q * 32 + lane;
-      uint32_t v[2][32];
-      tmem_ld32(acc_base, v[0]);
+      const uint32_t sb = smem_u32(s_bias), sx = smem_u32(s_hx), eb = smem_u32(&tmem_empty[as]);
+      if constexpr (HEAD) {
+        // four warps per lane quarter: warp (hh, cc) owns accumulator half hh (rows 128*hh..) and column half cc, so
+        // every head weight is used exactly once per warp and is an immediate constant-bank operand
+        static_assert(NCG == 4, "HEAD epilogue: four warps per lane quarter");
+        const int hh = cg >> 1, cc = cg & 1;
+        const int r = hh * 128 + q * 32 + lane;
+        auto body = [&](const int cb) {
+          constexpr int NCHH = COUT / 2 / 16;
+          const uint32_t a0 = acc_base + (uint32_t)(hh * COUT + cb);
+          uint32_t v[2][16];
+          float hacc[1][6];
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int half = i / CHUNKS, c0 = cbase + (i % CHUNKS) * 32;
-        tmem_ld_wait_regs(v[i & 1]);
-        if (i + 1 < NCH) {
-          tmem_ld32(acc_base + (uint32_t)(((i + 1) / CHUNKS) * COUT + ((i + 1) % CHUNKS) * 32), v[(i + 1) & 1]);
-        } else {
-          // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
-          tc_fence_before();
-          mbar_arrive(smem_u32(&tmem_empty[as]));
-          if (warp == kCtrlWarps) CTRACE(2, it, 2);
-        }
-        const int r = half * 128 + q * 32 + lane;
-        const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
-        const long long grow = grow0 + half * 128;
+          for (int o = 0; o < 6; ++o) hacc[0][o] = 0.f;
+          tmem_ld16_nowait(a0, v[0]);
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const int c = c0 + gi * 8;
-          const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
-          float f[8];
-          f[0] = __uint_as_float(v[i & 1][gi * 8 + 0]) + b0.x;
-          f[1] = __uint_as_float(v[i & 1][gi * 8 + 1]) + b0.y;
-          f[2] = __uint_as_float(v[i & 1][gi * 8 + 2]) + b0.z;
-          f[3] = __uint_as_float(v[i & 1][gi * 8 + 3]) + b0.w;
-          f[4] = __uint_as_float(v[i & 1][gi * 8 + 4]) + b1.x;
-          f[5] = __uint_as_float(v[i & 1][gi * 8 + 5]) + b1.y;
-          f[6] = __uint_as_float(v[i & 1][gi * 8 + 6]) + b1.z;
-          f[7] = __uint_as_float(v[i & 1][gi * 8 + 7]) + b1.w;
-          if (RESID) {
-            uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float2 t = __half22float2(rh[k]);
-              f[2 * k] += t.x;
-              f[2 * k + 1] += t.y;
+          for (int i = 0; i < NCHH; ++i) {
+            tmem_ld_wait_regs16(v[i & 1]);
+            if (i + 1 < NCHH) {
+              tmem_ld16_nowait(a0 + (uint32_t)((i + 1) * 16), v[(i + 1) & 1]);
+            } else {
+              tc_fence_before();
+              mbar_arrive(eb);
+              if (warp == kCtrlWarps) CTRACE(2, it, 2);
             }
+            epi_chunk<COUT, RESID, true, 2>(p, hw, v[i & 1], cb + i * 16, grow0 + hh * 128, true, sb, hacc[0]);
           }
-          uint4 ov;
-          __half2* oh = reinterpret_cast<__half2*>(&ov);
-          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+          const int rows[1] = {r};
+          head_finish<1, 2>(p, hw, hacc, sx + (uint32_t)(hh * 128 * 6 * 4), 1 + q * 2 + hh, q, lane, cc, tile, rows);
+        };
+        if (cc == 0) body(0); else body(COUT / 2);
+      } else {
+        uint32_t v[2][32];
+        float hacc[6];
+        tmem_ld32(acc_base + cbase, v[0]);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-            if (p.relu) h = __hmax2(h, zero2);
-            oh[k] = h;
+        for (int i = 0; i < NCH; ++i) {
+          const int half = i / CHUNKS, c0 = cbase + (i % CHUNKS) * 32;
+          tmem_ld_wait_regs(v[i & 1]);
+          if (i + 1 < NCH) {
+            tmem_ld32(acc_base + (uint32_t)(cbase + ((i + 1) / CHUNKS) * COUT + ((i + 1) % CHUNKS) * 32), v[(i + 1) & 1]);
+          } else {
+            // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
+            tc_fence_before();
+            mbar_arrive(eb);
+            if (warp == kCtrlWarps) CTRACE(2, it, 2);
           }
-          if (!valid) ov = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(p.out + idx) = ov;
+          const int r = half * 128 + q * 32 + lane;
+          const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
+          epi_chunk<COUT, RESID, false, 4>(p, hw, v[i & 1], c0, grow0 + half * 128, valid, sb, hacc);
         }
       }
       if (warp == kCtrlWarps) CTRACE(2, it, 3);
@@ -351,8 +508,9 @@ constexpr int kSlab2Rows = 128 + 2 * 17;
 constexpr int kSlab2GroupBytes = kSlab2Rows * 16;
 constexpr int kTps2 = 3;  // taps per B stage
 
-template <int COUT, int KC, bool RESID>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3x3_tc2(ConvParams p) {
+template <int COUT, int KC, bool RESID, bool HEAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ HeadArg<HEAD> hw) {
   constexpr int TPS = kTps2;
   constexpr int STAGES_PER_KC = 9 / TPS;
   constexpr int ACC_STAGES = 2;
@@ -380,6 +538,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
   float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [COUT], float4 reads
+  float* s_hx = s_bias + COUT;          // HEAD: [NCG-1][128][NR*6] partial exchange between the warps of a lane quarter
 
   const int n_tiles = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -551,62 +710,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3
       if (!ok) break;
       if (warp == kCtrlWarps) CTRACE(2, it, 1);
       tc_fence_after();
-      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * COUT + cbase);
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * COUT);
       const int r = (int)rank * 128 + q * 32 + lane;
       const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
       const long long grow = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + r;
-      uint32_t v[2][32];
-      tmem_ld32(acc, v[0]);
+      const uint32_t sb = smem_u32(s_bias), sx = smem_u32(s_hx);
+      auto body = [&](const int cb) {
+        uint32_t v[2][32];
+        float hacc[1][6];
+        if (HEAD) {
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int c0 = cbase + i * 32;
-        tmem_ld_wait_regs(v[i & 1]);
-        if (i + 1 < NCH) {
-          tmem_ld32(acc + (uint32_t)((i + 1) * 32), v[(i + 1) & 1]);
-        } else {
-          // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(empty_remote + (uint32_t)(as * 8));
-          if (warp == kCtrlWarps) CTRACE(2, it, 2);
+          for (int o = 0; o < 6; ++o) hacc[0][o] = 0.f;
         }
+        tmem_ld32(acc + cb, v[0]);
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const int c = c0 + gi * 8;
-          const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
-          float f[8];
-          f[0] = __uint_as_float(v[i & 1][gi * 8 + 0]) + b0.x;
-          f[1] = __uint_as_float(v[i & 1][gi * 8 + 1]) + b0.y;
-          f[2] = __uint_as_float(v[i & 1][gi * 8 + 2]) + b0.z;
-          f[3] = __uint_as_float(v[i & 1][gi * 8 + 3]) + b0.w;
-          f[4] = __uint_as_float(v[i & 1][gi * 8 + 4]) + b1.x;
-          f[5] = __uint_as_float(v[i & 1][gi * 8 + 5]) + b1.y;
-          f[6] = __uint_as_float(v[i & 1][gi * 8 + 6]) + b1.z;
-          f[7] = __uint_as_float(v[i & 1][gi * 8 + 7]) + b1.w;
-          if (RESID) {
-            uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float2 t = __half22float2(rh[k]);
-              f[2 * k] += t.x;
-              f[2 * k + 1] += t.y;
-            }
+        for (int i = 0; i < NCH; ++i) {
+          const int c0 = cb + i * 32;
+          tmem_ld_wait_regs(v[i & 1]);
+          if (i + 1 < NCH) {
+            tmem_ld32(acc + (uint32_t)(cb + (i + 1) * 32), v[(i + 1) & 1]);
+          } else {
+            // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(empty_remote + (uint32_t)(as * 8));
+            if (warp == kCtrlWarps) CTRACE(2, it, 2);
           }
-          uint4 ov;
-          __half2* oh = reinterpret_cast<__half2*>(&ov);
-          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-            if (p.relu) h = __hmax2(h, zero2);
-            oh[k] = h;
-          }
-          if (!valid) ov = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(p.out + idx) = ov;
+          epi_chunk<COUT, RESID, HEAD, 4>(p, hw, v[i & 1], c0, grow, valid, sb, hacc[0]);
         }
+        if constexpr (HEAD) {
+          const int rows[1] = {r};
+          head_finish<1, 2>(p, hw, hacc, sx, 1 + q, q, lane, cbase != 0 ? 1 : 0, tile, rows);
+        }
+      };
+      if constexpr (HEAD) {
+        if (cbase == 0) body(0); else body(NH);
+      } else {
+        body(cbase);
       }
       if (warp == kCtrlWarps) CTRACE(2, it, 3);
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
@@ -626,12 +766,15 @@ struct SmemPlan {
   int ns, nb, bytes;
 };
 
+// HEAD instantiations also hold the partial-exchange slots [2][128][6]
+constexpr int head_smem_bytes(int) { return 2 * 128 * 6 * 4; }
+
 // slabs + B ring + barriers + TMEM slot + bias inside the 227 KB opt-in limit
-SmemPlan plan_smem(int cout, int kc, int nkc) {
+SmemPlan plan_smem(int cout, int kc, int nkc, bool head) {
   const int tps = (cout == 256) ? 1 : 3;
   const int slab = (((kc >> 3) * kSlabGroupBytes) + 127) & ~127;
   const int stage = tps * kc * cout * 2;
-  const int fixed = (2 * kMaxSlabs + 2 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128;
+  const int fixed = (2 * kMaxSlabs + 2 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128 + (head ? head_smem_bytes(cout) : 0);
   const int budget = 227 * 1024 - fixed;
   const int all = nkc * (9 / tps);  // stages that hold the whole layer
   SmemPlan s;
@@ -649,28 +792,10 @@ SmemPlan plan_smem(int cout, int kc, int nkc) {
   return s;
 }
 
-template <int COUT, int KC>
-int launch_t(ap_engine* e, const ConvParams& p, bool resid, int grid, int smem) {
-  if (resid)
-    k_conv3x3_tc<COUT, KC, true><<<grid, kThreads, smem, e->stream>>>(p);
-  else
-    k_conv3x3_tc<COUT, KC, false><<<grid, kThreads, smem, e->stream>>>(p);
-  AP_LAUNCH_CHECK(e);
-  return AP_OK;
-}
-
-template <int COUT, int KC>
-cudaError_t optin_t() {
-  cudaError_t a = cudaFuncSetAttribute(k_conv3x3_tc<COUT, KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaError_t b = cudaFuncSetAttribute(k_conv3x3_tc<COUT, KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  return a != cudaSuccess ? a : b;
-}
-
-
-SmemPlan plan_smem2(int cout, int kc, int nkc) {
+SmemPlan plan_smem2(int cout, int kc, int nkc, bool head) {
   const int slab = (((kc >> 3) * kSlab2GroupBytes) + 127) & ~127;
   const int stage = kTps2 * kc * (cout / 2) * 2;
-  const int fixed = (3 * kMaxSlabs + 3 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128;
+  const int fixed = (3 * kMaxSlabs + 3 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128 + (head ? head_smem_bytes(cout) : 0);
   const int budget = 227 * 1024 - fixed;
   const int all = nkc * (9 / kTps2);
   SmemPlan s;
@@ -688,28 +813,55 @@ SmemPlan plan_smem2(int cout, int kc, int nkc) {
   return s;
 }
 
-template <int COUT, int KC>
-int launch2_t(ap_engine* e, const ConvParams& p, bool resid, int grid, int smem) {
-  if (resid)
-    k_conv3x3_tc2<COUT, KC, true><<<grid, kThreads, smem, e->stream>>>(p);
-  else
-    k_conv3x3_tc2<COUT, KC, false><<<grid, kThreads, smem, e->stream>>>(p);
+template <int COUT, int KC, bool RESID, bool HEAD>
+int launch1(ap_engine* e, const ConvParams& p, const HeadArg<HEAD>& hw, int grid, int smem) {
+  k_conv3x3_tc<COUT, KC, RESID, HEAD><<<grid, EpiCfg<HEAD>::THREADS, smem, e->stream>>>(p, hw);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+template <int COUT, int KC, bool RESID, bool HEAD>
+int launch2(ap_engine* e, const ConvParams& p, const HeadArg<HEAD>& hw, int grid, int smem) {
+  k_conv3x3_tc2<COUT, KC, RESID, HEAD><<<grid, kThreads, smem, e->stream>>>(p, hw);
   AP_LAUNCH_CHECK(e);
   return AP_OK;
 }
 
 template <int COUT, int KC>
-cudaError_t optin2_t() {
-  cudaError_t a = cudaFuncSetAttribute(k_conv3x3_tc2<COUT, KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaError_t b = cudaFuncSetAttribute(k_conv3x3_tc2<COUT, KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  return a != cudaSuccess ? a : b;
+int launch_t(ap_engine* e, const ConvParams& p, bool resid, bool pair, int grid, int smem) {
+  const HeadArg<false> none{};
+  if (pair)
+    return resid ? launch2<COUT, KC, true, false>(e, p, none, grid, smem) : launch2<COUT, KC, false, false>(e, p, none, grid, smem);
+  return resid ? launch1<COUT, KC, true, false>(e, p, none, grid, smem) : launch1<COUT, KC, false, false>(e, p, none, grid, smem);
+}
+
+template <int COUT, int KC>
+cudaError_t optin_t() {
+  const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  const int lim = 227 * 1024;
+  cudaError_t r = cudaFuncSetAttribute(k_conv3x3_tc<COUT, KC, true, false>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<COUT, KC, false, false>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc2<COUT, KC, true, false>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc2<COUT, KC, false, false>, a, lim);
+  return r;
+}
+
+// HEAD instantiations: the last trunk layer of the simple net (256 -> 256, no residual) and of the
+// residual net (128 -> 128 with residual)
+cudaError_t optin_head() {
+  const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  const int lim = 227 * 1024;
+  cudaError_t r = cudaFuncSetAttribute(k_conv3x3_tc<256, 64, false, true>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc2<256, 64, false, true>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 64, true, true>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc2<128, 64, true, true>, a, lim);
+  return r;
 }
 
 }  // namespace
 
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb) {
   const int kc = L.cin_pad < 64 ? L.cin_pad : 64;
-  SmemPlan s = plan_smem(L.cout, kc, L.cin_pad / kc);
+  SmemPlan s = plan_smem(L.cout, kc, L.cin_pad / kc, false);
   if (out_nb) *out_nb = s.nb;
   return s.bytes;
 }
@@ -717,6 +869,12 @@ int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb) {
 bool conv_tc_supported(int cin_pad, int cout) {
   const int kc = cin_pad < 64 ? cin_pad : 64;
   return (cout == 64 || cout == 128 || cout == 256) && (kc == 16 || kc == 64) && cin_pad % kc == 0;
+}
+
+// can this layer run the fused head epilogue?
+bool conv_tc_head_supported(const ConvLayer& L) {
+  if (L.cin_pad < 64 || L.cin_pad % 64) return false;
+  return (L.cout == 256 && L.resid_buf < 0) || (L.cout == 128 && L.resid_buf >= 0);
 }
 
 // per-device opt-in to > 48 KB dynamic shared memory for every instantiation (called from ap_net_load)
@@ -727,16 +885,11 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, (optin_t<128, 64>()));
   AP_CUDA(e, (optin_t<256, 16>()));
   AP_CUDA(e, (optin_t<256, 64>()));
-  AP_CUDA(e, (optin2_t<64, 16>()));
-  AP_CUDA(e, (optin2_t<64, 64>()));
-  AP_CUDA(e, (optin2_t<128, 16>()));
-  AP_CUDA(e, (optin2_t<128, 64>()));
-  AP_CUDA(e, (optin2_t<256, 16>()));
-  AP_CUDA(e, (optin2_t<256, 64>()));
+  AP_CUDA(e, optin_head());
   return AP_OK;
 }
 
-int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev) {
+int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev, bool head) {
   ConvParams p;
   p.in = (L.in_buf < 0) ? n->feat : n->act[L.in_buf];
   p.out = n->act[L.out_buf];
@@ -752,43 +905,46 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   p.W = n->W;
   p.H = n->H;
   p.errflag = n->d_err;
+  p.ha = n->fc_a;
+  p.ha_rows = n->fc_rows;
+  p.ha_kg = n->fc_kp / 8;
 #ifdef AP_CONV_TRACE
   p.trace = g_conv_trace;
 #endif
   if (!conv_tc_supported(L.cin_pad, L.cout)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
+  if (head && !conv_tc_head_supported(L)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: no fused-head instantiation for this layer");
   const bool resid = p.resid != nullptr;
   // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks); the
   // memory-bound small layers and the L2-bound 256->256 layer run the single-CTA kernel
-  const bool pair = n->conv_mode == 2 || (n->conv_mode == 0 && L.cin_pad == 128);
+  const bool pair = n->conv_mode == 2 || (n->conv_mode == 0 && (L.cin_pad == 128 || (head && n->head_pair)));
+  SmemPlan s;
+  int grid;
   if (pair) {
     // CTA pairs: one board per cluster of two
     p.wimg = L.wimg2;
-    const SmemPlan s = plan_smem2(L.cout, kc, p.nkc);
-    p.ns = s.ns;
-    p.nb = s.nb;
+    s = plan_smem2(L.cout, kc, p.nkc, head);
     const int pairs = n->sm_count / 2;
-    const int grid = 2 * (n_boards < pairs ? n_boards : pairs);
-    switch (L.cout * 100 + kc) {
-      case 64 * 100 + 16: return launch2_t<64, 16>(e, p, resid, grid, s.bytes);
-      case 64 * 100 + 64: return launch2_t<64, 64>(e, p, resid, grid, s.bytes);
-      case 128 * 100 + 16: return launch2_t<128, 16>(e, p, resid, grid, s.bytes);
-      case 128 * 100 + 64: return launch2_t<128, 64>(e, p, resid, grid, s.bytes);
-      case 256 * 100 + 16: return launch2_t<256, 16>(e, p, resid, grid, s.bytes);
-      case 256 * 100 + 64: return launch2_t<256, 64>(e, p, resid, grid, s.bytes);
-    }
-    return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
+    grid = 2 * (n_boards < pairs ? n_boards : pairs);
+  } else {
+    s = plan_smem(L.cout, kc, p.nkc, head);
+    grid = n_boards < n->sm_count ? n_boards : n->sm_count;
   }
-  const SmemPlan s = plan_smem(L.cout, kc, p.nkc);
   p.ns = s.ns;
   p.nb = s.nb;
-  const int grid = n_boards < n->sm_count ? n_boards : n->sm_count;
+  if (head) {
+    HeadArg<true> hw;
+    hw.h = n->head_w;  // host copy of the folded 1x1 weights (refreshed by net_prep), passed in the constant bank
+    if (L.cout == 256)
+      return pair ? launch2<256, 64, false, true>(e, p, hw, grid, s.bytes) : launch1<256, 64, false, true>(e, p, hw, grid, s.bytes);
+    return pair ? launch2<128, 64, true, true>(e, p, hw, grid, s.bytes) : launch1<128, 64, true, true>(e, p, hw, grid, s.bytes);
+  }
   switch (L.cout * 100 + kc) {
-    case 64 * 100 + 16: return launch_t<64, 16>(e, p, resid, grid, s.bytes);
-    case 64 * 100 + 64: return launch_t<64, 64>(e, p, resid, grid, s.bytes);
-    case 128 * 100 + 16: return launch_t<128, 16>(e, p, resid, grid, s.bytes);
-    case 128 * 100 + 64: return launch_t<128, 64>(e, p, resid, grid, s.bytes);
-    case 256 * 100 + 16: return launch_t<256, 16>(e, p, resid, grid, s.bytes);
-    case 256 * 100 + 64: return launch_t<256, 64>(e, p, resid, grid, s.bytes);
+    case 64 * 100 + 16: return launch_t<64, 16>(e, p, resid, pair, grid, s.bytes);
+    case 64 * 100 + 64: return launch_t<64, 64>(e, p, resid, pair, grid, s.bytes);
+    case 128 * 100 + 16: return launch_t<128, 16>(e, p, resid, pair, grid, s.bytes);
+    case 128 * 100 + 64: return launch_t<128, 64>(e, p, resid, pair, grid, s.bytes);
+    case 256 * 100 + 16: return launch_t<256, 16>(e, p, resid, pair, grid, s.bytes);
+    case 256 * 100 + 64: return launch_t<256, 64>(e, p, resid, pair, grid, s.bytes);
   }
   return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
 }

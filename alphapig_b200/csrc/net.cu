@@ -166,7 +166,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 // hbuf [nb][6][S] fp32, pixel index p = y*W + x in tensor coordinates (Flatten order C,H,W).
 __global__ void __launch_bounds__(256)
 k_head_conv(const __half* __restrict__ act, long long mpad, int cfin, int W, int H, HeadParams h,
-            float* __restrict__ hbuf) {
+            float* __restrict__ hbuf, __half* __restrict__ fc_a, long long fc_rows, int fc_kg) {
   extern __shared__ __align__(16) float sh[];
   float* s_w = sh;  // [6][cfin]
   const int tid = threadIdx.x, b = blockIdx.x, S = W * H;
@@ -203,7 +203,18 @@ k_head_conv(const __half* __restrict__ act, long long mpad, int cfin, int W, int
   }
   const int p = y * W + x;
 #pragma unroll
-  for (int o = 0; o < 6; ++o) hbuf[((size_t)b * 6 + o) * S + p] = fmaxf(acc[o] + h.b1x1[o], 0.f);
+  for (int o = 0; o < 6; ++o) {
+    const float v = fmaxf(acc[o] + h.b1x1[o], 0.f);
+    if (fc_a) {  // split-fp16 A operand of the tensor-core FC (heads_tc.cu)
+      const __half hi = __float2half_rn(v);
+      const int k = o * S + p;
+      const long long at = ((long long)(k >> 3) * fc_rows + b) * 8 + (k & 7);
+      fc_a[at] = hi;
+      fc_a[(long long)fc_kg * fc_rows * 8 + at] = __float2half_rn(v - __half2float(hi));
+    } else {
+      hbuf[((size_t)b * 6 + o) * S + p] = v;
+    }
+  }
 }
 
 // (B) FC(4S->S)+softmax and FC(2S->1)+tanh for FC_HB boards per CTA.  The policy FC is a
@@ -410,6 +421,12 @@ static int net_prep(ap_engine* e) {
   }
   k_prep_heads<<<256, 256, 0, e->stream>>>(n->master, n->head, n->S);
   AP_LAUNCH_CHECK(e);
+  AP_TRY(fc_tc_prep(e, n));
+  // host copy of the folded 1x1 weights for the fused-head conv kernels (kernel-parameter constants)
+  memset(&n->head_w, 0, sizeof(n->head_w));
+  AP_CUDA(e, cudaMemcpyAsync(n->head_w.w, n->head.w1x1, (size_t)6 * n->head.cfin * 4, cudaMemcpyDeviceToHost, e->stream));
+  AP_CUDA(e, cudaMemcpyAsync(n->head_w.b, n->head.b1x1, 6 * 4, cudaMemcpyDeviceToHost, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
   return AP_OK;
 }
 
@@ -458,6 +475,8 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   n->S = e->geo.S;
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device);
   if (const char* m = getenv("AP_CONV_MODE")) n->conv_mode = (m[0] == '1') ? 1 : (m[0] == '2') ? 2 : 0;
+  if (const char* m = getenv("AP_HEAD_PAIR")) n->head_pair = m[0] != '0';
+  if (const char* m = getenv("AP_HEAD_MODE")) n->head_mode = (m[0] == '0') ? 0 : (m[0] == '1') ? 1 : 2;
   long long total = 0;
   for (int i = 0; i < n_tensors; ++i) {
     n->names.push_back(tensors[i].name);
@@ -578,6 +597,13 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if (cudaFuncSetAttribute(k_head_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
     return bad(ap_fail(e, AP_ERR_CUDA, "cudaFuncSetAttribute(k_head_fc)"));
   if ((rc = nalloc(e, n, (void**)&n->hbuf, (size_t)n->bcap * 6 * S * 4)) != AP_OK) return bad(rc);
+  fc_tc_dims(S, &n->fc_kp, &n->fc_np);
+  n->fc_rows = ((long long)n->bcap + 127) / 128 * 128;
+  if ((rc = nalloc(e, n, (void**)&n->fc_a, (size_t)2 * (n->fc_kp / 8) * n->fc_rows * 16)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&n->fc_w, (size_t)2 * (n->fc_kp / 8) * n->fc_np * 16)) != AP_OK) return bad(rc);
+  if ((rc = nalloc(e, n, (void**)&n->fc_bias, (size_t)n->fc_np * 4)) != AP_OK) return bad(rc);
+  if ((rc = fc_tc_configure(e, n)) != AP_OK) return bad(rc);
+  if (n->head_mode == 2 && !conv_tc_head_supported(n->trunk.back())) n->head_mode = 1;
   if ((rc = net_prep(e)) != AP_OK) return bad(rc);
   AP_CUDA(e, cudaStreamSynchronize(e->stream));
   return AP_OK;
@@ -616,18 +642,26 @@ int net_phase_count(ap_engine* e) { return e->net ? (int)e->net->trunk.size() + 
 
 static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values) {
   NetState* n = e->net;
-  for (auto& L : n->trunk) {
-    AP_TRY(conv_tc_launch(e, n, L, nb));
+  const size_t last = n->trunk.size() - 1;
+  for (size_t i = 0; i < n->trunk.size(); ++i) {
+    // head_mode 2: the last trunk layer also computes the two 1x1 head convs and never stores its own output
+    AP_TRY(conv_tc_launch(e, n, n->trunk[i], nb, nullptr, n->head_mode == 2 && i == last));
     prof_mark(e);
   }
   const int S = n->S;
-  k_head_conv<<<nb, 256, (size_t)6 * n->head.cfin * 4, e->stream>>>(n->act[n->final_buf], n->mpad, n->head.cfin, n->W,
-                                                                  n->H, n->head, n->hbuf);
-  AP_LAUNCH_CHECK(e);
-  size_t smem = (size_t)(2 * FC_KC * FC_NPAD + FC_HB * 6 * S + FC_HB * FC_NPAD) * 4 + 16;
-  k_head_fc<<<(nb + FC_HB - 1) / FC_HB, FC_THREADS, smem, e->stream>>>(n->hbuf, S, nb, n->head, d_probs, d_values);
-  AP_LAUNCH_CHECK(e);
-  return AP_OK;
+  if (n->head_mode != 2) {
+    k_head_conv<<<nb, 256, (size_t)6 * n->head.cfin * 4, e->stream>>>(n->act[n->final_buf], n->mpad, n->head.cfin, n->W,
+                                                                    n->H, n->head, n->hbuf, n->head_mode ? n->fc_a : nullptr,
+                                                                    n->fc_rows, n->fc_kp / 8);
+    AP_LAUNCH_CHECK(e);
+  }
+  if (n->head_mode == 0) {
+    size_t smem = (size_t)(2 * FC_KC * FC_NPAD + FC_HB * 6 * S + FC_HB * FC_NPAD) * 4 + 16;
+    k_head_fc<<<(nb + FC_HB - 1) / FC_HB, FC_THREADS, smem, e->stream>>>(n->hbuf, S, nb, n->head, d_probs, d_values);
+    AP_LAUNCH_CHECK(e);
+    return AP_OK;
+  }
+  return fc_tc_launch(e, n, nb, d_probs, d_values);
 }
 
 // fp32 path on dense NCHW states (device) for nb <= bcap_ref boards

@@ -35,6 +35,12 @@ struct HeadParams {
   float* fcv_bias = nullptr;
 };
 
+// host copy of the scale-folded 1x1 head-conv weights, passed BY VALUE to the fused-head conv kernels
+struct NetHeadW {
+  float w[6 * 256];  // [6][cfin] (cfin <= 256): 4 policy + 2 value output channels
+  float b[6];
+};
+
 struct NetState {
   int arch = 0, n_blocks = 0, n_filter = 0;
   int W = 0, H = 0, S = 0;
@@ -50,7 +56,15 @@ struct NetState {
   __half* feat = nullptr;      // [2][mpad][8]
   __half* act[3] = {nullptr, nullptr, nullptr};  // [32][mpad][8]
   int final_buf = 0;
-  float* hbuf = nullptr;  // [bcap][6][S] fp32 outputs of the two 1x1 head convs
+  float* hbuf = nullptr;  // [bcap][6][S] fp32 outputs of the two 1x1 head convs (legacy fp32 FC path only)
+  // tensor-core FC heads (heads_tc.cu): split-fp16 operands
+  __half* fc_a = nullptr;    // [2 (hi,lo)][fc_kp/8][fc_rows][8]  head-conv outputs, k = o*S + pixel
+  __half* fc_w = nullptr;    // [2][fc_kp/8][fc_np][8]
+  float* fc_bias = nullptr;  // [fc_np]
+  long long fc_rows = 0;     // bcap rounded up to 128
+  int fc_kp = 0, fc_np = 0;  // 6S rounded up to the K stage; S+1 rounded up to 16
+  int head_mode = 2;         // 0 = fp32 CUDA-core FC (legacy), 1 = k_head_conv + tensor-core FC, 2 = head convs fused into
+                             // the last trunk epilogue + tensor-core FC; AP_HEAD_MODE overrides for A/B timing
   // fp32 CUDA-core reference path
   float* ref_a = nullptr;  // [bcap_ref][256][S]
   float* ref_b = nullptr;
@@ -59,12 +73,22 @@ struct NetState {
   int bcap_ref = 0;
   int sm_count = 148;
   int conv_mode = 0;  // 0 = per-layer choice, 1 = single-CTA kernel, 2 = CTA-pair kernel (cta_group::2); AP_CONV_MODE overrides for A/B timing
+  NetHeadW head_w;
+  int head_pair = 1;  // run the fused-head layer on the CTA-pair kernel (measured faster: its double-buffered TMEM hides
+                      // the longer epilogue); AP_HEAD_PAIR=0 selects the single-CTA kernel for A/B timing
   int* d_err = nullptr;
   std::vector<void*> allocs;
 };
 
 // conv_tc.cu
-int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev = nullptr);
+int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev = nullptr,
+                   bool head = false);
+bool conv_tc_head_supported(const ConvLayer& L);
 bool conv_tc_supported(int cin_pad, int cout);
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb);
 int conv_tc_configure(ap_engine* e);
+// heads_tc.cu
+void fc_tc_dims(int S, int* kp, int* np);
+int fc_tc_configure(ap_engine* e, NetState* n);
+int fc_tc_prep(ap_engine* e, NetState* n);
+int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_values);

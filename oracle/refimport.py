@@ -23,7 +23,7 @@ _cache = {}
 
 
 def load():
-    """-> namespace with Board, Game, Game_AI, mcts_alphaZero, mcts_pure."""
+    """-> namespace with Board, Game, Game_AI, mcts_alphaZero, mcts_pure, train_mxnet / TrainPipeline."""
     if _cache:
         return _cache["ns"]
     if not available():
@@ -39,7 +39,10 @@ def load():
         sg.get_data_from_files = lambda file_name, sgf_home: _cache["sgf"][file_name]
         cl = types.ModuleType("utils.config_loader")
         cl.config_ = {"train_logging": {"version": 1}}
-        u.sgf_dataIter, u.config_loader = sg, cl
+        se = types.ModuleType("utils.send_email")
+        se.send_mail = lambda *a, **k: None
+        u.sgf_dataIter, u.config_loader, u.send_email = sg, cl, se
+        sys.modules["utils.send_email"] = se
         sys.modules["utils"] = u
         sys.modules["utils.sgf_dataIter"] = sg
         sys.modules["utils.config_loader"] = cl
@@ -53,8 +56,16 @@ def load():
         import game_ai
         import mcts_alphaZero
         import mcts_pure
+        # train_mxnet.py:22 overwrites CUDA_VISIBLE_DEVICES at import time: put the caller's value back
+        cvd = os.environ.get("CUDA_VISIBLE_DEVICES")
+        import train_mxnet
+        if cvd is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = cvd
     ns = types.SimpleNamespace(
         Board=game.Board, Game=game.Game, Game_AI=game_ai.Game_AI, game=game, game_ai=game_ai,
-        mcts_alphaZero=mcts_alphaZero, mcts_pure=mcts_pure, sgf_records=_cache["sgf"])
+        mcts_alphaZero=mcts_alphaZero, mcts_pure=mcts_pure, train_mxnet=train_mxnet,
+        TrainPipeline=train_mxnet.TrainPipeline, sgf_records=_cache["sgf"])
     _cache["ns"] = ns
     return ns

@@ -49,6 +49,32 @@ def test_net_forward_vs_oracle(W, arch, nblk):
     eng.close()
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("W,arch,nblk,nst", [(15, "simple", 0, 300), (8, "simple", 0, 130), (15, "resnet", 2, 140),
+                                             (6, "simple", 0, 20)])
+def test_net_head_modes(monkeypatch, mode, W, arch, nblk, nst):
+    """The three head implementations (fp32 CUDA-core FC; split-fp16 tensor-core FC fed by k_head_conv; head convs
+    fused into the last trunk epilogue) against the oracle, on batches that are not a multiple of the 128-board
+    FC tile and span several tiles."""
+    monkeypatch.setenv("AP_HEAD_MODE", mode)
+    n_row = 5 if W >= 8 else 4
+    arg, aux = onet.init_params(arch, W, W, seed=2, n_blocks=nblk)
+    boards = [oboard_from(W, W, n_row, synth_position(W, W, n_row, 500 + g, 31 if W == 15 else 6)) for g in range(nst)]
+    st = np.stack([np.ascontiguousarray(b.current_state()) for b in boards]).astype(np.float32)
+    ref_p, ref_v = onet.forward(arg, aux, st, arch, n_blocks=nblk)
+    eng = _engine(width=W, height=W, n_in_row=n_row, n_games=4)
+    eng.net_load(arch, _merged(arg, aux), n_blocks=nblk)
+    for rep in range(2):  # second pass: stale operand rows of the first must not leak
+        sub = st if rep == 0 else st[: nst // 3]
+        p, v = eng.net_forward(sub)
+        dlp = np.abs(np.log(p) - np.log(ref_p[: len(sub)])).max()
+        dv = np.abs(v - ref_v[: len(sub)]).max()
+        print("mode %s arch %s W %d: max|dlogp| %.3e max|dv| %.3e" % (mode, arch, W, dlp, dv))
+        assert np.allclose(p.sum(1), 1.0, atol=1e-5)
+        assert dlp <= TOL and dv <= TOL
+    eng.close()
+
+
 def test_net_on_leaf_boards_and_policy_value_fn_order():
     """Features emitted on device from bitboards feed the net: same result as the host-state path,
     and probabilities line up with move indices (policy_value_net_mxnet_simple.py:207-226)."""

@@ -123,3 +123,93 @@ def test_sgf_replay_live():
     ref.sgf_records["bad.sgf"] = {"winner": 1, "seq_num_list": [3, 3]}
     assert ref.Game(a).start_self_play(P(), sgf_home=".", file_name="bad.sgf") == (1, None, None)
     assert osp.sgf_self_play(b, P(), {"winner": 1, "seq_num_list": [3, 3]}) == (1, None, None)
+
+
+# ---- TrainPipeline data path: augmentation, replay sampling, policy_update ----
+class _FakeNet(object):
+    """Deterministic stand-in for PolicyValueNet: probabilities drift with every train_step so the KL
+    early-stop / lr-multiplier branches are all reachable."""
+
+    def __init__(self, S, drift):
+        self.S, self.drift, self.steps, self.lrs = S, drift, 0, []
+
+    def policy_value(self, state_batch):
+        B = len(state_batch)
+        base = np.stack([np.asarray(s, dtype=np.float64).reshape(9, -1).sum(0) for s in state_batch])
+        logits = base + self.drift * self.steps * np.linspace(-1, 1, self.S)[None, :]
+        e = np.exp(logits - logits.max(1, keepdims=True))
+        return e / e.sum(1, keepdims=True), np.tanh(base.mean(1, keepdims=True) - 0.3 + 0.1 * self.steps)
+
+    def train_step(self, state_batch, mcts_probs, winner_batch, lr):
+        self.steps += 1
+        self.lrs.append(lr)
+        return np.array([1.0 / self.steps]), np.array([2.0 + self.steps])
+
+
+def _fake_play_data(H, W, n, seed):
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        st = (rs.rand(9, H, W) < 0.3).astype(np.float64)
+        pi = rs.dirichlet(np.ones(H * W))
+        out.append((st, pi, float(rs.choice([-1.0, 0.0, 1.0]))))
+    return out
+
+
+def test_equi_data_live():
+    from oracle import pipeline as opl
+    ref = refimport.load()
+    import types
+    for H in (6, 15):
+        data = _fake_play_data(H, H, 3, H)
+        a = ref.TrainPipeline.get_equi_data(types.SimpleNamespace(board_height=H, board_width=H), data)
+        b = opl.equi_data(data, H, H)
+        assert len(a) == len(b) == 24
+        for (sa, pa_, za), (sb, pb_, zb) in zip(a, b):
+            assert np.array_equal(sa, sb) and np.array_equal(pa_, pb_) and za == zb
+
+
+@pytest.mark.parametrize("drift,mult0", [(0.0, 1.0), (0.05, 1.0), (0.6, 1.0), (3.0, 0.04), (0.0, 25.0)])
+def test_policy_update_live(drift, mult0):
+    """Reference TrainPipeline.policy_update driven with a fake net vs the oracle restatement: same
+    minibatch (random.sample), same number of epochs, same lr multiplier."""
+    from collections import deque
+    import types
+    from oracle import pipeline as opl
+    ref = refimport.load()
+    H = 6
+    games = [_fake_play_data(H, H, 5, 100 + g) for g in range(4)]
+    rep = opl.ReplayDeque(150, H, H)
+    dq = deque(maxlen=150)
+    for g in games:
+        rep.extend_game(g)
+        dq.extend(ref.TrainPipeline.get_equi_data(types.SimpleNamespace(board_height=H, board_width=H), g))
+    assert len(rep) == len(dq) == 150
+    na, nb = _FakeNet(H * H, drift), _FakeNet(H * H, drift)
+    me = types.SimpleNamespace(data_buffer=dq, batch_size=16, policy_value_net=na, learn_rate=2e-3, lr_multiplier=mult0,
+                               epochs=5, kl_targ=0.02)
+    random.seed(3)
+    la, ea = ref.TrainPipeline.policy_update(me)
+    random.seed(3)
+    lb, eb, mult, kl, ran, _, _ = opl.policy_update(nb, rep, 16, 2e-3, mult0, 5, 0.02)
+    assert np.array_equal(la, lb) and np.array_equal(ea, eb)
+    assert me.lr_multiplier == mult and na.steps == nb.steps == ran and na.lrs == nb.lrs
+
+
+def test_policy_evaluate_live():
+    import types
+    from oracle import pipeline as opl
+    ref = refimport.load()
+    seq = [1, 2, -1, 1, 1, 2, 1, -1, 1, 1]
+    calls = []
+
+    class G(object):
+        def start_play(self, p1, p2, start_player=0, is_shown=1):
+            calls.append(start_player)
+            return seq[len(calls) - 1]
+    me = types.SimpleNamespace(policy_value_net=types.SimpleNamespace(policy_value_fn=None), c_puct=5, n_playout=10,
+                               pure_mcts_playout_num=20, game=G())
+    ra = ref.TrainPipeline.policy_evaluate(me, n_games=10)
+    it = iter(seq)
+    rb, cnt = opl.policy_evaluate(lambda a, b, sp: next(it), None, None, 10)
+    assert ra == rb == (6 + 0.5 * 2) / 10 and calls == [0, 1] * 5
