@@ -39,6 +39,11 @@ struct ConvParams {
   __half* out;
   const __half* resid;
   const __half* wimg;
+  // SPLIT instantiations (near-fp32 "hi + lo" fp16 pairs, three tensor-core products per K step):
+  const __half* in_lo;
+  __half* out_lo;
+  const __half* resid_lo;
+  const __half* wimg_lo;
   const float* bias;  // folded BN shift; the BN scale is folded into the fp16 weights
   long long mpad;
   int nkc, relu;
@@ -107,12 +112,32 @@ struct HeadArg<true> {
   NetHeadW h;
 };
 
+// residual operand of one chunk, fetched one chunk ahead of its use (the first one before the accumulator is even
+// complete) so that its HBM latency hides under the TMEM drain instead of serialising the epilogue
+template <int NG, bool SPLIT>
+struct ResidRegs {
+  uint4 hi[NG];
+  uint4 lo[SPLIT ? NG : 1];
+};
+template <bool RESID, int NG, bool SPLIT>
+__device__ __forceinline__ void resid_load(const ConvParams& p, int c0, long long grow, ResidRegs<NG, SPLIT>& r) {
+  if constexpr (RESID) {
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      const long long idx = ((long long)((c0 + gi * 8) >> 3) * p.mpad + grow) * 8;
+      r.hi[gi] = __ldg(reinterpret_cast<const uint4*>(p.resid + idx));
+      if constexpr (SPLIT) r.lo[gi] = __ldg(reinterpret_cast<const uint4*>(p.resid_lo + idx));
+    }
+  }
+}
+
 // one chunk (NG groups of 8 columns) of one accumulator row: +shift (+residual) -> ReLU, then either fp16 store of the
 // activation row (trunk layers) or 6 running dot products with the 1x1 head weights (HEAD; c0 is a compile-time
 // constant after inlining + unrolling, so every weight is an immediate constant-bank operand)
-template <int COUT, bool RESID, bool HEAD, int NG>
+template <int COUT, bool RESID, bool HEAD, int NG, bool SPLIT = false>
 __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEAD>& hw, const uint32_t (&v)[8 * NG], int c0,
-                                          long long grow, bool valid, uint32_t s_bias, float (&hacc)[6]) {
+                                          long long grow, bool valid, uint32_t s_bias, float (&hacc)[6],
+                                          const ResidRegs<NG, SPLIT>& rr) {
 #pragma unroll
   for (int gi = 0; gi < NG; ++gi) {
     const int c = c0 + gi * 8;
@@ -129,13 +154,21 @@ __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEA
     f[6] = __uint_as_float(v[gi * 8 + 6]) + b1.z;
     f[7] = __uint_as_float(v[gi * 8 + 7]) + b1.w;
     if (RESID) {
-      uint4 rv = *reinterpret_cast<const uint4*>(p.resid + idx);
-      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rr.hi[gi]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float2 t = __half22float2(rh[k]);
         f[2 * k] += t.x;
         f[2 * k + 1] += t.y;
+      }
+      if constexpr (SPLIT) {
+        const __half2* rlh = reinterpret_cast<const __half2*>(&rr.lo[gi]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 t = __half22float2(rlh[k]);
+          f[2 * k] += t.x;
+          f[2 * k + 1] += t.y;
+        }
       }
     }
     if constexpr (HEAD) {
@@ -148,6 +181,28 @@ __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEA
 #pragma unroll
         for (int k = 0; k < 8; ++k) hacc[o] = fmaf(f[k], hw.h.w[o * COUT + c + k], hacc[o]);
       }
+    } else if constexpr (SPLIT) {
+      uint4 ov, ol;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+      __half2* olh = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a = f[2 * k], b = f[2 * k + 1];
+        if (p.relu) {
+          a = fmaxf(a, 0.f);
+          b = fmaxf(b, 0.f);
+        }
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        oh[k] = h;
+        olh[k] = __floats2half2_rn(a - hf.x, b - hf.y);
+      }
+      if (!valid) {
+        ov = make_uint4(0u, 0u, 0u, 0u);
+        ol = ov;
+      }
+      *reinterpret_cast<uint4*>(p.out + idx) = ov;
+      *reinterpret_cast<uint4*>(p.out_lo + idx) = ol;
     } else {
       uint4 ov;
       __half2* oh = reinterpret_cast<__half2*>(&ov);
@@ -238,7 +293,7 @@ struct EpiCfg {
   static constexpr int THREADS = 32 * (kCtrlWarps + WARPS);
 };
 
-template <int COUT, int KC, bool RESID, bool HEAD>
+template <int COUT, int KC, bool RESID, bool HEAD, bool SPLIT = false>
 __global__ void __launch_bounds__(EpiCfg<HEAD>::THREADS, 1)
 k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadArg<HEAD> hw) {
   using Cfg = ConvCfg<COUT>;
@@ -248,10 +303,12 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
   constexpr int STAGES_PER_KC = 9 / TPS;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
   constexpr int KG = KC / 8;                              // 8-channel groups per K-chunk
-  constexpr uint32_t SLAB_BYTES = KG * kSlabGroupBytes;   // multiple of 16
+  constexpr uint32_t SLAB_HALF = KG * kSlabGroupBytes;                 // one of hi / lo; multiple of 16
+  constexpr uint32_t SLAB_BYTES = (SPLIT ? 2 : 1) * SLAB_HALF;         // SPLIT: [hi groups][lo groups]
   constexpr uint32_t SLAB_STRIDE = (SLAB_BYTES + 127u) & ~127u;
   constexpr uint32_t TAP_BYTES = (uint32_t)KC * COUT * 2;
-  constexpr uint32_t STAGE_BYTES = TPS * TAP_BYTES;
+  constexpr uint32_t STAGE_HALF = TPS * TAP_BYTES;
+  constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * STAGE_HALF;       // SPLIT: [hi taps][lo taps]
 
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(AP_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -318,6 +375,12 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
           for (int j = 0; j < KG; ++j)
             bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
                      p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+          if constexpr (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < KG; ++j)
+              bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + SLAB_HALF + j * kSlabGroupBytes),
+                       p.in_lo + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+          }
         }
         __syncwarp();
         if (++sl == p.ns) { sl = 0; slph ^= 1; }
@@ -331,7 +394,10 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
           if (elect_one()) {
             mbar_expect_tx(bb, STAGE_BYTES);
             bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES),
-                     p.wimg + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_BYTES, bb);
+                     p.wimg + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
+            if constexpr (SPLIT)
+              bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES + STAGE_HALF),
+                       p.wimg_lo + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
           }
           __syncwarp();
           if (++bs == p.nb) { bs = 0; bph ^= 1; }
@@ -383,6 +449,10 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
                   const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
                   const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
                   tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad, bd, IDESC, (kc | tap | j) != 0);
+                  if constexpr (SPLIT) {  // + a_lo * b_hi + a_hi * b_lo (lo * lo is below fp32 round-off)
+                    tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad + (SLAB_HALF >> 4), bd, IDESC, 1);
+                    tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad, bd + (STAGE_HALF >> 4), IDESC, 1);
+                  }
                 }
               }
             }
@@ -433,6 +503,8 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
         auto body = [&](const int cb) {
           constexpr int NCHH = COUT / 2 / 16;
           const uint32_t a0 = acc_base + (uint32_t)(hh * COUT + cb);
+          ResidRegs<2, SPLIT> rrh[2];
+          resid_load<RESID, 2, SPLIT>(p, cb, grow0 + hh * 128, rrh[0]);
           uint32_t v[2][16];
           float hacc[1][6];
 #pragma unroll
@@ -443,12 +515,13 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
             tmem_ld_wait_regs16(v[i & 1]);
             if (i + 1 < NCHH) {
               tmem_ld16_nowait(a0 + (uint32_t)((i + 1) * 16), v[(i + 1) & 1]);
+              resid_load<RESID, 2, SPLIT>(p, cb + (i + 1) * 16, grow0 + hh * 128, rrh[(i + 1) & 1]);
             } else {
               tc_fence_before();
               mbar_arrive(eb);
               if (warp == kCtrlWarps) CTRACE(2, it, 2);
             }
-            epi_chunk<COUT, RESID, true, 2>(p, hw, v[i & 1], cb + i * 16, grow0 + hh * 128, true, sb, hacc[0]);
+            epi_chunk<COUT, RESID, true, 2, SPLIT>(p, hw, v[i & 1], cb + i * 16, grow0 + hh * 128, true, sb, hacc[0], rrh[i & 1]);
           }
           const int rows[1] = {r};
           head_finish<1, 2>(p, hw, hacc, sx + (uint32_t)(hh * 128 * 6 * 4), 1 + q * 2 + hh, q, lane, cc, tile, rows);
@@ -457,6 +530,8 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
       } else {
         uint32_t v[2][32];
         float hacc[6];
+        ResidRegs<4, SPLIT> rr[2];
+        resid_load<RESID, 4, SPLIT>(p, cbase, grow0, rr[0]);
         tmem_ld32(acc_base + cbase, v[0]);
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
@@ -464,6 +539,7 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
           tmem_ld_wait_regs(v[i & 1]);
           if (i + 1 < NCH) {
             tmem_ld32(acc_base + (uint32_t)(cbase + ((i + 1) / CHUNKS) * COUT + ((i + 1) % CHUNKS) * 32), v[(i + 1) & 1]);
+            resid_load<RESID, 4, SPLIT>(p, cbase + ((i + 1) % CHUNKS) * 32, grow0 + ((i + 1) / CHUNKS) * 128, rr[(i + 1) & 1]);
           } else {
             // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
             tc_fence_before();
@@ -472,7 +548,7 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
           }
           const int r = half * 128 + q * 32 + lane;
           const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
-          epi_chunk<COUT, RESID, false, 4>(p, hw, v[i & 1], c0, grow0 + half * 128, valid, sb, hacc);
+          epi_chunk<COUT, RESID, false, 4, SPLIT>(p, hw, v[i & 1], c0, grow0 + half * 128, valid, sb, hacc, rr[i & 1]);
         }
       }
       if (warp == kCtrlWarps) CTRACE(2, it, 3);
@@ -722,6 +798,8 @@ k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ Head
 #pragma unroll
           for (int o = 0; o < 6; ++o) hacc[0][o] = 0.f;
         }
+        ResidRegs<4, false> rr[2];
+        resid_load<RESID, 4, false>(p, cb, grow, rr[0]);
         tmem_ld32(acc + cb, v[0]);
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
@@ -729,6 +807,7 @@ k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ Head
           tmem_ld_wait_regs(v[i & 1]);
           if (i + 1 < NCH) {
             tmem_ld32(acc + (uint32_t)(cb + (i + 1) * 32), v[(i + 1) & 1]);
+            resid_load<RESID, 4, false>(p, cb + (i + 1) * 32, grow, rr[(i + 1) & 1]);
           } else {
             // the accumulator stage is fully in registers: hand it back before the arithmetic and the stores
             tc_fence_before();
@@ -736,7 +815,7 @@ k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ Head
             if (lane == 0) mbar_arrive_cluster_relaxed(empty_remote + (uint32_t)(as * 8));
             if (warp == kCtrlWarps) CTRACE(2, it, 2);
           }
-          epi_chunk<COUT, RESID, HEAD, 4>(p, hw, v[i & 1], c0, grow, valid, sb, hacc[0]);
+          epi_chunk<COUT, RESID, HEAD, 4>(p, hw, v[i & 1], c0, grow, valid, sb, hacc[0], rr[i & 1]);
         }
         if constexpr (HEAD) {
           const int rows[1] = {r};
@@ -770,10 +849,11 @@ struct SmemPlan {
 constexpr int head_smem_bytes(int) { return 2 * 128 * 6 * 4; }
 
 // slabs + B ring + barriers + TMEM slot + bias inside the 227 KB opt-in limit
-SmemPlan plan_smem(int cout, int kc, int nkc, bool head) {
+SmemPlan plan_smem(int cout, int kc, int nkc, bool head, bool split = false) {
   const int tps = (cout == 256) ? 1 : 3;
-  const int slab = (((kc >> 3) * kSlabGroupBytes) + 127) & ~127;
-  const int stage = tps * kc * cout * 2;
+  const int mul = split ? 2 : 1;
+  const int slab = ((mul * (kc >> 3) * kSlabGroupBytes) + 127) & ~127;
+  const int stage = mul * tps * kc * cout * 2;
   const int fixed = (2 * kMaxSlabs + 2 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128 + (head ? head_smem_bytes(cout) : 0);
   const int budget = 227 * 1024 - fixed;
   const int all = nkc * (9 / tps);  // stages that hold the whole layer
@@ -845,6 +925,24 @@ cudaError_t optin_t() {
   return r;
 }
 
+// SPLIT instantiations (residual net at near-fp32 accuracy): stem, convA, convB (+residual), last convB with heads
+cudaError_t optin_split() {
+  const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  const int lim = 227 * 1024;
+  cudaError_t r = cudaFuncSetAttribute(k_conv3x3_tc<128, 16, false, false, true>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, false, false, true>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, true, false, true>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, true, true, true>, a, lim);
+  return r;
+}
+
+template <int COUT, int KC, bool RESID, bool HEAD>
+int launch1s(ap_engine* e, const ConvParams& p, const HeadArg<HEAD>& hw, int grid, int smem) {
+  k_conv3x3_tc<COUT, KC, RESID, HEAD, true><<<grid, EpiCfg<HEAD>::THREADS, smem, e->stream>>>(p, hw);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+
 // HEAD instantiations: the last trunk layer of the simple net (256 -> 256, no residual) and of the
 // residual net (128 -> 128 with residual)
 cudaError_t optin_head() {
@@ -872,6 +970,11 @@ bool conv_tc_supported(int cin_pad, int cout) {
 }
 
 // can this layer run the fused head epilogue?
+// K chunk of a layer: the split-precision kernels stage hi + lo of both operands, so they use half the chunk
+int conv_tc_kc(const ConvLayer& L, bool split) { return L.cin_pad < 64 ? L.cin_pad : (split ? 32 : 64); }
+
+bool conv_tc_split_supported(const ConvLayer& L) { return L.cout == 128 && (L.cin_pad == 16 || L.cin_pad % 32 == 0); }
+
 bool conv_tc_head_supported(const ConvLayer& L) {
   if (L.cin_pad < 64 || L.cin_pad % 64) return false;
   return (L.cout == 256 && L.resid_buf < 0) || (L.cout == 128 && L.resid_buf >= 0);
@@ -886,18 +989,24 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, (optin_t<256, 16>()));
   AP_CUDA(e, (optin_t<256, 64>()));
   AP_CUDA(e, optin_head());
+  AP_CUDA(e, optin_split());
   return AP_OK;
 }
 
 int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev, bool head) {
+  const bool split = n->split;
   ConvParams p;
   p.in = (L.in_buf < 0) ? n->feat : n->act[L.in_buf];
   p.out = n->act[L.out_buf];
   p.resid = (L.resid_buf >= 0) ? n->act[L.resid_buf] : nullptr;
   p.wimg = L.wimg;
+  p.in_lo = (L.in_buf < 0) ? n->feat_lo : n->act_lo[L.in_buf];
+  p.out_lo = n->act_lo[L.out_buf];
+  p.resid_lo = (L.resid_buf >= 0) ? n->act_lo[L.resid_buf] : nullptr;
+  p.wimg_lo = L.wimg_lo;
   p.bias = L.shift;
   p.mpad = n->mpad;
-  const int kc = L.cin_pad < 64 ? L.cin_pad : 64;
+  const int kc = conv_tc_kc(L, split);
   p.nkc = L.cin_pad / kc;
   p.relu = L.relu;
   p.n_tiles = n_boards;
@@ -914,8 +1023,26 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   if (!conv_tc_supported(L.cin_pad, L.cout)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
   if (head && !conv_tc_head_supported(L)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: no fused-head instantiation for this layer");
   const bool resid = p.resid != nullptr;
-  // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks); the
-  // memory-bound small layers and the L2-bound 256->256 layer run the single-CTA kernel
+  if (split) {
+    // near-fp32 path of the residual net: single-CTA kernel, three products per K step
+    if (!conv_tc_split_supported(L)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: no split-precision instantiation for this layer");
+    const SmemPlan s = plan_smem(L.cout, kc, p.nkc, head, true);
+    p.ns = s.ns;
+    p.nb = s.nb;
+    const int grid = n_boards < n->sm_count ? n_boards : n->sm_count;
+    const HeadArg<false> none{};
+    if (head) {
+      if (!resid || kc != 32) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: split fused head needs a residual 128-channel layer");
+      HeadArg<true> hw;
+      hw.h = n->head_w;
+      return launch1s<128, 32, true, true>(e, p, hw, grid, s.bytes);
+    }
+    if (kc == 16) return launch1s<128, 16, false, false>(e, p, none, grid, s.bytes);
+    return resid ? launch1s<128, 32, true, false>(e, p, none, grid, s.bytes)
+                 : launch1s<128, 32, false, false>(e, p, none, grid, s.bytes);
+  }
+  // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks, the fused-head
+  // layer); the memory-bound small layers run the single-CTA kernel
   const bool pair = n->conv_mode == 2 || (n->conv_mode == 0 && (L.cin_pad == 128 || (head && n->head_pair)));
   SmemPlan s;
   int grid;

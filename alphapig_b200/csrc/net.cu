@@ -24,7 +24,7 @@
 // ------------------------------------------------------------------------------------------
 __global__ void k_prep_conv(const float* __restrict__ master, long long w, long long b, long long gamma, long long beta,
                             long long mean, long long var, int fix_gamma, int cin, int cin_pad, int cout, int kc,
-                            __half* wimg, __half* wimg2, float* scale, float* shift) {
+                            __half* wimg, __half* wimg2, __half* wimg_lo, float* scale, float* shift) {
   const long long total = (long long)9 * cin_pad * cout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     // image order: [kcI][tap][j][n][e]
@@ -40,7 +40,9 @@ __global__ void k_prep_conv(const float* __restrict__ master, long long w, long 
     float sc = 1.f / sqrtf(master[var + n] + BN_EPS);
     if (!fix_gamma) sc *= master[gamma + n];
     float v = (k < cin) ? master[w + ((long long)n * cin + k) * 9 + tap] * sc : 0.f;  // BN scale folded in fp32
-    wimg[i] = __float2half_rn(v);
+    const __half vh = __float2half_rn(v);
+    wimg[i] = vh;
+    if (wimg_lo) wimg_lo[i] = __float2half_rn(v - __half2float(vh));
     // CTA-pair image: [r][kcI][tap][j][n'][e], n = r*cout/2 + n'
     const int nh = cout >> 1, rr = n / nh, np = n - rr * nh;
     const long long i2 = ((((long long)rr * (cin_pad / kc) + kcI) * 9 + tap) * (kc >> 3) + j) * nh * 8 + (long long)np * 8 + e;
@@ -414,9 +416,9 @@ int net_destroy(ap_engine* e) {
 static int net_prep(ap_engine* e) {
   NetState* n = e->net;
   for (auto& L : n->trunk) {
-    int kc = L.cin_pad < 64 ? L.cin_pad : 64;
+    const int kc = conv_tc_kc(L, n->split);
     k_prep_conv<<<256, 256, 0, e->stream>>>(n->master, L.w, L.b, L.gamma, L.beta, L.mean, L.var, L.fix_gamma, L.cin,
-                                            L.cin_pad, L.cout, kc, L.wimg, L.wimg2, L.scale, L.shift);
+                                            L.cin_pad, L.cout, kc, L.wimg, L.wimg2, L.wimg_lo, L.scale, L.shift);
     AP_LAUNCH_CHECK(e);
   }
   k_prep_heads<<<256, 256, 0, e->stream>>>(n->master, n->head, n->S);
@@ -452,6 +454,7 @@ static int conv_bind(ap_engine* e, NetState* n, ConvLayer& L, const std::string&
   L.cin_pad = (L.cin + 15) & ~15;
   AP_TRY(nalloc(e, n, (void**)&L.wimg, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.wimg2, (size_t)9 * L.cin_pad * L.cout * 2));
+  if (n->split) AP_TRY(nalloc(e, n, (void**)&L.wimg_lo, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.scale, (size_t)L.cout * 4));
   AP_TRY(nalloc(e, n, (void**)&L.shift, (size_t)L.cout * 4));
   return AP_OK;
@@ -463,11 +466,16 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if (!tensors || n_tensors <= 0) return ap_fail(e, AP_ERR_BAD_ARG, "no tensors");
   if (e->geo.W != e->geo.H || e->geo.W > 15)
     return ap_fail(e, AP_ERR_BAD_ARG, "the net path needs a square board of width <= 15");
+  const int split = (arch & AP_NET_SPLIT) != 0;
+  arch &= ~AP_NET_SPLIT;
   if (arch != AP_ARCH_SIMPLE && arch != AP_ARCH_RESNET) return ap_fail(e, AP_ERR_BAD_ARG, "unknown arch");
+  if (split && arch != AP_ARCH_RESNET)
+    return ap_fail(e, AP_ERR_BAD_ARG, "AP_NET_SPLIT is implemented for the residual net only (the 6-conv net meets 1e-3 in fp16)");
   net_destroy(e);
   NetState* n = new NetState();
   e->net = n;
   n->arch = arch;
+  n->split = split;
   n->n_blocks = n_blocks;
   n->n_filter = n_filter;
   n->W = e->geo.W;
@@ -583,6 +591,13 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if ((rc = nalloc(e, n, (void**)&n->feat, (size_t)2 * n->mpad * 16)) != AP_OK) return bad(rc);
   for (int i = 0; i < nbuf; ++i)
     if ((rc = nalloc(e, n, (void**)&n->act[i], (size_t)(maxc / 8) * n->mpad * 16)) != AP_OK) return bad(rc);
+  if (n->split) {
+    if ((rc = nalloc(e, n, (void**)&n->feat_lo, (size_t)2 * n->mpad * 16)) != AP_OK) return bad(rc);
+    for (int i = 0; i < nbuf; ++i)
+      if ((rc = nalloc(e, n, (void**)&n->act_lo[i], (size_t)(maxc / 8) * n->mpad * 16)) != AP_OK) return bad(rc);
+    for (auto& L : n->trunk)
+      if (!conv_tc_split_supported(L)) return bad(ap_fail(e, AP_ERR_BAD_ARG, "split precision: unsupported layer shape"));
+  }
   n->bcap_ref = 128;
   const size_t refb = (size_t)n->bcap_ref * 256 * S * 4;
   if ((rc = nalloc(e, n, (void**)&n->ref_a, refb)) != AP_OK) return bad(rc);
@@ -604,6 +619,8 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if ((rc = nalloc(e, n, (void**)&n->fc_bias, (size_t)n->fc_np * 4)) != AP_OK) return bad(rc);
   if ((rc = fc_tc_configure(e, n)) != AP_OK) return bad(rc);
   if (n->head_mode == 2 && !conv_tc_head_supported(n->trunk.back())) n->head_mode = 1;
+  if (n->split && n->head_mode != 2)
+    return bad(ap_fail(e, AP_ERR_BAD_ARG, "split precision needs the fused head epilogue (n_blocks >= 1, AP_HEAD_MODE=2)"));
   if ((rc = net_prep(e)) != AP_OK) return bad(rc);
   AP_CUDA(e, cudaStreamSynchronize(e->stream));
   return AP_OK;

@@ -18,6 +18,7 @@ struct ConvLayer {
   // prepared (device)
   __half* wimg = nullptr;  // [nkc][9][KC/8][cout][8]
   __half* wimg2 = nullptr; // CTA-pair image [2][nkc][9][KC/8][cout/2][8]: half r holds output channels [r*cout/2, (r+1)*cout/2)
+  __half* wimg_lo = nullptr;  // split precision only: fp16(w - fp16(w)) in the wimg layout (K chunk 32)
   float* scale = nullptr;  // [cout]
   float* shift = nullptr;  // [cout]
 };
@@ -55,6 +56,11 @@ struct NetState {
   HeadParams head;
   __half* feat = nullptr;      // [2][mpad][8]
   __half* act[3] = {nullptr, nullptr, nullptr};  // [32][mpad][8]
+  // split precision (AP_NET_SPLIT): every activation is a hi + lo fp16 pair (22 significant bits), every weight too,
+  // and the conv kernels issue hi*hi + lo*hi + hi*lo: what the 10-block residual net needs to stay within 1e-3
+  int split = 0;
+  __half* feat_lo = nullptr;  // all zero (features are exactly 0/1)
+  __half* act_lo[3] = {nullptr, nullptr, nullptr};
   int final_buf = 0;
   float* hbuf = nullptr;  // [bcap][6][S] fp32 outputs of the two 1x1 head convs (legacy fp32 FC path only)
   // tensor-core FC heads (heads_tc.cu): split-fp16 operands
@@ -84,6 +90,8 @@ struct NetState {
 int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev = nullptr,
                    bool head = false);
 bool conv_tc_head_supported(const ConvLayer& L);
+bool conv_tc_split_supported(const ConvLayer& L);
+int conv_tc_kc(const ConvLayer& L, bool split);
 bool conv_tc_supported(int cin_pad, int cout);
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb);
 int conv_tc_configure(ap_engine* e);

@@ -34,7 +34,7 @@ class PolicyValueNetBase(object):
     arch = "simple"
 
     def __init__(self, board_width, board_height, batch_size=512, n_blocks=8, n_filter=128, model_params=None,
-                 device=0, n_in_row=5, seed=None):
+                 device=0, n_in_row=5, seed=None, precision="auto"):
         self.board_width = board_width
         self.board_height = board_height
         self.batchsize = batch_size
@@ -43,6 +43,7 @@ class PolicyValueNetBase(object):
         self._n_blocks = n_blocks
         self._n_filter = n_filter
         self._device = device
+        self._precision = precision  # see Engine.net_load: "auto" | "fp16" | "split"
         if model_params:
             arg, aux = model_params
             arg = OrderedDict((k, _to_numpy(v)) for k, v in arg.items())
@@ -72,7 +73,7 @@ class PolicyValueNetBase(object):
             merged = OrderedDict(arg)
             merged.update(aux)
         eng.net_load(self.arch, merged, n_blocks=self._n_blocks if self.arch == "resnet" else 0,
-                     n_filter=self._n_filter)
+                     n_filter=self._n_filter, precision=self._precision)
         return eng
 
     def search_engine(self, n_in_row=5, c_puct=5.0, n_playout=400, n_games=1, node_capacity=0):

@@ -129,6 +129,10 @@ typedef struct {
 } ap_tensor;
 #define AP_ARCH_SIMPLE 0 /* policy_value_net_mxnet_simple.py:68-92 */
 #define AP_ARCH_RESNET 1 /* policy_value_net_mxnet.py:70-102       */
+/* OR into `arch` (residual net only): every activation and weight is carried as a hi + lo fp16 pair and the
+ * tensor cores compute hi*hi + lo*hi + hi*lo (near-fp32 accuracy at 3x the MMA work).  The 10-block net of
+ * train_mxnet.py:79-91 needs it to stay within 1e-3 of fp32; plain fp16 operands reach 1.8e-3 there. */
+#define AP_NET_SPLIT 0x100
 /* set_params(arg_params, aux_params)                 policy_value_net_mxnet_simple.py:33-37 */
 int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t n_filter, const ap_tensor* tensors, int32_t n_tensors);
 /* PolicyValueNet.policy_value(state_batch): host fp32 states [B][9][H][W] -> probs [B][S], values [B]   (:178-188) */

@@ -75,6 +75,26 @@ def test_net_head_modes(monkeypatch, mode, W, arch, nblk, nst):
     eng.close()
 
 
+@pytest.mark.parametrize("nblk,precision,tol", [(10, "split", 5e-5), (10, "auto", 5e-5), (3, "split", 5e-5), (10, "fp16", 4e-3)])
+def test_resnet_split_precision(nblk, precision, tol):
+    """The as-trained residual net (10 blocks x 128, train_mxnet.py:79-91): plain fp16 operands drift to ~1.8e-3,
+    the split-precision kernels (hi + lo fp16 pairs, three tensor-core products) stay at fp32 round-off."""
+    W = 15
+    arg, aux = onet.init_params("resnet", W, W, seed=0, n_blocks=nblk)
+    boards, st = _states(W, 150, 1234, 31)
+    ref_p, ref_v = onet.forward(arg, aux, st, "resnet", n_blocks=nblk)
+    eng = _engine(width=W, height=W, n_in_row=5, n_games=4)
+    eng.net_load("resnet", _merged(arg, aux), n_blocks=nblk, precision=precision)
+    assert eng.net_precision == ("fp16" if precision == "fp16" else "split")
+    p, v = eng.net_forward(st)
+    dlp = np.abs(np.log(p) - np.log(ref_p)).max()
+    dv = np.abs(v - ref_v).max()
+    print("resnet-%d %s: max|dlogp| %.3e max|dv| %.3e" % (nblk, precision, dlp, dv))
+    assert dlp <= tol and dv <= tol
+    assert dlp <= TOL or precision == "fp16"
+    eng.close()
+
+
 def test_net_on_leaf_boards_and_policy_value_fn_order():
     """Features emitted on device from bitboards feed the net: same result as the host-state path,
     and probabilities line up with move indices (policy_value_net_mxnet_simple.py:207-226)."""

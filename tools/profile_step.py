@@ -17,13 +17,14 @@ ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--playouts", type=int, default=6)
 ap.add_argument("--arch", default="simple")
 ap.add_argument("--blocks", type=int, default=10)
+ap.add_argument("--precision", default="auto")
 a = ap.parse_args()
 arg, aux = init_params(a.arch, 15, 15, n_blocks=a.blocks, seed=0, synthetic_stats=True)
 merged = dict(arg)
 merged.update(aux)
 eng = Engine(width=15, height=15, n_in_row=5, n_games=a.games, c_puct=5, n_playout=a.playouts,
              node_capacity=a.playouts * 225 + 2)
-eng.net_load(a.arch, merged, n_blocks=a.blocks)
+eng.net_load(a.arch, merged, n_blocks=a.blocks, precision=a.precision)
 bench.synthetic_positions(eng, a.games)
 eng.search_profile(True)
 eng.search_run(a.playouts)
