@@ -72,6 +72,11 @@ SIGNATURES = {
     "ap_search_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ap_search_profile": (C.c_int, [_P, _I, _P, _I]),
     "ap_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "ap_replay_create": (C.c_int, [_P, C.c_int64]),
+    "ap_replay_push": (C.c_int, [_P, _P, _P, _P, _I]),
+    "ap_replay_size": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ap_replay_gather": (C.c_int, [_P, _P, _I, _P, _P, _P, _I]),
+    "ap_replay_push_sgf": (C.c_int, [_P, _P, _I, _P, _P, _I, _P]),
 }
 
 _lib = None

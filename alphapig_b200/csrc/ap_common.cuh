@@ -54,7 +54,8 @@ struct Leaves {
   int16_t* path;    // [G][S]
 };
 
-struct NetState;  // net.cu
+struct NetState;     // net.cu
+struct ReplayState;  // replay.cu
 
 struct ap_engine {
   ap_config cfg;
@@ -82,6 +83,7 @@ struct ap_engine {
   int32_t* d_ids = nullptr;  // [G]
   // net
   NetState* net = nullptr;
+  ReplayState* replay = nullptr;
   float* d_probs = nullptr;   // [G][S] fp32
   float* d_values = nullptr;  // [G]
   float last_total_ms = 0.f, last_net_ms = 0.f;
@@ -118,6 +120,8 @@ int ap_fail(ap_engine* e, int code, const std::string& msg);
 int ap_stage(ap_engine* e, size_t dbytes, size_t hbytes);
 int ap_ids(ap_engine* e, const int32_t* game_ids, int32_t n);  // uploads ids (or iota) into e->d_ids
 
+// replay.cu
+void replay_destroy(ap_engine* e);
 // net.cu
 int net_destroy(ap_engine* e);
 int net_forward_leaves(ap_engine* e, int precise);

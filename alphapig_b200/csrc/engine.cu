@@ -181,6 +181,7 @@ int ap_engine_destroy(ap_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   net_destroy(e);
+  replay_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_stage) cudaFree(e->d_stage);
   if (e->h_stage) cudaFreeHost(e->h_stage);

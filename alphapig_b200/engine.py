@@ -256,6 +256,55 @@ class Engine(object):
         self._check(self.lib.ap_net_load(self.h, code, int(n_blocks), int(n_filter), arr, len(names)))
         self.net_names = names
 
+    # -- replay ring (train_mxnet.py:57,115-135,196-199) ------------------------
+    def replay_create(self, maxlen):
+        self._check(self.lib.ap_replay_create(self.h, int(maxlen)))
+
+    def replay_push(self, state_bits, pis, zs):
+        """state_bits uint8 [n][ceil(9S/8)] (np.packbits of the 9xHxW planes), pis [n][S], zs [n]"""
+        zs = np.ascontiguousarray(zs, dtype=np.float32).reshape(-1)
+        n = zs.shape[0]
+        sb = (9 * self.S + 7) // 8
+        bits = np.ascontiguousarray(state_bits, dtype=np.uint8).reshape(n, sb)
+        pis = np.ascontiguousarray(pis, dtype=np.float32).reshape(n, self.S)
+        self._check(self.lib.ap_replay_push(self.h, _ptr(bits), _ptr(pis), _ptr(zs), n))
+
+    def replay_push_sgf(self, seqs, winners):
+        """SGF bootstrap (game.py:233-304) for a batch of recorded games: seqs = list of move-index lists
+        (``seq_num_list``), winners = 1 / 2 / -1 per game.  Returns the per-game warning flags (1 = illegal move,
+        game skipped)."""
+        n = len(seqs)
+        max_len = max(1, max(len(q) for q in seqs))
+        mv = np.full((n, max_len), -1, np.int16)
+        for g, q in enumerate(seqs):
+            mv[g, :len(q)] = q
+        ln = np.array([len(q) for q in seqs], np.int32)
+        wn = np.ascontiguousarray(winners, dtype=np.int8).reshape(n)
+        warn = np.zeros(n, np.uint8)
+        self._check(self.lib.ap_replay_push_sgf(self.h, _ptr(mv), max_len, _ptr(ln), _ptr(wn), n, _ptr(warn)))
+        return warn
+
+    def replay_size(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.ap_replay_size(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def replay_gather(self, idx):
+        """-> (states float32 [B][9][H][W], pis [B][S], zs [B]) as numpy (host copies)"""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        B = idx.shape[0]
+        st = np.zeros((B, 9, self.height, self.width), np.float32)
+        pi = np.zeros((B, self.S), np.float32)
+        z = np.zeros(B, np.float32)
+        self._check(self.lib.ap_replay_gather(self.h, _ptr(idx), B, _ptr(st), _ptr(pi), _ptr(z), 0))
+        return st, pi, z
+
+    def replay_gather_device(self, idx, states_ptr, pi_ptr, z_ptr):
+        """Same, written straight into device buffers (raw pointers, e.g. torch ``data_ptr()``)."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        self._check(self.lib.ap_replay_gather(self.h, _ptr(idx), idx.shape[0], C.c_void_p(states_ptr), C.c_void_p(pi_ptr),
+                                              C.c_void_p(z_ptr), 1))
+
     def _fwd(self, fn, states):
         st = np.ascontiguousarray(states, dtype=np.float32).reshape(-1, 9, self.height, self.width)
         B = st.shape[0]

@@ -156,6 +156,33 @@ int ap_search_profile(ap_engine* e, int32_t enable, float* out_ms, int32_t cap);
 /* number of kernels this library launched on the handle since creation */
 int ap_launch_count(const ap_engine* e, uint64_t* out);
 
+/* ---- replay ring: replaces TrainPipeline.data_buffer + get_equi_data + random.sample ------------------
+ * (train_mxnet.py:57 deque(maxlen=buffer_size); :115-135 get_equi_data; :153,180 data_buffer.extend;
+ *  :196-199 random.sample).  One packed record per position lives in HBM; the 8 rotations / flips the
+ * reference materialises in its deque are applied by the gather kernel.  A logical deque index j
+ * (0 = oldest) addresses augmented sample (total - len + j): record (a / 8), symmetry (a % 8) in the
+ * reference's order  [rot90^1, rot90^1+fliplr, rot90^2, rot90^2+fliplr, ...].  Square boards only. */
+/* deque(maxlen): maxlen counts AUGMENTED samples, as buffer_size does in the reference */
+int ap_replay_create(ap_engine* e, int64_t maxlen);
+/* data_buffer.extend(get_equi_data(play_data)) for n positions: state_bits = np.packbits of the (9,H,W) 0/1
+ * planes of Board.current_state() [n][ceil(9S/8)], pi [n][S], z [n] (host buffers) */
+int ap_replay_push(ap_engine* e, const uint8_t* state_bits, const float* pi, const float* z, int32_t n);
+/* len(data_buffer) and the number of augmented samples ever appended */
+int ap_replay_size(ap_engine* e, int64_t* out_len, int64_t* out_total);
+/* [data_buffer[j] for j in idx] as dense fp32 batches [B][9][H][W], [B][S], [B]; out_on_device != 0: the three
+ * outputs are DEVICE pointers (e.g. torch tensors feeding train_step with no host copy) */
+int ap_replay_gather(ap_engine* e, const int64_t* idx, int32_t B, float* out_states, float* out_pi, float* out_z,
+                     int32_t out_on_device);
+
+/* SGF bootstrap: Game.start_self_play(player, sgf_home, file_name) (game.py:233-304) for n_games recorded games
+ * at once, records written straight into the ring (8 augmented samples per ply): state = Board.current_state()
+ * before the move, pi = 0.99999 at the recorded move and 1e-6 elsewhere (:249-251), z = +-1 from `winners`
+ * (1, 2 or -1).  moves [n_games][max_len] (seq_num_list, utils/sgf_dataIter.py:36), lengths [n_games].
+ * out_warning[g] = 1 when a recorded move is illegal: that game contributes nothing (reference: returns
+ * warning=1 and no data, :262-266). */
+int ap_replay_push_sgf(ap_engine* e, const int16_t* moves, int32_t max_len, const int32_t* lengths, const int8_t* winners,
+                       int32_t n_games, uint8_t* out_warning /* [n_games] or NULL */);
+
 #ifdef __cplusplus
 }
 #endif
