@@ -119,7 +119,7 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
     long long want = 2ll * std::max(cfg->n_playout_hint, 1) * g.S + g.S + 2;
     cap = (int)std::min<long long>(want, 1 << 20);
   }
-  g.cap = cap;
+  g.cap = (cap + 3) & ~3;  // SoA pools and the compaction scratch slots keep every array 8-byte aligned
   int rc = AP_OK;
   auto fail = [&](int code) {
     e->err += " (engine_create)";

@@ -153,10 +153,15 @@ class PolicyValueNetBase(object):
         if self._opt is None:
             self._opt = T.AdamState()
         S = self.board_width * self.board_height
-        x = torch.as_tensor(np.asarray(state_batch, dtype=np.float32).reshape(
-            -1, self.channelnum, self.board_height, self.board_width), device=dev)
-        pi = torch.as_tensor(np.asarray(mcts_probs, dtype=np.float32).reshape(-1, S), device=dev)
-        z = torch.as_tensor(np.asarray(winner_batch, dtype=np.float32).reshape(-1, 1), device=dev)
+
+        def dev_tensor(a, shape):
+            # device tensors (e.g. ReplayBuffer.sample_torch) are used in place; anything else goes through numpy
+            if isinstance(a, torch.Tensor):
+                return a.to(device=dev, dtype=torch.float32).reshape(shape)
+            return torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(shape), device=dev)
+        x = dev_tensor(state_batch, (-1, self.channelnum, self.board_height, self.board_width))
+        pi = dev_tensor(mcts_probs, (-1, S))
+        z = dev_tensor(winner_batch, (-1, 1))
         arg = OrderedDict((k, views[k]) for k in self._arg_names)
         aux = OrderedDict((k, views[k]) for k in self._aux_names)
         loss, entropy = T.train_step(arg, aux, self._opt, x, pi, z, float(learning_rate), self.arch,

@@ -353,6 +353,120 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# C3: mcts_pure batched random-rollout player (BASELINE.json configs[2]); `--workload pure`
+# ------------------------------------------------------------------------------------------
+PURE_PLAYOUT = 1000
+PURE_GAMES = 8192
+
+
+def cpu_pure_baseline(n_playout=60):
+    """oracle port of mcts_pure.MCTSPlayer.get_action on one synthetic 15x15 position, 1 core"""
+    from oracle.board import OBoard
+    from oracle.mcts import OPureMCTSPlayer
+    rs = np.random.RandomState(1234)
+    b = OBoard(W, H, N_IN_ROW)
+    b.init_board(0)
+    for m in rs.permutation(W * H)[:2 * rs.randint(0, 8)]:
+        b.do_move(int(m))
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    OPureMCTSPlayer(c_puct=5, n_playout=n_playout).get_action(b)
+    dt = time.perf_counter() - t0
+    return {"value": n_playout / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle port of mcts_pure (Python tree + rollouts): 1 game, 1 move x %d playouts on 15x15, %.1f s"
+                      % (n_playout, dt)}
+
+
+def run_gpu_pure(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from alphapig_b200.engine import Engine
+    G = args.games if args.games != G_PER_GPU else PURE_GAMES
+    eng = Engine(width=W, height=H, n_in_row=N_IN_ROW, n_games=G, c_puct=5, n_playout=PURE_PLAYOUT,
+                 node_capacity=PURE_PLAYOUT * W * H + 2, device=local)
+    cells, meta = synthetic_positions(eng, G, seed0=1234 + rank * G)
+    pin_cells = torch.from_numpy(cells).pin_memory().numpy()
+    pin_meta = torch.from_numpy(meta).pin_memory().numpy()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        eng.pure_run(PURE_PLAYOUT, seed=i)
+    eng.search_stats()
+    clocks = ClockSampler(local)
+    sync_all()
+    clocks.start()
+    l0 = eng.launch_count()
+    dev_ms = 0.0
+    for i in range(args.steps):
+        eng.pure_run(PURE_PLAYOUT, seed=100 + i)
+        dev_ms += eng.search_timing()[0]
+    sync_all()
+    launches = eng.launch_count() - l0
+    clk = clocks.stop()
+    stats = eng.search_stats()
+    e2e_s = 0.0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        eng.boards_import(pin_cells, pin_meta)
+        mv = eng.pure_run(PURE_PLAYOUT, seed=200 + i)
+        if i >= args.warmup:
+            e2e_s += time.perf_counter() - t0
+    sync_all()
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total = world * G * PURE_PLAYOUT * args.steps
+    value = total / (float(t[0]) / 1000.0)
+    if rank == 0:
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            src = "measured (burst)"
+        except Exception:
+            peaks, src = {}, "fallback"
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        tree_bytes = 20 * stats["children_scanned"] + 20 * stats["children_written"] + 24 * stats["path_nodes"] + \
+            64 * stats["playouts"]
+        ach = tree_bytes / (dev_ms / 1000.0) / 1e9
+        out = {"metric": "mcts_pure_playouts_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64 tree / u32 bitboards", "data": "synthetic",
+               "config": {"workload": "15x15 mcts_pure batched random-rollout player, %d playouts/move, %d games per GPU"
+                                      % (PURE_PLAYOUT, G),
+                          "l2": "node pools (%d games x %d nodes x 32 B) are larger than L2; no flush needed"
+                                % (G, PURE_PLAYOUT * W * H + 2),
+                          "timing": "CUDA events on the engine stream around the fused k_pure_run launch"},
+               "moves_per_s": value / PURE_PLAYOUT,
+               "rollout_plies_per_s": stats["rollout_plies"] / (dev_ms / 1000.0),
+               "clocks": clk,
+               "e2e": {"value": total / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": int(pin_cells.nbytes + pin_meta.nbytes),
+                       "d2h_bytes_per_step": int(mv.nbytes), "timing": "wall clock around boards_import + pure_run"},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": "k_pure_run (one launch = one move search for every game)",
+                            "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src,
+                            "traffic": None, "avg_launch_ms": dev_ms / args.steps,
+                            "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
+                            "note": "latency/issue bound: ~100 register-resident random plies per playout dominate"}}
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_pure_baseline()
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,9 +475,13 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--games", type=int, default=G_PER_GPU, help="concurrent games per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="az", choices=["az", "pure"],
+                    help="az = BASELINE configs[1] (default, the headline metric); pure = configs[2] (mcts_pure, 1000 playouts)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "pure":
+        run_gpu_pure(args)
     else:
         run_gpu(args)
 

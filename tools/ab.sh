@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_replay.py -x -q 2>&1 | tail -30
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -15
