@@ -52,6 +52,10 @@ struct Leaves {
   int8_t* winner;   // [G] winner at the leaf (1,2,-1) when terminal
   int32_t* depth;   // [G]
   int16_t* path;    // [G][S]
+  // compaction of the non-terminal leaves for the device-net path (terminal leaves never reach the net)
+  int32_t* slot;          // [G] net tile of game g, -1 = terminal leaf
+  int32_t* game_of_slot;  // [G]
+  int32_t* n_eval;        // [1] non-terminal leaves of the last compaction
 };
 
 struct NetState;     // net.cu
@@ -124,8 +128,8 @@ int ap_ids(ap_engine* e, const int32_t* game_ids, int32_t n);  // uploads ids (o
 void replay_destroy(ap_engine* e);
 // net.cu
 int net_destroy(ap_engine* e);
-int net_forward_leaves(ap_engine* e, int precise);
-int net_emit_features_launch(ap_engine* e);
+int net_forward_leaves(ap_engine* e, int precise, bool compact = false);
+int net_emit_features_launch(ap_engine* e, bool compact = false);
 int net_check_err(ap_engine* e);
 int net_phase_count(ap_engine* e);
 void prof_mark(ap_engine* e);

@@ -151,6 +151,9 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
   ALLOC(e->leaves.winner, G);
   ALLOC(e->leaves.depth, G * 4);
   ALLOC(e->leaves.path, G * (size_t)g.S * 2);
+  ALLOC(e->leaves.slot, G * 4);
+  ALLOC(e->leaves.game_of_slot, G * 4);
+  ALLOC(e->leaves.n_eval, 4);
   ALLOC(e->errflag, G * 4);
   ALLOC(e->stats, 8 * 8);
   ALLOC(e->d_ids, G * 4);
@@ -397,8 +400,10 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
     launch_select(e);
     AP_LAUNCH_CHECK(e);
     prof_mark(e);
-    AP_TRY(net_forward_leaves(e, 0));
-    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values);
+    // only the non-terminal leaves are evaluated (the reference discards the evaluator's answer at a terminal
+    // leaf, mcts_alphaZero.py:124-136): the net runs on the compacted batch, expand/backup reads through the slot map
+    AP_TRY(net_forward_leaves(e, 0, true));
+    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values, e->leaves.slot);
     AP_LAUNCH_CHECK(e);
     prof_mark(e);
   }

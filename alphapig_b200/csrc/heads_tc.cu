@@ -46,6 +46,7 @@ struct FcParams {
   float* values;     // [nb]
   long long rows;
   int kg, np, S, nb;
+  const int* nb_dev;  // when non-null the number of boards is read from device memory (compacted leaf batches)
   int* errflag;
 };
 
@@ -62,6 +63,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
   float* s_bias = (float*)(tmem_slot + 2);
   const int nchunks = p.kg / (kFcKC / 8);
   const int b0 = blockIdx.x * 128;
+  const int nb = p.nb_dev ? *p.nb_dev : p.nb;
+  if (b0 >= nb) return;  // whole CTA, before any barrier / TMEM allocation
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFcStages; ++i) {
@@ -166,10 +169,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
         }
       }
       const float inv = 1.f / sum;
-      if (b < p.nb) p.values[b] = tanhf(vlogit);
+      if (b < nb) p.values[b] = tanhf(vlogit);
       for (int ch = 0; ch < nch; ++ch) {
         tmem_ld16(acc + ch * 16, v);
-        if (b < p.nb) {
+        if (b < nb) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int n = ch * 16 + i;
@@ -231,7 +234,7 @@ int fc_tc_prep(ap_engine* e, NetState* n) {
   return AP_OK;
 }
 
-int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_values) {
+int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_values, const int* nb_dev) {
   FcParams p;
   p.a = n->fc_a;
   p.w = n->fc_w;
@@ -243,6 +246,7 @@ int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_val
   p.np = n->fc_np;
   p.S = n->S;
   p.nb = nb;
+  p.nb_dev = nb_dev;
   p.errflag = n->d_err;
   k_head_fc_tc<<<(nb + 127) / 128, kFcThreads, fc_tc_smem_bytes(n->fc_np), e->stream>>>(p);
   AP_LAUNCH_CHECK(e);

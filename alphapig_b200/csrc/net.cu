@@ -86,11 +86,12 @@ __global__ void k_prep_heads(const float* __restrict__ master, HeadParams h, int
 // features: leaf bitboards -> fp16 planes [2][mpad][8]  (Board.current_state, game.py:68-94)
 // ------------------------------------------------------------------------------------------
 __global__ void k_emit_features(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, int nb,
-                                __half* feat, long long mpad) {
+                                const int32_t* __restrict__ game_of_slot, const int32_t* __restrict__ nb_dev, __half* feat,
+                                long long mpad) {
   int lane = threadIdx.x & 31;
-  int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= nb) return;
-  WBoard wb = wb_load(rows, meta, b, lane);
+  int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // net tile
+  if (b >= (nb_dev ? *nb_dev : nb)) return;
+  WBoard wb = wb_load(rows, meta, game_of_slot ? game_of_slot[b] : b, lane);
   const int W = geo.W, H = geo.H;
   uint32_t pl[8];
 #pragma unroll
@@ -657,12 +658,14 @@ extern "C" int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, 
 // trunk + heads on the first nb boards of the feature planes -> probs/values (device)
 int net_phase_count(ap_engine* e) { return e->net ? (int)e->net->trunk.size() + 2 : 0; }
 
-static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values) {
+// nb_dev != nullptr: the number of boards is read on the device (compacted leaf batch, at most nb)
+static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values, const int32_t* nb_dev = nullptr) {
   NetState* n = e->net;
   const size_t last = n->trunk.size() - 1;
+  if (nb_dev && n->head_mode != 2) return ap_fail(e, AP_ERR_BAD_ARG, "compacted batches need the fused head path");
   for (size_t i = 0; i < n->trunk.size(); ++i) {
     // head_mode 2: the last trunk layer also computes the two 1x1 head convs and never stores its own output
-    AP_TRY(conv_tc_launch(e, n, n->trunk[i], nb, nullptr, n->head_mode == 2 && i == last));
+    AP_TRY(conv_tc_launch(e, n, n->trunk[i], nb, nb_dev, n->head_mode == 2 && i == last));
     prof_mark(e);
   }
   const int S = n->S;
@@ -678,7 +681,7 @@ static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values) {
     AP_LAUNCH_CHECK(e);
     return AP_OK;
   }
-  return fc_tc_launch(e, n, nb, d_probs, d_values);
+  return fc_tc_launch(e, n, nb, d_probs, d_values, nb_dev);
 }
 
 // fp32 path on dense NCHW states (device) for nb <= bcap_ref boards
@@ -721,23 +724,29 @@ int net_check_err(ap_engine* e) {
   return AP_OK;
 }
 
-int net_emit_features_launch(ap_engine* e) {
+int net_emit_features_launch(ap_engine* e, bool compact) {
   NetState* n = e->net;
-  k_emit_features<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->leaves.rows, e->leaves.meta, e->geo.G, n->feat,
-                                                            n->mpad);
+  k_emit_features<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->leaves.rows, e->leaves.meta, e->geo.G,
+                                                            compact ? e->leaves.game_of_slot : nullptr,
+                                                            compact ? e->leaves.n_eval : nullptr, n->feat, n->mpad);
   AP_LAUNCH_CHECK(e);
   return AP_OK;
 }
 
 // leaves of the last select -> e->d_probs / e->d_values
-int net_forward_leaves(ap_engine* e, int precise) {
+int net_forward_leaves(ap_engine* e, int precise, bool compact) {
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
   NetState* n = e->net;
   const int G = e->geo.G;
   if (!precise) {
-    AP_TRY(net_emit_features_launch(e));
+    compact = compact && n->head_mode == 2;
+    if (compact) {
+      launch_compact_leaves(e);
+      AP_LAUNCH_CHECK(e);
+    }
+    AP_TRY(net_emit_features_launch(e, compact));
     prof_mark(e);
-    AP_TRY(run_fast(e, G, e->d_probs, e->d_values));
+    AP_TRY(run_fast(e, G, e->d_probs, e->d_values, compact ? e->leaves.n_eval : nullptr));
     prof_mark(e);
     return AP_OK;
   }

@@ -55,7 +55,8 @@ k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict
 __global__ void __launch_bounds__(32 * SEL_WARPS)
 k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts, const int16_t* __restrict__ acts,
                 const double* __restrict__ pri64, const double* __restrict__ val64, const float* __restrict__ pri32,
-                const float* __restrict__ val32, int32_t* errflag, unsigned long long* stats) {
+                const float* __restrict__ val32, const int32_t* __restrict__ slot, int32_t* errflag,
+                unsigned long long* stats) {
   __shared__ int16_t s_list[SEL_WARPS][AP_MAX_S];
   int lane = threadIdx.x & 31;
   int w = threadIdx.x >> 5;
@@ -66,7 +67,8 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
   double v;
   if (!lv.terminal[g]) {
     int A;
-    const size_t row = (size_t)g * geo.S;
+    const int src = slot ? slot[g] : g;  // compacted net batch: row of this game's priors / value
+    const size_t row = (size_t)src * geo.S;
     bool ok;
     if (acts) {
       A = counts[g];
@@ -86,7 +88,7 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
     }
     if (!ok && lane == 0) errflag[g] = AP_ERR_POOL_EXHAUSTED;
     if (ok && lane == 0) atomicAdd(&stats[2], (unsigned long long)A);
-    v = val64 ? val64[g] : (double)val32[g];
+    v = val64 ? val64[src] : (double)val32[src];
   } else {
     int winner = lv.winner[g];
     int cur = lv.meta[g].cur;
@@ -297,10 +299,48 @@ void launch_select(ap_engine* e) {
   k_select<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, e->leaves, e->stats);
 }
 void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* d_acts, const double* d_pri64,
-                          const double* d_val64, const float* d_pri32, const float* d_val32) {
+                          const double* d_val64, const float* d_pri32, const float* d_val32, const int32_t* d_slot) {
   k_expand_backup<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, e->leaves, d_counts, d_acts,
-                                                                       d_pri64, d_val64, d_pri32, d_val32, e->errflag,
-                                                                       e->stats);
+                                                                       d_pri64, d_val64, d_pri32, d_val32, d_slot,
+                                                                       e->errflag, e->stats);
+}
+
+// Order-preserving compaction of the non-terminal leaves: slot[g] = number of non-terminal leaves before game g
+// (or -1), game_of_slot its inverse, n_eval the count.  One CTA; G is a few thousand.
+__global__ void __launch_bounds__(1024) k_compact_leaves(int G, const int8_t* __restrict__ terminal, int32_t* slot,
+                                                         int32_t* game_of_slot, int32_t* n_eval) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int g0 = 0; g0 < G; g0 += 1024) {
+    const int g = g0 + tid;
+    const int live = (g < G && !terminal[g]) ? 1 : 0;
+    const unsigned m = __ballot_sync(AP_FULL, live);
+    const int pre = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[w] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int i = 0; i < w; ++i) off += s_warp[i];
+    if (g < G) {
+      slot[g] = live ? off + pre : -1;
+      if (live) game_of_slot[off + pre] = g;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int i = 0; i < 32; ++i) t += s_warp[i];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *n_eval = s_base;
+}
+
+void launch_compact_leaves(ap_engine* e) {
+  k_compact_leaves<<<1, 1024, 0, e->stream>>>(e->geo.G, e->leaves.terminal, e->leaves.slot, e->leaves.game_of_slot,
+                                             e->leaves.n_eval);
 }
 void launch_advance(ap_engine* e, int n, const int32_t* d_moves) {
   int grid = n < e->scratch_slots ? n : e->scratch_slots;

@@ -309,12 +309,15 @@ def run_gpu(args):
                                                           (256, 256))) * W * H
         lockstep = args.steps * N_PLAYOUT
         conv_launches = lockstep * n_conv
-        achieved = conv_flop_leaf * G * lockstep / (conv_ms / 1000.0) / 1e12
+        # terminal leaves never reach the net (compacted out on the device): only evaluated leaves count as work
+        evaluated = stats["playouts"] - stats["terminal_leaves"]
+        achieved = conv_flop_leaf * evaluated / (conv_ms / 1000.0) / 1e12
         roof = {"bound": "tensor", "kernel": "k_conv3x3_tc (6 launches per lock-step, all trunk layers)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": pk_src, "traffic": None,
                 "avg_launch_ms": conv_ms / conv_launches,
-                "algorithmic_flop_per_launch_avg": conv_flop_leaf * G / n_conv,
+                "algorithmic_flop_per_launch_avg": conv_flop_leaf * evaluated / conv_launches,
+                "evaluated_leaves": int(evaluated), "terminal_leaves_skipped": int(stats["terminal_leaves"]),
                 "phase_ms_per_lockstep": {"select": float(phase_ms[0]) / lockstep, "features": float(phase_ms[1]) / lockstep,
                                           "trunk_convs": [float(x) / lockstep for x in phase_ms[2:2 + n_conv]],
                                           "heads": float(phase_ms[2 + n_conv]) / lockstep,

@@ -158,3 +158,41 @@ def test_search_run_device_net_matches_host_evaluator_path():
     assert ra.min() == n_playout
     a.close()
     b.close()
+
+
+def test_search_run_compacts_terminal_leaves():
+    """Near-won positions: the search reaches terminal leaves within a few playouts.  The device path evaluates only
+    the non-terminal leaves (compacted batch + slot map); the tree must equal the host-evaluator path's, which
+    evaluates every leaf and discards the terminal answers as the reference does (mcts_alphaZero.py:124-136)."""
+    W = 8
+    G, n_playout = 12, 80
+    arg, aux = onet.init_params("simple", W, W, seed=7)
+    roots = []
+    for g in range(G):
+        # black has an open four on row g % 3 + 2 (white scattered): black to move wins at once, many lines end fast
+        r = g % 3 + 2
+        mv = []
+        whites = [0, 7, 56, 63][: 4]
+        for i in range(4):
+            mv += [r * W + 2 + i, whites[i]]
+        roots.append(oboard_from(W, W, 5, mv))
+    cm = [export_oboard(b) for b in roots]
+    a = _engine(width=W, height=W, n_in_row=5, n_games=G, n_playout=n_playout)
+    b = _engine(width=W, height=W, n_in_row=5, n_games=G, n_playout=n_playout)
+    for e in (a, b):
+        e.net_load("simple", _merged(arg, aux))
+        e.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+    a.search_stats()
+    a.search_run(n_playout)
+    st = a.search_stats()
+    assert st["playouts"] == G * n_playout and st["terminal_leaves"] > G  # terminal leaves did occur
+    for _ in range(n_playout):
+        b.search_select(want_path=False)
+        p, v = b.net_forward_leaves(precise=False)
+        b.search_expand_backup_dense(p, v)
+    ca, aa, va, qa, ra = a.search_root(want_q=True)
+    cb, ab, vb, qb, rb = b.search_root(want_q=True)
+    assert np.array_equal(ca, cb) and np.array_equal(aa, ab) and np.array_equal(va, vb)
+    assert np.array_equal(qa, qb) and np.array_equal(ra, rb)
+    a.close()
+    b.close()
