@@ -841,6 +841,255 @@ k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ Head
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Two boards per CTA pair" version for the 256-channel layers (conv5, conv_final of the simple net).
+// A cluster tile is 2 boards x 128 output channels: CTA r stages the full 290-row slab of ITS board and 64
+// of the 128 weight columns; per (tap, K step) the leader issues two cta_group::2 MMAs (M=256 = rows
+// [128h,128h+128) of both boards, N=128).  Per FLOP this moves 35 % fewer bytes from L2 into the SMs than
+// the one-board pair tile (weights are shared by twice as many rows) and the accumulator (2 x 128 columns)
+// is still double buffered.  The one-board pair form needs ~50 B/clk/SM on conv5 (32 weights + 4.5 slab +
+// 14 output) against a fabric that sustains ~42 B/clk/SM: ncu shows 82 % tensor-pipe activity there.
+// Tiles are ordered column half 0 for every board pair, then column half 1, so a layer whose half weight
+// tensor fits the ring (cin 128: 6 stages) only re-reads it once per launch.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNT4 = 128;  // tile columns
+
+template <int KC, bool RESID>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3x3_tc4(const __grid_constant__ ConvParams p) {
+  constexpr int COUT = 256;
+  constexpr int TPS = kTps2;
+  constexpr int STAGES_PER_KC = 9 / TPS;
+  constexpr int ACC_STAGES = 2;
+  constexpr int TMEM_COLS = 512;                      // 2 stages x 2 row halves x 128 columns
+  constexpr int KG = KC / 8;
+  constexpr int NHC = kNT4 / 2;                       // B columns staged by one CTA
+  constexpr uint32_t SLAB_BYTES = KG * kSlabGroupBytes;
+  constexpr uint32_t SLAB_STRIDE = (SLAB_BYTES + 127u) & ~127u;
+  constexpr uint32_t TAP_BYTES = (uint32_t)KC * NHC * 2;
+  constexpr uint32_t STAGE_BYTES = TPS * TAP_BYTES;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(AP_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* slab0 = smem;
+  uint8_t* bstage0 = smem + (size_t)p.ns * SLAB_STRIDE;
+  uint64_t* bars = (uint64_t*)(bstage0 + (size_t)p.nb * STAGE_BYTES);
+  uint64_t* slab_full = bars;
+  uint64_t* slab_ready = slab_full + kMaxSlabs;
+  uint64_t* slab_empty = slab_ready + kMaxSlabs;
+  uint64_t* b_full = slab_empty + kMaxSlabs;
+  uint64_t* b_ready = b_full + kMaxStages;
+  uint64_t* b_empty = b_ready + kMaxStages;
+  uint64_t* tmem_full = b_empty + kMaxStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [COUT]
+
+  const int n_boards = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
+  const int n_pairs = (n_boards + 1) >> 1;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // the ring holds exactly one column half of the layer: a stage keeps its content from tile to tile
+  const bool keeps = p.nkc * STAGES_PER_KC == p.nb;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxSlabs; ++i) {
+      mbar_init(smem_u32(&slab_full[i]), 1);
+      mbar_init(smem_u32(&slab_ready[i]), 2);
+      mbar_init(smem_u32(&slab_empty[i]), 1);
+    }
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(smem_u32(&b_full[i]), 1);
+      mbar_init(smem_u32(&b_ready[i]), 2);
+      mbar_init(smem_u32(&b_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full[i]), 1);
+      mbar_init(smem_u32(&tmem_empty[i]), 2 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: the slab of this CTA's board + this CTA's 64 weight columns =====
+    int sl = 0, slph = 0, bs = 0, bph = 0;
+    bool ok = true;
+    for (int nh = 0; nh < 2 && ok; ++nh) {
+      // image [nh][rank][kc][tap][KC/8][64][8]
+      const __half* wsrc = p.wimg + ((size_t)nh * 2 + rank) * ((size_t)p.nkc * 9 * KC * NHC);
+      bool first = true;
+      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters) {
+        int board = 2 * bp + (int)rank;
+        if (board >= n_boards) board = n_boards - 1;  // odd batch: the peer re-reads the last board, stores nothing
+        const long long row0 = NET_PAD_ROWS + (long long)board * NET_TILE_ROWS - 17;
+        for (int kc = 0; kc < p.nkc && ok; ++kc) {
+          ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&slab_empty[sl]), slph ^ 1, p.errflag));
+          if (!ok) break;
+          const uint32_t fb = smem_u32(&slab_full[sl]);
+          if (elect_one()) {
+            mbar_expect_tx(fb, SLAB_BYTES);
+#pragma unroll
+            for (int j = 0; j < KG; ++j)
+              bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
+                       p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+          }
+          __syncwarp();
+          if (++sl == p.ns) { sl = 0; slph ^= 1; }
+          for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+            ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag));
+            if (!ok) break;
+            const uint32_t bb = smem_u32(&b_full[bs]);
+            if (elect_one()) {
+              if (keeps && !first) {
+                mbar_arrive(bb);  // the stage still holds (nh, kc, ts): complete the phase without moving data
+              } else {
+                mbar_expect_tx(bb, STAGE_BYTES);
+                bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES), wsrc + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * NHC),
+                         STAGE_BYTES, bb);
+              }
+            }
+            __syncwarp();
+            if (++bs == p.nb) { bs = 0; bph ^= 1; }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===== relay: local TMA completion -> arrive on the leader's *_ready barrier =====
+    int sl = 0, slph = 0, bs = 0, bph = 0;
+    bool ok = true;
+    for (int nh = 0; nh < 2 && ok; ++nh)
+      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters)
+        for (int kc = 0; kc < p.nkc && ok; ++kc) {
+          ok = mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag);
+          if (!ok) break;
+          mbar_arrive_cluster(mapa_u32(smem_u32(&slab_ready[sl]), 0));
+          if (++sl == p.ns) { sl = 0; slph ^= 1; }
+          for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+            ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.errflag);
+            if (!ok) break;
+            mbar_arrive_cluster(mapa_u32(smem_u32(&b_ready[bs]), 0));
+            if (++bs == p.nb) { bs = 0; bph ^= 1; }
+          }
+        }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(kNT4 >> 3) << 17) | ((256u >> 4) << 24);
+    constexpr uint64_t DESC_HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    constexpr uint32_t A_LBO = (uint32_t)kSlabGroupBytes >> 4;  // 290
+    constexpr uint32_t B_LBO = (uint32_t)NHC;                   // 64 columns * 16 B >> 4
+    int sl = 0, slph = 0, bs = 0, bph = 0, as = 0, aph = 0;
+    bool ok = true;
+    for (int nh = 0; nh < 2 && ok; ++nh)
+      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters) {
+        ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag));
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(as * 2 * kNT4);
+        for (int kc = 0; kc < p.nkc && ok; ++kc) {
+          ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&slab_ready[sl]), slph, p.errflag));
+          if (!ok) break;
+          const uint32_t a_lo = (smem_u32(slab0 + sl * SLAB_STRIDE) >> 4) | (A_LBO << 16);
+#pragma unroll
+          for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+            ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&b_ready[bs]), bph, p.errflag));
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t b_lo = (smem_u32(bstage0 + (size_t)bs * STAGE_BYTES) >> 4) | (B_LBO << 16);
+            if (elect_one()) {
+#pragma unroll
+              for (int t = 0; t < TPS; ++t) {
+                const int tap = ts * TPS + t;
+                const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                  for (int j = 0; j < KC / 16; ++j) {
+                    const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
+                    const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
+                    tc_mma_f16_2cta(acc + (uint32_t)(half * kNT4), ad, bd, IDESC, (kc | tap | j) != 0);
+                  }
+                }
+              }
+              tc_commit_2cta(smem_u32(&b_empty[bs]));
+              if (ts == STAGES_PER_KC - 1) {
+                tc_commit_2cta(smem_u32(&slab_empty[sl]));
+                if (kc == p.nkc - 1) tc_commit_2cta(smem_u32(&tmem_full[as]));
+              }
+            }
+            __syncwarp();
+            if (++bs == p.nb) { bs = 0; bph ^= 1; }
+          }
+          if (++sl == p.ns) { sl = 0; slph ^= 1; }
+        }
+        if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+      }
+  } else if (warp >= kCtrlWarps) {
+    // ===== epilogue: this CTA's board (256 rows) x 128 columns; warp = lane quarter x 64-column half =====
+    const int q = warp & 3;
+    const int cw = ((warp - kCtrlWarps) >> 2) * 64;
+    const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t sb = smem_u32(s_bias);
+    const HeadArg<false> none{};
+    int as = 0, aph = 0;
+    bool ok = true;
+    for (int nh = 0; nh < 2 && ok; ++nh)
+      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters) {
+        ok = mbar_wait(smem_u32(&tmem_full[as]), aph, p.errflag);
+        ok = __all_sync(AP_FULL, ok);
+        if (!ok) break;
+        tc_fence_after();
+        const int board = 2 * bp + (int)rank;
+        const bool live = board < n_boards;
+        const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * kNT4 + cw);
+        const long long grow0 = NET_PAD_ROWS + (long long)(live ? board : 0) * NET_TILE_ROWS + q * 32 + lane;
+        const int cabs = nh * kNT4 + cw;  // first output channel of this warp
+        uint32_t v[2][32];
+        float hacc[6];
+        ResidRegs<4, false> rr[2];
+        if (live) resid_load<RESID, 4, false>(p, cabs, grow0, rr[0]);
+        tmem_ld32(acc, v[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // (row half, 32-column chunk)
+          const int half = i >> 1, c0 = cabs + (i & 1) * 32;
+          tmem_ld_wait_regs(v[i & 1]);
+          if (i + 1 < 4) {
+            tmem_ld32(acc + (uint32_t)(((i + 1) >> 1) * kNT4 + ((i + 1) & 1) * 32), v[(i + 1) & 1]);
+            if (live) resid_load<RESID, 4, false>(p, cabs + ((i + 1) & 1) * 32, grow0 + ((i + 1) >> 1) * 128, rr[(i + 1) & 1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(empty_remote + (uint32_t)(as * 8));
+          }
+          const int r = half * 128 + q * 32 + lane;
+          const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
+          if (live) epi_chunk<COUT, RESID, false, 4>(p, none, v[i & 1], c0, grow0 + half * 128, valid, sb, hacc, rr[i & 1]);
+        }
+        if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 struct SmemPlan {
   int ns, nb, bytes;
 };
@@ -891,6 +1140,29 @@ SmemPlan plan_smem2(int cout, int kc, int nkc, bool head) {
   }
   s.bytes = s.ns * slab + s.nb * stage + fixed;
   return s;
+}
+
+SmemPlan plan_smem4(int kc, int nkc) {
+  const int slab = (((kc >> 3) * kSlabGroupBytes) + 127) & ~127;
+  const int stage = kTps2 * kc * (kNT4 / 2) * 2;
+  const int fixed = (3 * kMaxSlabs + 3 * kMaxStages + 4) * 8 + 16 + 256 * 4 + 128;
+  const int budget = 227 * 1024 - fixed;
+  const int all = nkc * (9 / kTps2);
+  SmemPlan s;
+  s.ns = 2;
+  s.nb = (budget - s.ns * slab) / stage;
+  if (s.nb > kMaxStages) s.nb = kMaxStages;
+  if (s.nb > all) s.nb = all;  // exactly one column half of the layer: stages keep their content between tiles
+  if (s.nb == all && budget - all * stage >= 3 * slab) s.ns = 3;
+  s.bytes = s.ns * slab + s.nb * stage + fixed;
+  return s;
+}
+
+template <int KC, bool RESID>
+int launch4(ap_engine* e, const ConvParams& p, int grid, int smem) {
+  k_conv3x3_tc4<KC, RESID><<<grid, kThreads, smem, e->stream>>>(p);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
 }
 
 template <int COUT, int KC, bool RESID, bool HEAD>
@@ -990,6 +1262,8 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, (optin_t<256, 64>()));
   AP_CUDA(e, optin_head());
   AP_CUDA(e, optin_split());
+  AP_CUDA(e, cudaFuncSetAttribute(k_conv3x3_tc4<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  AP_CUDA(e, cudaFuncSetAttribute(k_conv3x3_tc4<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return AP_OK;
 }
 
@@ -1040,6 +1314,16 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
     if (kc == 16) return launch1s<128, 16, false, false>(e, p, none, grid, s.bytes);
     return resid ? launch1s<128, 32, true, false>(e, p, none, grid, s.bytes)
                  : launch1s<128, 32, false, false>(e, p, none, grid, s.bytes);
+  }
+  // 256-channel layers without a fused head: two boards per CTA pair, 128-column tiles (AP_CONV4=0 disables)
+  if (n->conv4 && !head && L.cout == 256 && kc == 64 && n->conv_mode == 0) {
+    p.wimg = L.wimg4;
+    const SmemPlan s4 = plan_smem4(kc, p.nkc);
+    p.ns = s4.ns;
+    p.nb = s4.nb;
+    const int pairs = n->sm_count / 2, bpairs = (n_boards + 1) / 2;
+    const int grid4 = 2 * (bpairs < pairs ? bpairs : pairs);
+    return resid ? launch4<64, true>(e, p, grid4, s4.bytes) : launch4<64, false>(e, p, grid4, s4.bytes);
   }
   // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks, the fused-head
   // layer); the memory-bound small layers run the single-CTA kernel

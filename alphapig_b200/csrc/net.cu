@@ -24,7 +24,7 @@
 // ------------------------------------------------------------------------------------------
 __global__ void k_prep_conv(const float* __restrict__ master, long long w, long long b, long long gamma, long long beta,
                             long long mean, long long var, int fix_gamma, int cin, int cin_pad, int cout, int kc,
-                            __half* wimg, __half* wimg2, __half* wimg_lo, float* scale, float* shift) {
+                            __half* wimg, __half* wimg2, __half* wimg_lo, __half* wimg4, float* scale, float* shift) {
   const long long total = (long long)9 * cin_pad * cout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     // image order: [kcI][tap][j][n][e]
@@ -47,6 +47,12 @@ __global__ void k_prep_conv(const float* __restrict__ master, long long w, long 
     const int nh = cout >> 1, rr = n / nh, np = n - rr * nh;
     const long long i2 = ((((long long)rr * (cin_pad / kc) + kcI) * 9 + tap) * (kc >> 3) + j) * nh * 8 + (long long)np * 8 + e;
     wimg2[i2] = __float2half_rn(v);
+    if (wimg4) {  // [nh][r][kcI][tap][j][n''][e], n = nh*128 + r*64 + n''
+      const int nh4 = n >> 7, r4 = (n >> 6) & 1, n4 = n & 63;
+      const long long i4 = (((((long long)nh4 * 2 + r4) * (cin_pad / kc) + kcI) * 9 + tap) * (kc >> 3) + j) * 64 * 8 +
+                           (long long)n4 * 8 + e;
+      wimg4[i4] = vh;
+    }
   }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < cout; n += gridDim.x * blockDim.x) {
     float s = 1.f / sqrtf(master[var + n] + BN_EPS);
@@ -419,7 +425,7 @@ static int net_prep(ap_engine* e) {
   for (auto& L : n->trunk) {
     const int kc = conv_tc_kc(L, n->split);
     k_prep_conv<<<256, 256, 0, e->stream>>>(n->master, L.w, L.b, L.gamma, L.beta, L.mean, L.var, L.fix_gamma, L.cin,
-                                            L.cin_pad, L.cout, kc, L.wimg, L.wimg2, L.wimg_lo, L.scale, L.shift);
+                                            L.cin_pad, L.cout, kc, L.wimg, L.wimg2, L.wimg_lo, L.wimg4, L.scale, L.shift);
     AP_LAUNCH_CHECK(e);
   }
   k_prep_heads<<<256, 256, 0, e->stream>>>(n->master, n->head, n->S);
@@ -456,6 +462,7 @@ static int conv_bind(ap_engine* e, NetState* n, ConvLayer& L, const std::string&
   AP_TRY(nalloc(e, n, (void**)&L.wimg, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.wimg2, (size_t)9 * L.cin_pad * L.cout * 2));
   if (n->split) AP_TRY(nalloc(e, n, (void**)&L.wimg_lo, (size_t)9 * L.cin_pad * L.cout * 2));
+  if (L.cout == 256 && L.cin_pad % 64 == 0) AP_TRY(nalloc(e, n, (void**)&L.wimg4, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.scale, (size_t)L.cout * 4));
   AP_TRY(nalloc(e, n, (void**)&L.shift, (size_t)L.cout * 4));
   return AP_OK;
@@ -484,6 +491,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   n->S = e->geo.S;
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device);
   if (const char* m = getenv("AP_CONV_MODE")) n->conv_mode = (m[0] == '1') ? 1 : (m[0] == '2') ? 2 : 0;
+  if (const char* m = getenv("AP_CONV4")) n->conv4 = m[0] != '0';
   if (const char* m = getenv("AP_HEAD_PAIR")) n->head_pair = m[0] != '0';
   if (const char* m = getenv("AP_HEAD_MODE")) n->head_mode = (m[0] == '0') ? 0 : (m[0] == '1') ? 1 : 2;
   long long total = 0;

@@ -18,6 +18,7 @@ struct ConvLayer {
   // prepared (device)
   __half* wimg = nullptr;  // [nkc][9][KC/8][cout][8]
   __half* wimg2 = nullptr; // CTA-pair image [2][nkc][9][KC/8][cout/2][8]: half r holds output channels [r*cout/2, (r+1)*cout/2)
+  __half* wimg4 = nullptr; // cout 256 only: [2 column halves][2 ranks][nkc][9][KC/8][64][8] for k_conv3x3_tc4
   __half* wimg_lo = nullptr;  // split precision only: fp16(w - fp16(w)) in the wimg layout (K chunk 32)
   float* scale = nullptr;  // [cout]
   float* shift = nullptr;  // [cout]
@@ -79,6 +80,7 @@ struct NetState {
   int bcap_ref = 0;
   int sm_count = 148;
   int conv_mode = 0;  // 0 = per-layer choice, 1 = single-CTA kernel, 2 = CTA-pair kernel (cta_group::2); AP_CONV_MODE overrides for A/B timing
+  int conv4 = 1;      // 256-channel layers on the two-boards-per-pair kernel (AP_CONV4=0 for A/B timing)
   NetHeadW head_w;
   int head_pair = 1;  // run the fused-head layer on the CTA-pair kernel (measured faster: its double-buffered TMEM hides
                       // the longer epilogue); AP_HEAD_PAIR=0 selects the single-CTA kernel for A/B timing

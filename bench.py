@@ -213,6 +213,27 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def ncu_conv_traffic(G):
+    """dram bytes (read + write) per conv launch, averaged over the trunk launches of the committed ncu launch
+    list of this workload (profiles/, `ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum` on
+    tools/profile_step.py --games 4096).  None when the list is missing or the batch differs."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_launches_v5_final.csv")
+    if G != 4096 or not os.path.exists(path):
+        return None, None
+    per = {}
+    with open(path) as f:
+        rows = [r for r in csv.reader(f) if len(r) > 5]
+    h = {k: i for i, k in enumerate(rows[0])}
+    for r in rows[1:]:
+        if "k_conv3x3_tc" in r[h["Kernel Name"]] and r[h["Metric Name"]].startswith("dram__bytes"):
+            per.setdefault(r[h["ID"]], 0.0)
+            per[r[h["ID"]]] += float(r[h["Metric Value"]])
+    if not per:
+        return None, None
+    return sum(per.values()) / len(per), os.path.relpath(path, ROOT)
+
+
 def run_gpu(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -312,9 +333,10 @@ def run_gpu(args):
         # terminal leaves never reach the net (compacted out on the device): only evaluated leaves count as work
         evaluated = stats["playouts"] - stats["terminal_leaves"]
         achieved = conv_flop_leaf * evaluated / (conv_ms / 1000.0) / 1e12
+        traffic, traffic_src = ncu_conv_traffic(G)
         roof = {"bound": "tensor", "kernel": "k_conv3x3_tc (6 launches per lock-step, all trunk layers)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_source": pk_src, "traffic": None,
+                "peak_source": pk_src, "traffic": traffic, "traffic_source": traffic_src,
                 "avg_launch_ms": conv_ms / conv_launches,
                 "algorithmic_flop_per_launch_avg": conv_flop_leaf * evaluated / conv_launches,
                 "evaluated_leaves": int(evaluated), "terminal_leaves_skipped": int(stats["terminal_leaves"]),

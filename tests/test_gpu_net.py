@@ -50,7 +50,7 @@ def test_net_forward_vs_oracle(W, arch, nblk):
 
 
 @pytest.mark.parametrize("mode", ["0", "1", "2"])
-@pytest.mark.parametrize("W,arch,nblk,nst", [(15, "simple", 0, 300), (8, "simple", 0, 130), (15, "resnet", 2, 140),
+@pytest.mark.parametrize("W,arch,nblk,nst", [(15, "simple", 0, 301), (8, "simple", 0, 131), (15, "resnet", 2, 140),
                                              (6, "simple", 0, 20)])
 def test_net_head_modes(monkeypatch, mode, W, arch, nblk, nst):
     """The three head implementations (fp32 CUDA-core FC; split-fp16 tensor-core FC fed by k_head_conv; head convs
