@@ -854,8 +854,24 @@ k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ Head
 // ---------------------------------------------------------------------------------------------
 constexpr int kNT4 = 128;  // tile columns
 
-template <int KC, bool RESID>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3x3_tc4(const __grid_constant__ ConvParams p) {
+// iteration -> (board pair, column half) of one cluster.  Plain layers run column half 0 for all their board pairs,
+// then column half 1 (weights stay in the ring); the fused-head layer alternates the halves per board pair so that
+// one epilogue warp sees all 256 channels of its rows in two consecutive tiles and keeps the head sums in registers.
+template <bool HEAD>
+struct Tc4Iter {
+  int n_my, cluster_id, n_clusters;
+  __device__ Tc4Iter(int n_pairs, int cid, int ncl) : cluster_id(cid), n_clusters(ncl) {
+    n_my = cid < n_pairs ? (n_pairs - cid + ncl - 1) / ncl : 0;
+  }
+  __device__ int count() const { return 2 * n_my; }
+  __device__ int nh(int it) const { return HEAD ? (it & 1) : (it >= n_my ? 1 : 0); }
+  __device__ int bp(int it) const { return cluster_id + (HEAD ? (it >> 1) : (it >= n_my ? it - n_my : it)) * n_clusters; }
+  __device__ bool first_of_half(int it) const { return HEAD ? true : (it == 0 || it == n_my); }
+};
+
+template <int KC, bool RESID, bool HEAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_conv3x3_tc4(const __grid_constant__ ConvParams p, const __grid_constant__ HeadArg<HEAD> hw) {
   constexpr int COUT = 256;
   constexpr int TPS = kTps2;
   constexpr int STAGES_PER_KC = 9 / TPS;
@@ -884,12 +900,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
   float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [COUT]
+  float* s_hx = s_bias + COUT;                  // HEAD: [128][12] partial exchange between the two column-half warps
 
   const int n_boards = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
-  const int n_pairs = (n_boards + 1) >> 1;
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const Tc4Iter<HEAD> iter((n_boards + 1) >> 1, blockIdx.x >> 1, gridDim.x >> 1);
+  const int n_iter = iter.count();
   // the ring holds exactly one column half of the layer: a stage keeps its content from tile to tile
-  const bool keeps = p.nkc * STAGES_PER_KC == p.nb;
+  const bool keeps = !HEAD && p.nkc * STAGES_PER_KC == p.nb;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxSlabs; ++i) {
@@ -925,65 +942,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3
     // ===== TMA producer: the slab of this CTA's board + this CTA's 64 weight columns =====
     int sl = 0, slph = 0, bs = 0, bph = 0;
     bool ok = true;
-    for (int nh = 0; nh < 2 && ok; ++nh) {
+    for (int it = 0; it < n_iter && ok; ++it) {
+      const int nh = iter.nh(it), bp = iter.bp(it);
+      const bool first = iter.first_of_half(it);
       // image [nh][rank][kc][tap][KC/8][64][8]
       const __half* wsrc = p.wimg + ((size_t)nh * 2 + rank) * ((size_t)p.nkc * 9 * KC * NHC);
-      bool first = true;
-      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters) {
-        int board = 2 * bp + (int)rank;
-        if (board >= n_boards) board = n_boards - 1;  // odd batch: the peer re-reads the last board, stores nothing
-        const long long row0 = NET_PAD_ROWS + (long long)board * NET_TILE_ROWS - 17;
-        for (int kc = 0; kc < p.nkc && ok; ++kc) {
-          ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&slab_empty[sl]), slph ^ 1, p.errflag));
-          if (!ok) break;
-          const uint32_t fb = smem_u32(&slab_full[sl]);
-          if (elect_one()) {
-            mbar_expect_tx(fb, SLAB_BYTES);
+      int board = 2 * bp + (int)rank;
+      if (board >= n_boards) board = n_boards - 1;  // odd batch: the peer re-reads the last board, stores nothing
+      const long long row0 = NET_PAD_ROWS + (long long)board * NET_TILE_ROWS - 17;
+      for (int kc = 0; kc < p.nkc && ok; ++kc) {
+        ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&slab_empty[sl]), slph ^ 1, p.errflag));
+        if (!ok) break;
+        const uint32_t fb = smem_u32(&slab_full[sl]);
+        if (elect_one()) {
+          mbar_expect_tx(fb, SLAB_BYTES);
 #pragma unroll
-            for (int j = 0; j < KG; ++j)
-              bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
-                       p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+          for (int j = 0; j < KG; ++j)
+            bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
+                     p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+        }
+        __syncwarp();
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag));
+          if (!ok) break;
+          const uint32_t bb = smem_u32(&b_full[bs]);
+          if (elect_one()) {
+            if (keeps && !first) {
+              mbar_arrive(bb);  // the stage still holds (nh, kc, ts): complete the phase without moving data
+            } else {
+              mbar_expect_tx(bb, STAGE_BYTES);
+              bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES), wsrc + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * NHC),
+                       STAGE_BYTES, bb);
+            }
           }
           __syncwarp();
-          if (++sl == p.ns) { sl = 0; slph ^= 1; }
-          for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
-            ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.errflag));
-            if (!ok) break;
-            const uint32_t bb = smem_u32(&b_full[bs]);
-            if (elect_one()) {
-              if (keeps && !first) {
-                mbar_arrive(bb);  // the stage still holds (nh, kc, ts): complete the phase without moving data
-              } else {
-                mbar_expect_tx(bb, STAGE_BYTES);
-                bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES), wsrc + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * NHC),
-                         STAGE_BYTES, bb);
-              }
-            }
-            __syncwarp();
-            if (++bs == p.nb) { bs = 0; bph ^= 1; }
-          }
+          if (++bs == p.nb) { bs = 0; bph ^= 1; }
         }
-        first = false;
       }
     }
   } else if (warp == 3 && lane == 0) {
     // ===== relay: local TMA completion -> arrive on the leader's *_ready barrier =====
     int sl = 0, slph = 0, bs = 0, bph = 0;
     bool ok = true;
-    for (int nh = 0; nh < 2 && ok; ++nh)
-      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters)
-        for (int kc = 0; kc < p.nkc && ok; ++kc) {
-          ok = mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag);
+    for (int it = 0; it < n_iter && ok; ++it)
+      for (int kc = 0; kc < p.nkc && ok; ++kc) {
+        ok = mbar_wait(smem_u32(&slab_full[sl]), slph, p.errflag);
+        if (!ok) break;
+        mbar_arrive_cluster(mapa_u32(smem_u32(&slab_ready[sl]), 0));
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.errflag);
           if (!ok) break;
-          mbar_arrive_cluster(mapa_u32(smem_u32(&slab_ready[sl]), 0));
-          if (++sl == p.ns) { sl = 0; slph ^= 1; }
-          for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
-            ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.errflag);
-            if (!ok) break;
-            mbar_arrive_cluster(mapa_u32(smem_u32(&b_ready[bs]), 0));
-            if (++bs == p.nb) { bs = 0; bph ^= 1; }
-          }
+          mbar_arrive_cluster(mapa_u32(smem_u32(&b_ready[bs]), 0));
+          if (++bs == p.nb) { bs = 0; bph ^= 1; }
         }
+      }
   } else if (warp == 1 && rank == 0) {
     // ===== MMA issuer (leader CTA only) =====
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(kNT4 >> 3) << 17) | ((256u >> 4) << 24);
@@ -992,72 +1006,78 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3
     constexpr uint32_t B_LBO = (uint32_t)NHC;                   // 64 columns * 16 B >> 4
     int sl = 0, slph = 0, bs = 0, bph = 0, as = 0, aph = 0;
     bool ok = true;
-    for (int nh = 0; nh < 2 && ok; ++nh)
-      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters) {
-        ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag));
+    for (int it = 0; it < n_iter && ok; ++it) {
+      ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&tmem_empty[as]), aph ^ 1, p.errflag));
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(as * 2 * kNT4);
+      for (int kc = 0; kc < p.nkc && ok; ++kc) {
+        ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&slab_ready[sl]), slph, p.errflag));
         if (!ok) break;
-        tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(as * 2 * kNT4);
-        for (int kc = 0; kc < p.nkc && ok; ++kc) {
-          ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&slab_ready[sl]), slph, p.errflag));
+        const uint32_t a_lo = (smem_u32(slab0 + sl * SLAB_STRIDE) >> 4) | (A_LBO << 16);
+#pragma unroll
+        for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
+          ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&b_ready[bs]), bph, p.errflag));
           if (!ok) break;
-          const uint32_t a_lo = (smem_u32(slab0 + sl * SLAB_STRIDE) >> 4) | (A_LBO << 16);
+          tc_fence_after();
+          const uint32_t b_lo = (smem_u32(bstage0 + (size_t)bs * STAGE_BYTES) >> 4) | (B_LBO << 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int ts = 0; ts < STAGES_PER_KC; ++ts) {
-            ok = __all_sync(AP_FULL, mbar_wait_cl(smem_u32(&b_ready[bs]), bph, p.errflag));
-            if (!ok) break;
-            tc_fence_after();
-            const uint32_t b_lo = (smem_u32(bstage0 + (size_t)bs * STAGE_BYTES) >> 4) | (B_LBO << 16);
-            if (elect_one()) {
+            for (int t = 0; t < TPS; ++t) {
+              const int tap = ts * TPS + t;
+              const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
 #pragma unroll
-              for (int t = 0; t < TPS; ++t) {
-                const int tap = ts * TPS + t;
-                const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
+              for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                  for (int j = 0; j < KC / 16; ++j) {
-                    const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
-                    const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
-                    tc_mma_f16_2cta(acc + (uint32_t)(half * kNT4), ad, bd, IDESC, (kc | tap | j) != 0);
-                  }
+                for (int j = 0; j < KC / 16; ++j) {
+                  const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
+                  const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
+                  tc_mma_f16_2cta(acc + (uint32_t)(half * kNT4), ad, bd, IDESC, (kc | tap | j) != 0);
                 }
               }
-              tc_commit_2cta(smem_u32(&b_empty[bs]));
-              if (ts == STAGES_PER_KC - 1) {
-                tc_commit_2cta(smem_u32(&slab_empty[sl]));
-                if (kc == p.nkc - 1) tc_commit_2cta(smem_u32(&tmem_full[as]));
-              }
             }
-            __syncwarp();
-            if (++bs == p.nb) { bs = 0; bph ^= 1; }
+            tc_commit_2cta(smem_u32(&b_empty[bs]));
+            if (ts == STAGES_PER_KC - 1) {
+              tc_commit_2cta(smem_u32(&slab_empty[sl]));
+              if (kc == p.nkc - 1) tc_commit_2cta(smem_u32(&tmem_full[as]));
+            }
           }
-          if (++sl == p.ns) { sl = 0; slph ^= 1; }
+          __syncwarp();
+          if (++bs == p.nb) { bs = 0; bph ^= 1; }
         }
-        if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+        if (++sl == p.ns) { sl = 0; slph ^= 1; }
       }
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+    }
   } else if (warp >= kCtrlWarps) {
     // ===== epilogue: this CTA's board (256 rows) x 128 columns; warp = lane quarter x 64-column half =====
     const int q = warp & 3;
-    const int cw = ((warp - kCtrlWarps) >> 2) * 64;
+    const int ch = (warp - kCtrlWarps) >> 2;
+    const int cw = ch * 64;
     const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty[0]), 0);
-    const uint32_t sb = smem_u32(s_bias);
-    const HeadArg<false> none{};
+    const uint32_t sb = smem_u32(s_bias), sx = smem_u32(s_hx);
     int as = 0, aph = 0;
     bool ok = true;
-    for (int nh = 0; nh < 2 && ok; ++nh)
-      for (int bp = cluster_id; bp < n_pairs && ok; bp += n_clusters) {
-        ok = mbar_wait(smem_u32(&tmem_full[as]), aph, p.errflag);
-        ok = __all_sync(AP_FULL, ok);
-        if (!ok) break;
-        tc_fence_after();
-        const int board = 2 * bp + (int)rank;
-        const bool live = board < n_boards;
-        const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * kNT4 + cw);
-        const long long grow0 = NET_PAD_ROWS + (long long)(live ? board : 0) * NET_TILE_ROWS + q * 32 + lane;
-        const int cabs = nh * kNT4 + cw;  // first output channel of this warp
+    float hsum[2][6];  // HEAD: head-conv partial sums of this thread's two rows over its 2 x 64 channels
+    for (int it = 0; it < n_iter && ok; ++it) {
+      const int nh = iter.nh(it), bp = iter.bp(it);
+      ok = mbar_wait(smem_u32(&tmem_full[as]), aph, p.errflag);
+      ok = __all_sync(AP_FULL, ok);
+      if (!ok) break;
+      tc_fence_after();
+      const int board = 2 * bp + (int)rank;
+      const bool live = board < n_boards;
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * kNT4 + cw);
+      const long long grow0 = NET_PAD_ROWS + (long long)(live ? board : 0) * NET_TILE_ROWS + q * 32 + lane;
+      if (HEAD && nh == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int o = 0; o < 6; ++o) hsum[r][o] = 0.f;
+      }
+      auto body = [&](const int cabs) {  // cabs = first output channel of this warp (compile-time under HEAD)
         uint32_t v[2][32];
-        float hacc[6];
+        float dummy[6];
         ResidRegs<4, false> rr[2];
         if (live) resid_load<RESID, 4, false>(p, cabs, grow0, rr[0]);
         tmem_ld32(acc, v[0]);
@@ -1075,10 +1095,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv3
           }
           const int r = half * 128 + q * 32 + lane;
           const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
-          if (live) epi_chunk<COUT, RESID, false, 4>(p, none, v[i & 1], c0, grow0 + half * 128, valid, sb, hacc, rr[i & 1]);
+          if (live) {
+            if constexpr (HEAD)
+              epi_chunk<COUT, RESID, true, 4>(p, hw, v[i & 1], c0, grow0 + half * 128, valid, sb, hsum[half], rr[i & 1]);
+            else
+              epi_chunk<COUT, RESID, false, 4>(p, hw, v[i & 1], c0, grow0 + half * 128, valid, sb, dummy, rr[i & 1]);
+          }
         }
-        if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+      };
+      if constexpr (HEAD) {
+        switch (nh * 2 + ch) {
+          case 0: body(0); break;
+          case 1: body(64); break;
+          case 2: body(128); break;
+          default: body(192); break;
+        }
+        if (nh == 1) {
+          // both column halves of this board are in hsum: combine the two 64-column warps, finish, write the FC operand
+          const int rows[2] = {q * 32 + lane, 128 + q * 32 + lane};
+          if (live) {
+            head_finish<2, 2>(p, hw, hsum, sx, 1 + q, q, lane, ch, board, rows);
+          } else {  // keep the named barriers of head_finish balanced for the peer warp
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          }
+        }
+      } else {
+        body(nh * kNT4 + cw);
       }
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1142,10 +1188,10 @@ SmemPlan plan_smem2(int cout, int kc, int nkc, bool head) {
   return s;
 }
 
-SmemPlan plan_smem4(int kc, int nkc) {
+SmemPlan plan_smem4(int kc, int nkc, bool head) {
   const int slab = (((kc >> 3) * kSlabGroupBytes) + 127) & ~127;
   const int stage = kTps2 * kc * (kNT4 / 2) * 2;
-  const int fixed = (3 * kMaxSlabs + 3 * kMaxStages + 4) * 8 + 16 + 256 * 4 + 128;
+  const int fixed = (3 * kMaxSlabs + 3 * kMaxStages + 4) * 8 + 16 + 256 * 4 + 128 + (head ? 128 * 12 * 4 : 0);
   const int budget = 227 * 1024 - fixed;
   const int all = nkc * (9 / kTps2);
   SmemPlan s;
@@ -1158,9 +1204,9 @@ SmemPlan plan_smem4(int kc, int nkc) {
   return s;
 }
 
-template <int KC, bool RESID>
-int launch4(ap_engine* e, const ConvParams& p, int grid, int smem) {
-  k_conv3x3_tc4<KC, RESID><<<grid, kThreads, smem, e->stream>>>(p);
+template <int KC, bool RESID, bool HEAD>
+int launch4(ap_engine* e, const ConvParams& p, const HeadArg<HEAD>& hw, int grid, int smem) {
+  k_conv3x3_tc4<KC, RESID, HEAD><<<grid, kThreads, smem, e->stream>>>(p, hw);
   AP_LAUNCH_CHECK(e);
   return AP_OK;
 }
@@ -1262,8 +1308,9 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, (optin_t<256, 64>()));
   AP_CUDA(e, optin_head());
   AP_CUDA(e, optin_split());
-  AP_CUDA(e, cudaFuncSetAttribute(k_conv3x3_tc4<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  AP_CUDA(e, cudaFuncSetAttribute(k_conv3x3_tc4<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   return AP_OK;
 }
 
@@ -1316,14 +1363,20 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
                  : launch1s<128, 32, false, false>(e, p, none, grid, s.bytes);
   }
   // 256-channel layers without a fused head: two boards per CTA pair, 128-column tiles (AP_CONV4=0 disables)
-  if (n->conv4 && !head && L.cout == 256 && kc == 64 && n->conv_mode == 0) {
+  if (n->conv4 && L.cout == 256 && kc == 64 && n->conv_mode == 0 && !(head && (resid || n->conv4 < 2))) {
     p.wimg = L.wimg4;
-    const SmemPlan s4 = plan_smem4(kc, p.nkc);
+    const SmemPlan s4 = plan_smem4(kc, p.nkc, head);
     p.ns = s4.ns;
     p.nb = s4.nb;
     const int pairs = n->sm_count / 2, bpairs = (n_boards + 1) / 2;
     const int grid4 = 2 * (bpairs < pairs ? bpairs : pairs);
-    return resid ? launch4<64, true>(e, p, grid4, s4.bytes) : launch4<64, false>(e, p, grid4, s4.bytes);
+    const HeadArg<false> none{};
+    if (head) {
+      HeadArg<true> hw;
+      hw.h = n->head_w;
+      return launch4<64, false, true>(e, p, hw, grid4, s4.bytes);
+    }
+    return resid ? launch4<64, true, false>(e, p, none, grid4, s4.bytes) : launch4<64, false, false>(e, p, none, grid4, s4.bytes);
   }
   // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks, the fused-head
   // layer); the memory-bound small layers run the single-CTA kernel

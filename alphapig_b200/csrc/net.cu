@@ -491,7 +491,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   n->S = e->geo.S;
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device);
   if (const char* m = getenv("AP_CONV_MODE")) n->conv_mode = (m[0] == '1') ? 1 : (m[0] == '2') ? 2 : 0;
-  if (const char* m = getenv("AP_CONV4")) n->conv4 = m[0] != '0';
+  if (const char* m = getenv("AP_CONV4")) n->conv4 = m[0] - '0';
   if (const char* m = getenv("AP_HEAD_PAIR")) n->head_pair = m[0] != '0';
   if (const char* m = getenv("AP_HEAD_MODE")) n->head_mode = (m[0] == '0') ? 0 : (m[0] == '1') ? 1 : 2;
   long long total = 0;
