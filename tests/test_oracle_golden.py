@@ -127,3 +127,53 @@ def test_selfplay_golden():
         assert np.array_equal(np.array([zz for _, _, zz in data]), z["s%d_z" % i])
         st = np.stack([np.packbits(np.ascontiguousarray(s).astype(np.uint8).ravel()) for s, _, _ in data])
         assert np.array_equal(st, z["s%d_states" % i])
+
+
+# ---- TrainPipeline data path: oracle/pipeline.py vs vectors written from the reference (make_golden_pipeline.py) ----
+def _pipeline_case(z, ci):
+    W, maxlen, ng = [int(x) for x in z["c%d_meta" % ci]]
+    S = W * W
+    st = np.unpackbits(z["c%d_in_states" % ci], axis=1)[:, :9 * S].reshape(-1, 9, W, W).astype(np.float64)
+    pi, zz = z["c%d_in_pi" % ci], z["c%d_in_z" % ci]
+    games, k = [], 0
+    for n in z["c%d_lens" % ci]:
+        games.append([(st[i], pi[i], float(zz[i])) for i in range(k, k + int(n))])
+        k += int(n)
+    return W, maxlen, games
+
+
+@pytest.mark.parametrize("ci", [0, 1])
+def test_pipeline_golden(ci):
+    from oracle import pipeline as opl
+    z = np.load(os.path.join(GOLDEN, "pipeline_cases.npz"))
+    W, maxlen, games = _pipeline_case(z, ci)
+    rep = opl.ReplayDeque(maxlen, W, W)
+    for g in games:
+        rep.extend_game(g)
+    assert len(rep) == z["c%d_dq_z" % ci].shape[0]
+    for j, (s, p, zz) in enumerate(rep.buf):
+        assert np.array_equal(np.packbits(np.asarray(s).astype(np.uint8).ravel()), z["c%d_dq_states" % ci][j])
+        assert np.array_equal(p, z["c%d_dq_pi" % ci][j]) and zz == z["c%d_dq_z" % ci][j]
+    random.seed(7 + ci)
+    idx = random.sample(range(len(rep)), 16)
+    assert idx == [int(i) for i in z["c%d_sample_idx" % ci]]
+
+
+def test_sgf_golden():
+    z = np.load(os.path.join(GOLDEN, "pipeline_cases.npz"))
+
+    class P(object):
+        def reset_player(self):
+            pass
+    warn, winner, data = osp.sgf_self_play(OBoard(15, 15, 5), P(), {"winner": int(z["sgf_winner"][0]),
+                                                                   "seq_num_list": [int(m) for m in z["sgf_moves"]]})
+    assert (winner, warn) == tuple(int(x) for x in z["sgf_winner"])
+    data = list(data)
+    assert len(data) == len(z["sgf_z"])
+    for j, (s, p, zz) in enumerate(data):
+        assert np.array_equal(_packed_state_arr(s), z["sgf_states"][j])
+        assert np.array_equal(p, z["sgf_pi"][j]) and zz == z["sgf_z"][j]
+
+
+def _packed_state_arr(s):
+    return np.packbits(np.ascontiguousarray(s).astype(np.uint8).ravel())
