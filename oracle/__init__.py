@@ -19,6 +19,10 @@ Pinning status
   re-runs the comparison live whenever ``/root/reference`` is present) and
   against the committed golden vectors in ``tests/golden/*.npz`` that the same
   script wrote from the reference.
+* ``oracle.pipeline`` (``get_equi_data``, deque + ``random.sample``, ``policy_update``,
+  ``policy_evaluate``): PINNED live against ``train_mxnet.TrainPipeline`` driven with a fake net
+  (``tests/test_oracle_vs_reference.py``) and by ``tests/golden/pipeline_cases.npz``
+  (``tests/golden/make_golden_pipeline.py``).
 * ``oracle.net``: PARITY UNPINNED at the MXNet boundary.  The reference's net
   arithmetic lives in third-party MXNet (``requirements.txt:8`` pins
   ``mxnet==1.6.0``) which is not installed and not installable here (no
