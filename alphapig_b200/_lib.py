@@ -47,6 +47,7 @@ SIGNATURES = {
     "ap_boards_status": (C.c_int, [_P, _P, _I, _P, _P]),
     "ap_boards_legal": (C.c_int, [_P, _P, _I, _P]),
     "ap_boards_features": (C.c_int, [_P, _P, _I, _P]),
+    "ap_boards_features_packed": (C.c_int, [_P, _P, _I, _P]),
     "ap_boards_export": (C.c_int, [_P, _P, _I, _P, _P]),
     "ap_boards_import": (C.c_int, [_P, _P, _I, _P, _P]),
     "ap_search_select": (C.c_int, [_P, _P, _P, _P]),

@@ -108,6 +108,19 @@ __global__ void k_boards_features(Geo geo, const uint32_t* rows, const BoardMeta
   }
 }
 
+// np.packbits (MSB first) of the 0/1 feature planes: one thread per output byte
+__global__ void k_pack_bits(const float* __restrict__ f, int n, int nbits, int sb, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * sb) return;
+  const int g = (int)(i / sb), b = (int)(i % sb);
+  const float* src = f + (size_t)g * nbits + (size_t)b * 8;
+  unsigned v = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (b * 8 + k < nbits && src[k] != 0.f) v |= 0x80u >> k;
+  out[i] = (uint8_t)v;
+}
+
 __global__ void k_fill_f32(float* p, size_t n, float v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -192,6 +205,11 @@ void launch_boards_features(ap_engine* e, const uint32_t* rows, const BoardMeta*
   size_t tot = (size_t)n * 9 * e->geo.S;
   k_fill_f32<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(d_out, tot, 0.f);
   k_boards_features<<<warp_grid(n), 32 * WARPS_PER_BLOCK, 0, e->stream>>>(e->geo, rows, meta, d_ids, n, d_out);
+}
+void launch_pack_bits(ap_engine* e, const float* d_f, int n, int nbits, uint8_t* d_out) {
+  const int sb = (nbits + 7) / 8;
+  const size_t tot = (size_t)n * sb;
+  k_pack_bits<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(d_f, n, nbits, sb, d_out);
 }
 void launch_boards_export(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
                           int8_t* d_cells, int32_t* d_meta) {

@@ -287,6 +287,22 @@ int ap_boards_features(ap_engine* e, const int32_t* game_ids, int32_t n, float* 
   return d2h_sync(e, out, e->d_stage, bytes);
 }
 
+// Board.current_state() bit-packed (np.packbits of the 9xWxH planes): what the replay ring stores
+int ap_boards_features_packed(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* out) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(ap_ids(e, game_ids, n));
+  const int nbits = 9 * e->geo.S, sb = (nbits + 7) / 8;
+  const size_t fb = ((size_t)n * nbits * 4 + 15) & ~(size_t)15;
+  AP_TRY(ap_stage(e, fb + (size_t)n * sb, 0));
+  launch_boards_features(e, e->rows, e->meta, e->d_ids, n, (float*)e->d_stage);
+  e->launches++;
+  AP_LAUNCH_CHECK(e);
+  uint8_t* d_out = (uint8_t*)e->d_stage + fb;
+  launch_pack_bits(e, (const float*)e->d_stage, n, nbits, d_out);
+  AP_LAUNCH_CHECK(e);
+  return d2h_sync(e, out, d_out, (size_t)n * sb);
+}
+
 static int export_common(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
                          int8_t* out_cells, int32_t* out_meta) {
   size_t cb = ((size_t)n * e->geo.S + 15) & ~(size_t)15, mb = (size_t)n * AP_META_INTS * 4;

@@ -10,6 +10,7 @@ void launch_boards_status(ap_engine* e, const uint32_t* rows, const BoardMeta* m
 void launch_boards_legal(ap_engine* e, const int32_t* d_ids, int n, uint32_t* d_mask);
 void launch_boards_features(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
                             float* d_out);
+void launch_pack_bits(ap_engine* e, const float* d_f, int n, int nbits, uint8_t* d_out);
 void launch_boards_export(ap_engine* e, const uint32_t* rows, const BoardMeta* meta, const int32_t* d_ids, int n,
                           int8_t* d_cells, int32_t* d_meta);
 void launch_boards_import(ap_engine* e, int n, const int8_t* d_cells, const int32_t* d_meta);

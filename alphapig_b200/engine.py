@@ -123,6 +123,14 @@ class Engine(object):
         self._check(self.lib.ap_boards_features(self.h, _ptr(ids), n, _ptr(out)))
         return out
 
+    def boards_features_packed(self, game_ids=None):
+        """np.packbits(Board.current_state()) per game: uint8 [n][ceil(9S/8)]"""
+        ids = _ids(game_ids)
+        n = self._n(ids)
+        out = np.zeros((n, (9 * self.S + 7) // 8), np.uint8)
+        self._check(self.lib.ap_boards_features_packed(self.h, _ptr(ids), n, _ptr(out)))
+        return out
+
     def boards_export(self, game_ids=None):
         ids = _ids(game_ids)
         n = self._n(ids)

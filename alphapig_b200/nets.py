@@ -76,10 +76,11 @@ class PolicyValueNetBase(object):
                      n_filter=self._n_filter, precision=self._precision)
         return eng
 
-    def search_engine(self, n_in_row=5, c_puct=5.0, n_playout=400, n_games=1, node_capacity=0):
+    def search_engine(self, n_in_row=5, c_puct=5.0, n_playout=400, n_games=1, node_capacity=0, tag=0):
         """An engine holding ``n_games`` trees and a replica of the current weights (kept in sync by
-        ``train_step``); what ``MCTS`` uses when this net's ``policy_value_fn`` is the evaluator."""
-        key = (n_games, n_in_row, float(c_puct), int(n_playout), int(node_capacity))
+        ``train_step``); what ``MCTS`` uses when this net's ``policy_value_fn`` is the evaluator.
+        Engines are cached per configuration; ``tag`` distinguishes several engines of the same shape."""
+        key = (n_games, n_in_row, float(c_puct), int(n_playout), int(node_capacity), tag)
         eng = self._engines.get(key)
         if eng is None:
             eng = self._make_engine(n_games, n_in_row, c_puct, n_playout, node_capacity=node_capacity)

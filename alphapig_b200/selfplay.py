@@ -22,7 +22,7 @@ def visit_softmax(visits, counts, temp):
 
 class BatchedSelfPlay(object):
     def __init__(self, net, n_games, n_playout=400, c_puct=5, temp=1.0, n_in_row=5, seed=0,
-                 noise_eps=0.25, dirichlet_alpha=0.3, node_capacity=0, record_states=True):
+                 noise_eps=0.25, dirichlet_alpha=0.3, node_capacity=0, record_states=True, tag=0):
         self.net = net
         self.G = n_games
         self.n_playout = n_playout
@@ -32,25 +32,34 @@ class BatchedSelfPlay(object):
         self.record_states = record_states
         self.rs = np.random.RandomState(seed)
         self.eng = net.search_engine(n_in_row=n_in_row, c_puct=c_puct, n_playout=n_playout, n_games=n_games,
-                                     node_capacity=node_capacity)
+                                     node_capacity=node_capacity, tag=tag)
         self.S = self.eng.S
         self.eng.boards_reset()
         self.eng.search_advance(-1)
-        self._hist = [[] for _ in range(n_games)]  # per game: (state bits, pi, player)
+        self._reset_history()
         self.finished_games = 0
         self.plies = 0
+        self.host_seconds = 0.0  # time spent outside ap_search_run (sampling, recording, re-rooting)
+
+    def _reset_history(self):
+        # per-ply records for ALL games (bit-packed state, pi, player to move); a finished game gathers its own rows
+        self._ply = 0
+        self._rec = {}                                  # ply -> (feats uint8[G][sb], pi float32[G][S], players int8[G])
+        self._start = np.zeros(self.G, np.int64)        # first ply of the current game of every slot
 
     def load_positions(self, cells, meta):
         """Start every slot from a given position (benchmark's synthetic positions)."""
         self.eng.boards_import(cells, meta)
         self.eng.search_advance(-1)
-        self._hist = [[] for _ in range(self.G)]
+        self._reset_history()
 
     def step(self):
         """One ply for every game.  Returns the list of finished-game records
-        [(winner, states uint8[n][9*S/8 packed], pis float64[n][S], z float64[n])]."""
+        [(winner, states uint8[n][ceil(9S/8)] bit-packed, pis float64[n][S], z float64[n])]."""
+        import time
         eng, G, S = self.eng, self.G, self.S
         eng.search_run(self.n_playout)
+        t0 = time.perf_counter()
         count, acts, visits, _, _ = eng.search_root()
         probs = visit_softmax(visits, count, self.temp)  # child order
         # sampling distribution: 0.75 p + 0.25 Dir(0.3)   (mcts_alphaZero.py:198-201)
@@ -64,13 +73,12 @@ class BatchedSelfPlay(object):
         idx = np.minimum((cdf <= u[:, None]).sum(axis=1), count - 1)
         moves = acts[np.arange(G), idx].astype(np.int32)
         if self.record_states:
-            feats = np.packbits(eng.boards_features().astype(np.uint8).reshape(G, -1), axis=1)
+            feats = eng.boards_features_packed()
             _, meta = eng.boards_export()
-            pi = np.zeros((G, S))
+            pi = np.zeros((G, S), np.float32)
             rows = np.nonzero(mask)
             pi[rows[0], acts[rows]] = probs[rows]
-            for g in range(G):
-                self._hist[g].append((feats[g], pi[g], int(meta[g, 0])))
+            self._rec[self._ply] = (feats, pi, meta[:, 0].astype(np.int8))
         eng.search_advance(moves)
         eng.boards_do_move(moves)
         end, winner = eng.boards_status()
@@ -79,18 +87,93 @@ class BatchedSelfPlay(object):
         out = []
         if len(done):
             for g in done:
-                h = self._hist[g]
-                if h:
-                    players = np.array([p for _, _, p in h])
-                    z = np.zeros(len(h))
+                t_first = int(self._start[g])
+                if self.record_states and self._ply >= t_first:
+                    plies = range(t_first, self._ply + 1)
+                    players = np.array([self._rec[t][2][g] for t in plies])
+                    z = np.zeros(len(players))
                     if winner[g] != -1:
                         z[players == winner[g]] = 1.0
                         z[players != winner[g]] = -1.0
-                    out.append((int(winner[g]), np.stack([s for s, _, _ in h]), np.stack([p for _, p, _ in h]), z))
+                    out.append((int(winner[g]), np.stack([self._rec[t][0][g] for t in plies]),
+                                np.stack([self._rec[t][1][g] for t in plies]).astype(np.float64), z))
                 else:
                     out.append((int(winner[g]), None, None, None))
-                self._hist[g] = []
+                self._start[g] = self._ply + 1
             eng.boards_reset(done)
             eng.search_advance(np.full(len(done), -1, np.int32), done)
             self.finished_games += len(done)
+        self._ply += 1
+        # plies older than every live game's start are no longer needed
+        if self.record_states and self._rec:
+            oldest = int(self._start.min())
+            for t in [t for t in self._rec if t < oldest]:
+                del self._rec[t]
+        self.host_seconds += time.perf_counter() - t0
         return out
+
+
+class PipelinedSelfPlay(object):
+    """``n_groups`` independent ``BatchedSelfPlay`` groups (own engine, own CUDA stream), each stepped by its own
+    host thread and started half a period apart: while one group is in its host phase (visit-count softmax,
+    Dirichlet sampling, recording, re-rooting: ~70 ms per 4096 games) the GPU runs the search kernels of the other.
+    ``ctypes`` releases the GIL inside ``ap_search_run``, so plain threads are enough.  Games stay independent.
+
+    ``step()`` returns the finished games of ONE group's next ply (``last_moves`` = plies it covered)."""
+
+    def __init__(self, net, n_games, n_groups=2, seed=0, **kw):
+        from concurrent.futures import ThreadPoolExecutor
+        per = n_games // n_groups
+        self.groups = [BatchedSelfPlay(net, per + (1 if i < n_games - per * n_groups else 0), seed=seed + i, tag=("pipe", i), **kw)
+                       for i in range(n_groups)]
+        self.G = sum(g.G for g in self.groups)
+        self.pool = ThreadPoolExecutor(n_groups)
+        self._fut = None
+        self._next = 0
+        self._backlog = []
+        self.last_moves = 0
+
+    def load_positions(self, cells, meta):
+        assert self._fut is None, "load_positions before the first step"
+        k = 0
+        for g in self.groups:
+            g.load_positions(cells[k:k + g.G], meta[k:k + g.G])
+            k += g.G
+
+    def _start(self):
+        import time
+        t0 = time.perf_counter()
+        self._backlog = self.groups[0].step()           # one ply of group 0 alone: measures the period
+        period = time.perf_counter() - t0
+        self._fut = [self.pool.submit(self.groups[0].step)]
+        for g in self.groups[1:]:                        # the others start staggered by period / n_groups
+            time.sleep(period / len(self.groups))
+            self._fut.append(self.pool.submit(g.step))
+
+    def step(self):
+        if self._fut is None:
+            self._start()
+        i = self._next
+        out = self._backlog + self._fut[i].result()
+        self._backlog = []
+        self._fut[i] = self.pool.submit(self.groups[i].step)
+        self._next = (i + 1) % len(self.groups)
+        self.last_moves = self.groups[i].G
+        return out
+
+    def drain(self):
+        """Wait for the plies in flight (call before reading engine state or shutting down)."""
+        out = []
+        if self._fut is not None:
+            for f in self._fut:
+                out.extend(f.result())
+            self._fut = None
+        return out
+
+    @property
+    def finished_games(self):
+        return sum(g.finished_games for g in self.groups)
+
+    @property
+    def host_seconds(self):
+        return sum(g.host_seconds for g in self.groups)

@@ -492,6 +492,52 @@ def run_gpu_pure(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# real self-play plies (BatchedSelfPlay.step: search + host-side sampling, recording, re-rooting); `--workload selfplay`
+# ------------------------------------------------------------------------------------------
+def run_gpu_selfplay(args):
+    import torch
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    from alphapig_b200.params import init_params
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    from alphapig_b200.selfplay import BatchedSelfPlay, PipelinedSelfPlay
+    G = args.games
+    arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
+    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=local)
+    kw = dict(n_playout=N_PLAYOUT, c_puct=C_PUCT, temp=1.0, n_in_row=N_IN_ROW, seed=0, node_capacity=2 * N_PLAYOUT * W * H + 2)
+    sp = PipelinedSelfPlay(net, G, n_groups=args.groups, **kw) if args.groups > 1 else BatchedSelfPlay(net, G, **kw)
+    parts = sp.groups if args.groups > 1 else [sp]
+    cm, k = [], 0
+    for part in parts:
+        cm.append(synthetic_positions(part.eng, part.G, seed0=1234 + k))
+        k += part.G
+    cells = np.concatenate([c for c, _ in cm])
+    meta = np.concatenate([m for _, m in cm])
+    sp.load_positions(cells, meta)
+    calls = args.groups if args.groups > 1 else 1   # one pipelined step() advances one group
+    for _ in range(args.warmup * calls):
+        sp.step()
+    torch.cuda.synchronize()
+    host0 = sp.host_seconds
+    t0 = time.perf_counter()
+    games = moves = 0
+    for _ in range(args.steps * calls):
+        games += len(sp.step())
+        moves += sp.last_moves if args.groups > 1 else G
+    dt = time.perf_counter() - t0
+    if args.groups > 1:
+        sp.drain()
+    print(json.dumps({"metric": "selfplay_moves_per_s", "value": moves / dt, "unit": "moves/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+                      "higher_is_better": True, "data": "synthetic start positions, then real self-play with tree reuse",
+                      "playouts_per_s": moves * N_PLAYOUT / dt,
+                      "host_ms_per_step": 1000 * (sp.host_seconds - host0) / args.steps, "groups": args.groups,
+                      "games_finished": games,
+                      "config": {"workload": "BatchedSelfPlay.step: %d games, n_playout=%d, temp=1.0, Dirichlet noise, records kept"
+                                             % (G, N_PLAYOUT)}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -500,13 +546,16 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--games", type=int, default=G_PER_GPU, help="concurrent games per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="az", choices=["az", "pure"],
+    ap.add_argument("--groups", type=int, default=2, help="selfplay workload: pipelined game groups (1 = none)")
+    ap.add_argument("--workload", default="az", choices=["az", "pure", "selfplay"],
                     help="az = BASELINE configs[1] (default, the headline metric); pure = configs[2] (mcts_pure, 1000 playouts)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "pure":
         run_gpu_pure(args)
+    elif args.workload == "selfplay":
+        run_gpu_selfplay(args)
     else:
         run_gpu(args)
 

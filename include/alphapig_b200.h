@@ -73,6 +73,8 @@ int ap_boards_status(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* 
 int ap_boards_legal(ap_engine* e, const int32_t* game_ids, int32_t n, uint32_t* out_mask /* [n][8] */);
 /* Board.current_state() -> float32 [n][9][width][height], flip included  game.py:68-94 */
 int ap_boards_features(ap_engine* e, const int32_t* game_ids, int32_t n, float* out);
+/* the same planes bit-packed, np.packbits order: uint8 [n][ceil(9*S/8)] (the record format of ap_replay_push) */
+int ap_boards_features_packed(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* out);
 /* Board.states / history / current_player / last_move                game.py:24-44 */
 int ap_boards_export(ap_engine* e, const int32_t* game_ids, int32_t n, int8_t* out_cells /* [n][S] 0,1,2 */,
                      int32_t* out_meta /* [n][AP_META_INTS] */);

@@ -105,3 +105,21 @@ def test_boards_random_vs_oracle_full_size():
         c, m = export_oboard(ob)
         assert np.array_equal(cells[g], c) and np.array_equal(meta[g, :7], m[:7])
     eng.close()
+
+
+def test_features_packed_equals_packbits():
+    """ap_boards_features_packed == np.packbits(ap_boards_features), incl. a non-square board"""
+    from alphapig_b200.engine import Engine
+    for (W, H, n) in ((15, 15, 5), (8, 8, 5), (7, 5, 4)):
+        G = 33
+        eng = Engine(width=W, height=H, n_in_row=n, n_games=G)
+        rs = np.random.RandomState(W)
+        for ply in range(6):
+            legal = eng.boards_legal()
+            mv = np.array([rs.choice(np.nonzero(legal[g])[0]) for g in range(G)], np.int32)
+            eng.boards_do_move(mv)
+            f = eng.boards_features()
+            assert np.array_equal(eng.boards_features_packed(), np.packbits(f.reshape(G, -1).astype(np.uint8), axis=1))
+        sub = np.array([5, 0, 17], np.int32)
+        assert np.array_equal(eng.boards_features_packed(sub), np.packbits(eng.boards_features(sub).reshape(3, -1).astype(np.uint8), axis=1))
+        eng.close()

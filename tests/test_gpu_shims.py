@@ -274,3 +274,30 @@ def test_batched_self_play_records():
             assert not z.any()
         else:
             assert z[-1] == 1.0 and all(z[i] == -z[i + 1] for i in range(n - 1))
+
+
+def test_pipelined_self_play_groups():
+    """Two staggered groups on their own engines / host threads produce well-formed game records and keep
+    counting plies per group."""
+    from alphapig_b200.params import init_params
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    from alphapig_b200.selfplay import PipelinedSelfPlay
+    W = 6
+    S = W * W
+    arg, aux = init_params("simple", W, W, seed=2, synthetic_stats=True)
+    net = PolicyValueNet(W, W, batch_size=16, model_params=(arg, aux), n_in_row=4)
+    sp = PipelinedSelfPlay(net, n_games=50, n_groups=2, n_playout=16, c_puct=5, temp=1.0, n_in_row=4, seed=1)
+    assert [g.G for g in sp.groups] == [25, 25] and sp.groups[0].eng is not sp.groups[1].eng
+    recs, moves = [], 0
+    for _ in range(90):
+        recs += sp.step()
+        moves += sp.last_moves
+        if len(recs) >= 20:
+            break
+    recs += sp.drain()
+    assert len(recs) >= 20 and sp.finished_games == len(recs)
+    for winner, states, pis, z in recs:
+        n = len(z)
+        assert states.shape == (n, (9 * S + 7) // 8) and np.allclose(pis.sum(1), 1.0)
+        planes = np.unpackbits(states, axis=1)[:, :9 * S].reshape(n, 9, W, W)
+        assert list(planes[:, 6].sum((1, 2)) + planes[:, 7].sum((1, 2))) == list(range(n))
