@@ -857,22 +857,24 @@ constexpr int kNT4 = 128;  // tile columns
 // iteration -> (board pair, column half) of one cluster.  Plain layers run column half 0 for all their board pairs,
 // then column half 1 (weights stay in the ring); the fused-head layer alternates the halves per board pair so that
 // one epilogue warp sees all 256 channels of its rows in two consecutive tiles and keeps the head sums in registers.
-template <bool HEAD>
+template <bool HEAD, int NHALVES>
 struct Tc4Iter {
   int n_my, cluster_id, n_clusters;
   __device__ Tc4Iter(int n_pairs, int cid, int ncl) : cluster_id(cid), n_clusters(ncl) {
     n_my = cid < n_pairs ? (n_pairs - cid + ncl - 1) / ncl : 0;
   }
-  __device__ int count() const { return 2 * n_my; }
-  __device__ int nh(int it) const { return HEAD ? (it & 1) : (it >= n_my ? 1 : 0); }
-  __device__ int bp(int it) const { return cluster_id + (HEAD ? (it >> 1) : (it >= n_my ? it - n_my : it)) * n_clusters; }
-  __device__ bool first_of_half(int it) const { return HEAD ? true : (it == 0 || it == n_my); }
+  __device__ int count() const { return NHALVES * n_my; }
+  __device__ int nh(int it) const { return NHALVES == 1 ? 0 : (HEAD ? (it & 1) : (it >= n_my ? 1 : 0)); }
+  __device__ int bp(int it) const {
+    return cluster_id + (NHALVES == 1 ? it : (HEAD ? (it >> 1) : (it >= n_my ? it - n_my : it))) * n_clusters;
+  }
+  __device__ bool first_of_half(int it) const { return HEAD ? true : (it == 0 || (NHALVES == 2 && it == n_my)); }
 };
 
-template <int KC, bool RESID, bool HEAD>
+template <int KC, bool RESID, bool HEAD, int COUT = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_conv3x3_tc4(const __grid_constant__ ConvParams p, const __grid_constant__ HeadArg<HEAD> hw) {
-  constexpr int COUT = 256;
+  static_assert(COUT == 256 || (COUT == 128 && !HEAD), "column tiles of 128: 128- or 256-channel layers");
   constexpr int TPS = kTps2;
   constexpr int STAGES_PER_KC = 9 / TPS;
   constexpr int ACC_STAGES = 2;
@@ -903,7 +905,7 @@ k_conv3x3_tc4(const __grid_constant__ ConvParams p, const __grid_constant__ Head
   float* s_hx = s_bias + COUT;                  // HEAD: [128][12] partial exchange between the two column-half warps
 
   const int n_boards = p.n_tiles_dev ? *p.n_tiles_dev : p.n_tiles;
-  const Tc4Iter<HEAD> iter((n_boards + 1) >> 1, blockIdx.x >> 1, gridDim.x >> 1);
+  const Tc4Iter<HEAD, COUT / kNT4> iter((n_boards + 1) >> 1, blockIdx.x >> 1, gridDim.x >> 1);
   const int n_iter = iter.count();
   // the ring holds exactly one column half of the layer: a stage keeps its content from tile to tile
   const bool keeps = !HEAD && p.nkc * STAGES_PER_KC == p.nb;
@@ -1204,9 +1206,9 @@ SmemPlan plan_smem4(int kc, int nkc, bool head) {
   return s;
 }
 
-template <int KC, bool RESID, bool HEAD>
+template <int KC, bool RESID, bool HEAD, int COUT = 256>
 int launch4(ap_engine* e, const ConvParams& p, const HeadArg<HEAD>& hw, int grid, int smem) {
-  k_conv3x3_tc4<KC, RESID, HEAD><<<grid, kThreads, smem, e->stream>>>(p, hw);
+  k_conv3x3_tc4<KC, RESID, HEAD, COUT><<<grid, kThreads, smem, e->stream>>>(p, hw);
   AP_LAUNCH_CHECK(e);
   return AP_OK;
 }
@@ -1311,6 +1313,8 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, true, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   return AP_OK;
 }
 
@@ -1363,6 +1367,16 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
                  : launch1s<128, 32, false, false>(e, p, none, grid, s.bytes);
   }
   // 256-channel layers without a fused head: two boards per CTA pair, 128-column tiles (AP_CONV4=0 disables)
+  if (n->conv4_128 && L.cout == 128 && kc == 64 && n->conv_mode == 0 && !head && (n->conv4_128 > 1 || L.cin_pad == 64)) {
+    p.wimg = L.wimg4;
+    const SmemPlan s4 = plan_smem4(kc, p.nkc, false);
+    p.ns = s4.ns;
+    p.nb = s4.nb;
+    const int pairs = n->sm_count / 2, bpairs = (n_boards + 1) / 2;
+    const int grid4 = 2 * (bpairs < pairs ? bpairs : pairs);
+    const HeadArg<false> none{};
+    return resid ? launch4<64, true, false, 128>(e, p, none, grid4, s4.bytes) : launch4<64, false, false, 128>(e, p, none, grid4, s4.bytes);
+  }
   if (n->conv4 && L.cout == 256 && kc == 64 && n->conv_mode == 0 && !(head && (resid || n->conv4 < 2))) {
     p.wimg = L.wimg4;
     const SmemPlan s4 = plan_smem4(kc, p.nkc, head);

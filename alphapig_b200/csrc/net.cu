@@ -462,7 +462,7 @@ static int conv_bind(ap_engine* e, NetState* n, ConvLayer& L, const std::string&
   AP_TRY(nalloc(e, n, (void**)&L.wimg, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.wimg2, (size_t)9 * L.cin_pad * L.cout * 2));
   if (n->split) AP_TRY(nalloc(e, n, (void**)&L.wimg_lo, (size_t)9 * L.cin_pad * L.cout * 2));
-  if (L.cout == 256 && L.cin_pad % 64 == 0) AP_TRY(nalloc(e, n, (void**)&L.wimg4, (size_t)9 * L.cin_pad * L.cout * 2));
+  if ((L.cout == 256 || L.cout == 128) && L.cin_pad % 64 == 0 && !n->split) AP_TRY(nalloc(e, n, (void**)&L.wimg4, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.scale, (size_t)L.cout * 4));
   AP_TRY(nalloc(e, n, (void**)&L.shift, (size_t)L.cout * 4));
   return AP_OK;
@@ -492,6 +492,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device);
   if (const char* m = getenv("AP_CONV_MODE")) n->conv_mode = (m[0] == '1') ? 1 : (m[0] == '2') ? 2 : 0;
   if (const char* m = getenv("AP_CONV4")) n->conv4 = m[0] - '0';
+  if (const char* m = getenv("AP_CONV4_128")) n->conv4_128 = m[0] - '0';
   if (const char* m = getenv("AP_HEAD_PAIR")) n->head_pair = m[0] != '0';
   if (const char* m = getenv("AP_HEAD_MODE")) n->head_mode = (m[0] == '0') ? 0 : (m[0] == '1') ? 1 : 2;
   long long total = 0;

@@ -82,6 +82,7 @@ struct NetState {
   int conv_mode = 0;  // 0 = per-layer choice, 1 = single-CTA kernel, 2 = CTA-pair kernel (cta_group::2); AP_CONV_MODE overrides for A/B timing
   int conv4 = 2;      // 256-channel layers on the two-boards-per-pair kernel: 0 off, 1 plain layers, 2 also the
                       // fused-head layer (AP_CONV4 for A/B timing)
+  int conv4_128 = 0;  // 128-channel layers on that kernel too: 1 = cin 64 (conv3), 2 = all (AP_CONV4_128, A/B timing)
   NetHeadW head_w;
   int head_pair = 1;  // run the fused-head layer on the CTA-pair kernel (measured faster: its double-buffered TMEM hides
                       // the longer epilogue); AP_HEAD_PAIR=0 selects the single-CTA kernel for A/B timing
