@@ -46,6 +46,8 @@ struct ConvParams {
   const __half* wimg_lo;
   const float* bias;  // folded BN shift; the BN scale is folded into the fp16 weights
   long long mpad;
+  int out_coff;     // the COUT output channels land at channels [out_coff, out_coff + cout_store) of the output planes
+  int cout_store;   // channels actually stored (a multiple of 8; the rest are zero-weight padding)
   int nkc, relu;
   int n_tiles, W, H;
   const int* n_tiles_dev;  // when non-null the tile count is read from device memory (compacted leaf batches)
@@ -141,7 +143,8 @@ __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEA
 #pragma unroll
   for (int gi = 0; gi < NG; ++gi) {
     const int c = c0 + gi * 8;
-    const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;
+    const long long idx = ((long long)(c >> 3) * p.mpad + grow) * 8;                    // residual operand (same channel)
+    const long long oidx = ((long long)((c + p.out_coff) >> 3) * p.mpad + grow) * 8;     // output
     const float4 b0 = lds128(s_bias + c * 4);
     const float4 b1 = lds128(s_bias + c * 4 + 16);
     float f[8];
@@ -181,6 +184,8 @@ __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEA
 #pragma unroll
         for (int k = 0; k < 8; ++k) hacc[o] = fmaf(f[k], hw.h.w[o * COUT + c + k], hacc[o]);
       }
+    } else if (c >= p.cout_store) {
+      // zero-weight padding channels of a narrower layer: nothing to store
     } else if constexpr (SPLIT) {
       uint4 ov, ol;
       __half2* oh = reinterpret_cast<__half2*>(&ov);
@@ -201,8 +206,8 @@ __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEA
         ov = make_uint4(0u, 0u, 0u, 0u);
         ol = ov;
       }
-      *reinterpret_cast<uint4*>(p.out + idx) = ov;
-      *reinterpret_cast<uint4*>(p.out_lo + idx) = ol;
+      *reinterpret_cast<uint4*>(p.out + oidx) = ov;
+      *reinterpret_cast<uint4*>(p.out_lo + oidx) = ol;
     } else {
       uint4 ov;
       __half2* oh = reinterpret_cast<__half2*>(&ov);
@@ -214,7 +219,7 @@ __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEA
         oh[k] = h;
       }
       if (!valid) ov = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(p.out + idx) = ov;
+      *reinterpret_cast<uint4*>(p.out + oidx) = ov;
     }
   }
 }
@@ -293,14 +298,15 @@ struct EpiCfg {
   static constexpr int THREADS = 32 * (kCtrlWarps + WARPS);
 };
 
-template <int COUT, int KC, bool RESID, bool HEAD, bool SPLIT = false>
+// TAPS = 9: 3x3 conv; TAPS = 1: 1x1 conv (only the centre tap of the same slab)
+template <int COUT, int KC, bool RESID, bool HEAD, bool SPLIT = false, int TAPS = 9>
 __global__ void __launch_bounds__(EpiCfg<HEAD>::THREADS, 1)
 k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadArg<HEAD> hw) {
   using Cfg = ConvCfg<COUT>;
   constexpr int EPI = EpiCfg<HEAD>::WARPS;
   constexpr int NTHR = EpiCfg<HEAD>::THREADS;
-  constexpr int TPS = Cfg::TPS;
-  constexpr int STAGES_PER_KC = 9 / TPS;
+  constexpr int TPS = TAPS == 1 ? 1 : Cfg::TPS;
+  constexpr int STAGES_PER_KC = TAPS / TPS;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
   constexpr int KG = KC / 8;                              // 8-channel groups per K-chunk
   constexpr uint32_t SLAB_HALF = KG * kSlabGroupBytes;                 // one of hi / lo; multiple of 16
@@ -394,10 +400,10 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
           if (elect_one()) {
             mbar_expect_tx(bb, STAGE_BYTES);
             bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES),
-                     p.wimg + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
+                     p.wimg + (size_t)(kc * TAPS + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
             if constexpr (SPLIT)
               bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES + STAGE_HALF),
-                       p.wimg_lo + (size_t)(kc * 9 + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
+                       p.wimg_lo + (size_t)(kc * TAPS + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
           }
           __syncwarp();
           if (++bs == p.nb) { bs = 0; bph ^= 1; }
@@ -441,7 +447,7 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
 #pragma unroll
             for (int t = 0; t < TPS; ++t) {
               const int tap = ts * TPS + t;
-              const int off = 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
+              const int off = TAPS == 1 ? 17 : 17 + (tap / 3 - 1) * 16 + (tap % 3 - 1);
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -1146,14 +1152,14 @@ struct SmemPlan {
 constexpr int head_smem_bytes(int) { return 2 * 128 * 6 * 4; }
 
 // slabs + B ring + barriers + TMEM slot + bias inside the 227 KB opt-in limit
-SmemPlan plan_smem(int cout, int kc, int nkc, bool head, bool split = false) {
-  const int tps = (cout == 256) ? 1 : 3;
+SmemPlan plan_smem(int cout, int kc, int nkc, bool head, bool split = false, int taps = 9) {
+  const int tps = (cout == 256 || taps == 1) ? 1 : 3;
   const int mul = split ? 2 : 1;
   const int slab = ((mul * (kc >> 3) * kSlabGroupBytes) + 127) & ~127;
   const int stage = mul * tps * kc * cout * 2;
   const int fixed = (2 * kMaxSlabs + 2 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128 + (head ? head_smem_bytes(cout) : 0);
   const int budget = 227 * 1024 - fixed;
-  const int all = nkc * (9 / tps);  // stages that hold the whole layer
+  const int all = nkc * (taps / tps);  // stages that hold the whole layer
   SmemPlan s;
   if (all <= kMaxStages && 2 * slab + all * stage <= budget) {
     s.nb = all;  // resident weights; spend what is left on a deeper slab ring
@@ -1263,6 +1269,15 @@ int launch1s(ap_engine* e, const ConvParams& p, const HeadArg<HEAD>& hw, int gri
   return AP_OK;
 }
 
+// 1x1 instantiations (Inception-ResNet variant: tower stems and the up-projection, 128 -> 128)
+template <bool RESID>
+int launch1x1(ap_engine* e, const ConvParams& p, int grid, int smem) {
+  const HeadArg<false> none{};
+  k_conv3x3_tc<128, 64, RESID, false, false, 1><<<grid, kThreads, smem, e->stream>>>(p, none);
+  AP_LAUNCH_CHECK(e);
+  return AP_OK;
+}
+
 // HEAD instantiations: the last trunk layer of the simple net (256 -> 256, no residual) and of the
 // residual net (128 -> 128 with residual)
 cudaError_t optin_head() {
@@ -1310,6 +1325,8 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, (optin_t<256, 64>()));
   AP_CUDA(e, optin_head());
   AP_CUDA(e, optin_split());
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc<128, 64, false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc<128, 64, true, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
@@ -1331,6 +1348,8 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   p.wimg_lo = L.wimg_lo;
   p.bias = L.shift;
   p.mpad = n->mpad;
+  p.out_coff = L.out_coff;
+  p.cout_store = L.cout_store > 0 ? L.cout_store : L.cout;
   const int kc = conv_tc_kc(L, split);
   p.nkc = L.cin_pad / kc;
   p.relu = L.relu;
@@ -1348,6 +1367,15 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   if (!conv_tc_supported(L.cin_pad, L.cout)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
   if (head && !conv_tc_head_supported(L)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: no fused-head instantiation for this layer");
   const bool resid = p.resid != nullptr;
+  if (L.ksz == 1) {
+    // 1x1 conv: single-CTA kernel, centre tap only
+    if (split || head || L.cout != 128 || kc != 64) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: 1x1 convs are built for 128 output channels");
+    const SmemPlan s1 = plan_smem(L.cout, kc, p.nkc, false, false, 1);
+    p.ns = s1.ns;
+    p.nb = s1.nb;
+    const int grid1 = n_boards < n->sm_count ? n_boards : n->sm_count;
+    return resid ? launch1x1<true>(e, p, grid1, s1.bytes) : launch1x1<false>(e, p, grid1, s1.bytes);
+  }
   if (split) {
     // near-fp32 path of the residual net: single-CTA kernel, three products per K step
     if (!conv_tc_split_supported(L)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: no split-precision instantiation for this layer");
@@ -1367,7 +1395,7 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
                  : launch1s<128, 32, false, false>(e, p, none, grid, s.bytes);
   }
   // 256-channel layers without a fused head: two boards per CTA pair, 128-column tiles (AP_CONV4=0 disables)
-  if (n->conv4_128 && L.cout == 128 && kc == 64 && n->conv_mode == 0 && !head && (n->conv4_128 > 1 || L.cin_pad == 64)) {
+  if (n->conv4_128 && !L.force_single && L.cout == 128 && kc == 64 && n->conv_mode == 0 && !head && (n->conv4_128 > 1 || L.cin_pad == 64)) {
     p.wimg = L.wimg4;
     const SmemPlan s4 = plan_smem4(kc, p.nkc, false);
     p.ns = s4.ns;
@@ -1394,7 +1422,8 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   }
   // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks, the fused-head
   // layer); the memory-bound small layers run the single-CTA kernel
-  const bool pair = n->conv_mode == 2 || (n->conv_mode == 0 && (L.cin_pad == 128 || (head && n->head_pair)));
+  const bool pair = !L.force_single &&
+                    (n->conv_mode == 2 || (n->conv_mode == 0 && (L.cin_pad == 128 || (head && n->head_pair))));
   SmemPlan s;
   int grid;
   if (pair) {

@@ -23,9 +23,10 @@
 // prep kernels (run at load and after every weight refresh)
 // ------------------------------------------------------------------------------------------
 __global__ void k_prep_conv(const float* __restrict__ master, long long w, long long b, long long gamma, long long beta,
-                            long long mean, long long var, int fix_gamma, int cin, int cin_pad, int cout, int kc,
-                            __half* wimg, __half* wimg2, __half* wimg_lo, __half* wimg4, float* scale, float* shift) {
-  const long long total = (long long)9 * cin_pad * cout;
+                            long long mean, long long var, int fix_gamma, int cin, int cin_pad, int cout, int kc, int ntaps,
+                            float post, __half* wimg, __half* wimg2, __half* wimg_lo, __half* wimg4, float* scale,
+                            float* shift) {
+  const long long total = (long long)ntaps * cin_pad * cout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     // image order: [kcI][tap][j][n][e]
     int e = (int)(i & 7);
@@ -34,22 +35,22 @@ __global__ void k_prep_conv(const float* __restrict__ master, long long w, long 
     r /= cout;
     int j = (int)(r % (kc >> 3));
     r /= (kc >> 3);
-    int tap = (int)(r % 9);
-    int kcI = (int)(r / 9);
+    int tap = (int)(r % ntaps);
+    int kcI = (int)(r / ntaps);
     int k = kcI * kc + j * 8 + e;
-    float sc = 1.f / sqrtf(master[var + n] + BN_EPS);
+    float sc = post / sqrtf(master[var + n] + BN_EPS);
     if (!fix_gamma) sc *= master[gamma + n];
-    float v = (k < cin) ? master[w + ((long long)n * cin + k) * 9 + tap] * sc : 0.f;  // BN scale folded in fp32
+    float v = (k < cin) ? master[w + ((long long)n * cin + k) * ntaps + tap] * sc : 0.f;  // BN scale folded in fp32
     const __half vh = __float2half_rn(v);
     wimg[i] = vh;
     if (wimg_lo) wimg_lo[i] = __float2half_rn(v - __half2float(vh));
     // CTA-pair image: [r][kcI][tap][j][n'][e], n = r*cout/2 + n'
     const int nh = cout >> 1, rr = n / nh, np = n - rr * nh;
-    const long long i2 = ((((long long)rr * (cin_pad / kc) + kcI) * 9 + tap) * (kc >> 3) + j) * nh * 8 + (long long)np * 8 + e;
+    const long long i2 = ((((long long)rr * (cin_pad / kc) + kcI) * ntaps + tap) * (kc >> 3) + j) * nh * 8 + (long long)np * 8 + e;
     wimg2[i2] = __float2half_rn(v);
     if (wimg4) {  // [nh][r][kcI][tap][j][n''][e], n = nh*128 + r*64 + n''
       const int nh4 = n >> 7, r4 = (n >> 6) & 1, n4 = n & 63;
-      const long long i4 = (((((long long)nh4 * 2 + r4) * (cin_pad / kc) + kcI) * 9 + tap) * (kc >> 3) + j) * 64 * 8 +
+      const long long i4 = (((((long long)nh4 * 2 + r4) * (cin_pad / kc) + kcI) * ntaps + tap) * (kc >> 3) + j) * 64 * 8 +
                            (long long)n4 * 8 + e;
       wimg4[i4] = vh;
     }
@@ -57,9 +58,31 @@ __global__ void k_prep_conv(const float* __restrict__ master, long long w, long 
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < cout; n += gridDim.x * blockDim.x) {
     float s = 1.f / sqrtf(master[var + n] + BN_EPS);
     if (!fix_gamma) s *= master[gamma + n];
-    scale[n] = s;
-    shift[n] = (master[b + n] - master[mean + n]) * s + master[beta + n];
+    scale[n] = s * post;
+    shift[n] = ((master[b + n] - master[mean + n]) * s + master[beta + n]) * post;
   }
+}
+
+// Inception-ResNet variant: one named conv (weight [cout][cin][taps], bias, beta, mean, var) copied into the
+// (oo, io) block of a wider zero-initialised "virtual" conv (its var initialised to 1): several towers that read
+// the same input become one layer, a tower reading a channel slice becomes a layer over the whole buffer.
+__global__ void k_build_virtual(const float* __restrict__ master, float* vm, NetState::VCopy c) {
+  const long long nw = (long long)c.cout * c.cin * c.taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % c.taps);
+    const int ci = (int)((i / c.taps) % c.cin);
+    const int o = (int)(i / ((long long)c.taps * c.cin));
+    vm[c.dst_w + ((long long)(c.oo + o) * c.cin_v + (c.io + ci)) * c.taps + t] = master[c.src_w + i];
+  }
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < c.cout; o += gridDim.x * blockDim.x) {
+    vm[c.dst_b + c.oo + o] = master[c.src_b + o];
+    vm[c.dst_beta + c.oo + o] = master[c.src_beta + o];
+    vm[c.dst_mean + c.oo + o] = master[c.src_mean + o];
+    vm[c.dst_var + c.oo + o] = master[c.src_var + o];
+  }
+}
+__global__ void k_fill_range(float* p, long long off, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[off + i] = v;
 }
 
 __global__ void k_prep_heads(const float* __restrict__ master, HeadParams h, int S) {
@@ -422,10 +445,22 @@ int net_destroy(ap_engine* e) {
 
 static int net_prep(ap_engine* e) {
   NetState* n = e->net;
+  if (n->vmaster) {
+    AP_CUDA(e, cudaMemsetAsync(n->vmaster, 0, (size_t)n->vmaster_numel * 4, e->stream));
+    for (size_t i = 0; i + 1 < n->vvar_ranges.size(); i += 2) {
+      k_fill_range<<<8, 256, 0, e->stream>>>(n->vmaster, n->vvar_ranges[i], n->vvar_ranges[i + 1], 1.f);
+      AP_LAUNCH_CHECK(e);
+    }
+    for (auto& c : n->vcopies) {
+      k_build_virtual<<<64, 256, 0, e->stream>>>(n->master, n->vmaster, c);
+      AP_LAUNCH_CHECK(e);
+    }
+  }
   for (auto& L : n->trunk) {
     const int kc = conv_tc_kc(L, n->split);
-    k_prep_conv<<<256, 256, 0, e->stream>>>(n->master, L.w, L.b, L.gamma, L.beta, L.mean, L.var, L.fix_gamma, L.cin,
-                                            L.cin_pad, L.cout, kc, L.wimg, L.wimg2, L.wimg_lo, L.wimg4, L.scale, L.shift);
+    k_prep_conv<<<256, 256, 0, e->stream>>>(L.virt ? n->vmaster : n->master, L.w, L.b, L.gamma, L.beta, L.mean, L.var,
+                                            L.fix_gamma, L.cin, L.cin_pad, L.cout, kc, L.ksz * L.ksz, L.post_scale, L.wimg,
+                                            L.wimg2, L.wimg_lo, L.wimg4, L.scale, L.shift);
     AP_LAUNCH_CHECK(e);
   }
   k_prep_heads<<<256, 256, 0, e->stream>>>(n->master, n->head, n->S);
@@ -439,6 +474,7 @@ static int net_prep(ap_engine* e) {
   return AP_OK;
 }
 
+static int conv_alloc(ap_engine* e, NetState* n, ConvLayer& L);
 static int conv_bind(ap_engine* e, NetState* n, ConvLayer& L, const std::string& cname, const std::string& bnname,
                      bool conv_act_style, std::string* err) {
   const long long wn = (long long)L.cout * L.cin * 9;
@@ -458,6 +494,10 @@ static int conv_bind(ap_engine* e, NetState* n, ConvLayer& L, const std::string&
     L.fix_gamma = 0;
   }
   if (L.w < 0 || L.b < 0 || L.gamma < 0 || L.beta < 0 || L.mean < 0 || L.var < 0) return AP_ERR_BAD_ARG;
+  return conv_alloc(e, n, L);
+}
+
+static int conv_alloc(ap_engine* e, NetState* n, ConvLayer& L) {
   L.cin_pad = (L.cin + 15) & ~15;
   AP_TRY(nalloc(e, n, (void**)&L.wimg, (size_t)9 * L.cin_pad * L.cout * 2));
   AP_TRY(nalloc(e, n, (void**)&L.wimg2, (size_t)9 * L.cin_pad * L.cout * 2));
@@ -476,7 +516,8 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
     return ap_fail(e, AP_ERR_BAD_ARG, "the net path needs a square board of width <= 15");
   const int split = (arch & AP_NET_SPLIT) != 0;
   arch &= ~AP_NET_SPLIT;
-  if (arch != AP_ARCH_SIMPLE && arch != AP_ARCH_RESNET) return ap_fail(e, AP_ERR_BAD_ARG, "unknown arch");
+  if (arch != AP_ARCH_SIMPLE && arch != AP_ARCH_RESNET && arch != AP_ARCH_INCEPTION)
+    return ap_fail(e, AP_ERR_BAD_ARG, "unknown arch");
   if (split && arch != AP_ARCH_RESNET)
     return ap_fail(e, AP_ERR_BAD_ARG, "AP_NET_SPLIT is implemented for the residual net only (the 6-conv net meets 1e-3 in fp16)");
   net_destroy(e);
@@ -536,6 +577,68 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
     }
     n->final_buf = buf;
     n->head.cfin = cin;
+  } else if (arch == AP_ARCH_INCEPTION) {
+    // builder-defined board-sized Inception-ResNet: 3x3 stem + n_blocks x block35 (inception-resnet-v2.py:41-58), see
+    // alphapig_b200/params.py.  Per block, on buffers X (block input), T0, T1, Y:
+    //   mix1 : 1x1  X(128) -> T0 = [t0 32 | t1a 32 | t2a 32 | 0 32]      the three tower stems in one layer
+    //   t1b  : 3x3  T0 (input channels 32..63) -> T0[32:64]               in place: a tile reads its board before it writes
+    //   t2b  : 3x3  T0 (input channels 64..95) -> T1 (48 of 64)
+    //   t2c  : 3x3  T1 -> T0[64:128]      T0 is now the concat [t0 | t1b | t2c]
+    //   up   : 1x1  T0(128) -> Y = relu(X + 0.17 * BN(conv))
+    if (n_blocks < 1 || n_filter != 128) return bad(ap_fail(e, AP_ERR_BAD_ARG, "inception: n_filter must be 128, n_blocks >= 1"));
+    ConvLayer L{};
+    L.cin = 9; L.cout = 128; L.relu = 1; L.in_buf = -1; L.out_buf = 0; L.resid_buf = -1; L.force_single = 1;
+    if ((rc = conv_bind(e, n, L, "incep_conv1", "", true, &err)) != AP_OK) return bad(rc);
+    n->trunk.push_back(L);
+    long long vtot = 0;
+    auto valloc = [&](long long cnt) { long long o = vtot; vtot += (cnt + 3) & ~3ll; return o; };
+    struct Piece { const char* name; int cout, cin, oo, io; };
+    auto vlayer = [&](int blk, int cin_v, int cout_v, int ksz, std::vector<Piece> pieces, int in_buf, int out_buf,
+                      int out_coff, int cout_store, int resid_buf, int relu, float post) -> int {
+      ConvLayer V{};
+      V.cin = cin_v; V.cout = cout_v; V.ksz = ksz; V.relu = relu; V.in_buf = in_buf; V.out_buf = out_buf;
+      V.resid_buf = resid_buf; V.out_coff = out_coff; V.cout_store = cout_store; V.force_single = 1; V.virt = 1;
+      V.fix_gamma = 1; V.post_scale = post;
+      const int taps = ksz * ksz;
+      V.w = valloc((long long)cout_v * cin_v * taps);
+      V.b = valloc(cout_v); V.beta = valloc(cout_v); V.mean = valloc(cout_v); V.var = valloc(cout_v);
+      V.gamma = V.beta;  // unused (fix_gamma)
+      n->vvar_ranges.push_back(V.var);
+      n->vvar_ranges.push_back(cout_v);
+      for (auto& pc : pieces) {
+        const std::string nm = "b35_" + std::to_string(blk) + "_" + pc.name;
+        NetState::VCopy c{};
+        c.dst_w = V.w; c.dst_b = V.b; c.dst_beta = V.beta; c.dst_mean = V.mean; c.dst_var = V.var;
+        c.src_w = off_of(n, nm + "_weight", (long long)pc.cout * pc.cin * taps, &err);
+        c.src_b = off_of(n, nm + "_bias", pc.cout, &err);
+        c.src_beta = off_of(n, nm + "_beta", pc.cout, &err);
+        c.src_mean = off_of(n, nm + "_mean", pc.cout, &err);
+        c.src_var = off_of(n, nm + "_var", pc.cout, &err);
+        off_of(n, nm + "_gamma", pc.cout, &err);  // present in the table (fix_gamma: value unused)
+        if (!err.empty()) return AP_ERR_BAD_ARG;
+        c.cout = pc.cout; c.cin = pc.cin; c.cin_v = cin_v; c.taps = taps; c.oo = pc.oo; c.io = pc.io;
+        n->vcopies.push_back(c);
+      }
+      int r2 = conv_alloc(e, n, V);
+      if (r2 != AP_OK) return r2;
+      n->trunk.push_back(V);
+      return AP_OK;
+    };
+    int x = 0;  // buffers: 0 / 1 = block input / output (ping-pong), 2 = T0, 3 = T1
+    for (int i = 1; i <= n_blocks; ++i) {
+      const int y = 1 - x;
+      if ((rc = vlayer(i, 128, 128, 1, {{"t0", 32, 128, 0, 0}, {"t1a", 32, 128, 32, 0}, {"t2a", 32, 128, 64, 0}}, x, 2, 0, 128, -1, 1, 1.f)) != AP_OK) return bad(rc);
+      if ((rc = vlayer(i, 128, 64, 3, {{"t1b", 32, 32, 0, 32}}, 2, 2, 32, 32, -1, 1, 1.f)) != AP_OK) return bad(rc);
+      if ((rc = vlayer(i, 128, 64, 3, {{"t2b", 48, 32, 0, 64}}, 2, 3, 0, 64, -1, 1, 1.f)) != AP_OK) return bad(rc);
+      if ((rc = vlayer(i, 64, 64, 3, {{"t2c", 64, 48, 0, 0}}, 3, 2, 64, 64, -1, 1, 1.f)) != AP_OK) return bad(rc);
+      if ((rc = vlayer(i, 128, 128, 1, {{"up", 128, 128, 0, 0}}, 2, y, 0, 128, x, 1, 0.17f)) != AP_OK) return bad(rc);
+      x = y;
+    }
+    n->vmaster_numel = vtot;
+    if ((rc = nalloc(e, n, (void**)&n->vmaster, (size_t)vtot * 4)) != AP_OK) return bad(rc);
+    n->final_buf = x;
+    n->head.cfin = 128;
+    n->head_mode = n->head_mode == 0 ? 0 : 1;  // no fused-head instantiation for the 1x1 up-projection
   } else {
     if (n_blocks < 0 || n_filter != 128)
       return bad(ap_fail(e, AP_ERR_BAD_ARG, "resnet: n_filter must be 128 (stem is hard-coded 128, policy_value_net_mxnet.py:73)"));
@@ -597,7 +700,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   n->mpad = 2ll * NET_PAD_ROWS + (long long)n->bcap * NET_TILE_ROWS;
   int maxc = 0;
   for (auto& L : n->trunk) maxc = L.cout > maxc ? L.cout : maxc;
-  const int nbuf = (arch == AP_ARCH_RESNET) ? 3 : 2;
+  const int nbuf = (arch == AP_ARCH_INCEPTION) ? 4 : (arch == AP_ARCH_RESNET) ? 3 : 2;
   if ((rc = nalloc(e, n, (void**)&n->feat, (size_t)2 * n->mpad * 16)) != AP_OK) return bad(rc);
   for (int i = 0; i < nbuf; ++i)
     if ((rc = nalloc(e, n, (void**)&n->act[i], (size_t)(maxc / 8) * n->mpad * 16)) != AP_OK) return bad(rc);
@@ -696,6 +799,8 @@ static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values, const
 // fp32 path on dense NCHW states (device) for nb <= bcap_ref boards
 static int run_ref(ap_engine* e, const float* d_states, int nb, float* d_probs, float* d_values) {
   NetState* n = e->net;
+  if (n->arch == AP_ARCH_INCEPTION)
+    return ap_fail(e, AP_ERR_BAD_ARG, "the fp32 CUDA-core cross-check path is not built for the inception variant");
   const int S = n->S, W = n->W, H = n->H;
   float* bufs[3] = {n->ref_a, n->ref_b, n->ref_c};
   auto conv = [&](const float* in, float* out, const float* resid, long long w, long long b, long long gamma,

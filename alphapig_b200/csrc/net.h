@@ -15,6 +15,13 @@ struct ConvLayer {
   // offsets into the flat fp32 master buffer (-1 = absent)
   long long w, b, gamma, beta, mean, var;
   int fix_gamma;
+  // Inception-ResNet variant: 1x1 convs, channel-slice outputs and composite (block-assembled) weight tensors
+  int ksz = 3;            // 3 or 1
+  int out_coff = 0;       // output channel offset inside the output planes
+  int cout_store = 0;     // channels stored (0 = cout)
+  int force_single = 0;   // always the single-CTA kernel (the slice stores / 1x1 taps live there)
+  int virt = 0;           // parameter offsets index NetState::vmaster (assembled by k_build_virtual) instead of master
+  float post_scale = 1.f; // folded after BN (block35: net += 0.17 * up)
   // prepared (device)
   __half* wimg = nullptr;  // [nkc][9][KC/8][cout][8]
   __half* wimg2 = nullptr; // CTA-pair image [2][nkc][9][KC/8][cout/2][8]: half r holds output channels [r*cout/2, (r+1)*cout/2)
@@ -53,10 +60,17 @@ struct NetState {
   std::map<std::string, int> index;
   float* master = nullptr;
   long long master_numel = 0;
+  // Inception-ResNet variant: dense "virtual" conv parameters assembled from several named convs
+  struct VCopy { long long dst_w, dst_b, dst_beta, dst_mean, dst_var, src_w, src_b, src_beta, src_mean, src_var;
+                 int cout, cin, cin_v, taps, oo, io; };
+  float* vmaster = nullptr;
+  long long vmaster_numel = 0;
+  std::vector<long long> vvar_ranges;  // (offset, count) pairs of virtual `var` arrays: reset to 1 before assembling
+  std::vector<VCopy> vcopies;
   std::vector<ConvLayer> trunk;
   HeadParams head;
   __half* feat = nullptr;      // [2][mpad][8]
-  __half* act[3] = {nullptr, nullptr, nullptr};  // [32][mpad][8]
+  __half* act[4] = {nullptr, nullptr, nullptr, nullptr};  // [32][mpad][8]
   // split precision (AP_NET_SPLIT): every activation is a hi + lo fp16 pair (22 significant bits), every weight too,
   // and the conv kernels issue hi*hi + lo*hi + hi*lo: what the 10-block residual net needs to stay within 1e-3
   int split = 0;

@@ -258,7 +258,7 @@ class Engine(object):
             arr[i].name = k.encode()
             arr[i].data = a.ctypes.data
             arr[i].numel = a.size
-        code = L.AP_ARCH_SIMPLE if arch == "simple" else L.AP_ARCH_RESNET
+        code = {"simple": L.AP_ARCH_SIMPLE, "resnet": L.AP_ARCH_RESNET, "inception": L.AP_ARCH_INCEPTION}[arch]
         if split:
             code |= L.AP_NET_SPLIT
         self._check(self.lib.ap_net_load(self.h, code, int(n_blocks), int(n_filter), arr, len(names)))

@@ -72,7 +72,7 @@ class PolicyValueNetBase(object):
         else:
             merged = OrderedDict(arg)
             merged.update(aux)
-        eng.net_load(self.arch, merged, n_blocks=self._n_blocks if self.arch == "resnet" else 0,
+        eng.net_load(self.arch, merged, n_blocks=self._n_blocks if self.arch != "simple" else 0,
                      n_filter=self._n_filter, precision=self._precision)
         return eng
 
@@ -166,6 +166,6 @@ class PolicyValueNetBase(object):
         arg = OrderedDict((k, views[k]) for k in self._arg_names)
         aux = OrderedDict((k, views[k]) for k in self._aux_names)
         loss, entropy = T.train_step(arg, aux, self._opt, x, pi, z, float(learning_rate), self.arch,
-                                     self._n_blocks if self.arch == "resnet" else 0, wd=self.l2_const)
+                                     self._n_blocks if self.arch != "simple" else 0, wd=self.l2_const)
         self.sync_replicas()
         return loss.reshape(1).cpu().numpy(), entropy.reshape(1).cpu().numpy()

@@ -6,6 +6,15 @@ from collections import OrderedDict
 
 import numpy as np
 
+# builder-defined board-sized Inception-ResNet variant (BASELINE configs[3]): the reference's inception-resnet-v2.py is an
+# unwired ImageNet symbol (strides / pooling collapse a 15x15 plane), so the variant keeps what transfers: a 3x3 stem and
+# n_blocks x block35 (inception-resnet-v2.py:41-58: towers 1x1(32) | 1x1(32)-3x3(32) | 1x1(32)-3x3(48)-3x3(64), concat 128,
+# 1x1 up-projection with BN and no activation, net += 0.17 * up, ReLU), every conv = ConvFactory (conv + bias, BatchNorm with
+# the default fix_gamma=True, ReLU), then the reference's policy / value heads.
+INCEPTION_SCALE = 0.17
+BLOCK35 = (("t0", None, 32, 1), ("t1a", None, 32, 1), ("t1b", 32, 32, 3), ("t2a", None, 32, 1), ("t2b", 32, 48, 3),
+           ("t2c", 48, 64, 3), ("up", 128, None, 1))  # (name, cin (None = block input), cout (None = block input), k)
+
 SIMPLE_TRUNK = (("conv1", 9, 64), ("conv2", 64, 64), ("conv3", 64, 128), ("conv4", 128, 128),
                 ("conv5", 128, 256), ("conv_final", 256, 256))
 
@@ -39,8 +48,14 @@ def param_shapes(arch, width, height, n_blocks=8, n_filter=128):
                 aux["bn%s%d_moving_var" % (tag, i)] = (n_filter,)
             cin = n_filter
         cfin = n_filter
+    elif arch == "inception":
+        conv_act("incep_conv1", 9, n_filter, 3)
+        for i in range(1, n_blocks + 1):
+            for name, cin, cout, k in BLOCK35:
+                conv_act("b35_%d_%s" % (i, name), cin or n_filter, cout or n_filter, k)
+        cfin = n_filter
     else:
-        raise ValueError("arch must be 'simple' or 'resnet'")
+        raise ValueError("arch must be 'simple', 'resnet' or 'inception'")
     conv_act("conv3_1_1", cfin, 4, 1)
     arg["fc_3_1_1_weight"] = (S, 4 * S)
     arg["fc_3_1_1_bias"] = (S,)

@@ -24,6 +24,8 @@ BN_MOMENTUM = 0.9
 def trunk_plan(arch, n_blocks):
     if arch == "simple":
         return [("conv_act", n) for n in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv_final")]
+    if arch == "inception":
+        return [("conv_act", "incep_conv1")] + [("b35", i) for i in range(1, n_blocks + 1)]
     return [("conv_act", "res_conv1")] + [("res", i) for i in range(1, n_blocks + 1)]
 
 
@@ -44,14 +46,21 @@ def forward_train(P, x, arch, n_blocks, dropout_gen=None, dropout=True):
     """P: dict name -> tensor (arg params require grad).  Returns probs, value, new moving stats."""
     new_stats = {}
 
-    def conv_act(x, name, k):
+    def conv_act(x, name, k, act=True):
         y = F.conv2d(x, P[name + "_weight"], P[name + "_bias"], padding=k // 2)
         y = _bn_train(y, P, name + "_gamma", name + "_beta", name + "_mean", name + "_var", True, new_stats)
-        return F.relu(y)
+        return F.relu(y) if act else y
 
     for kind, key in trunk_plan(arch, n_blocks):
         if kind == "conv_act":
             x = conv_act(x, key, 3)
+        elif kind == "b35":  # block35 of the Inception-ResNet variant (params.py)
+            pre = "b35_%d_" % key
+            t0 = conv_act(x, pre + "t0", 1)
+            t1 = conv_act(conv_act(x, pre + "t1a", 1), pre + "t1b", 3)
+            t2 = conv_act(conv_act(conv_act(x, pre + "t2a", 1), pre + "t2b", 3), pre + "t2c", 3)
+            up = conv_act(torch.cat([t0, t1, t2], dim=1), pre + "up", 1, act=False)
+            x = F.relu(x + 0.17 * up)
         else:
             idn = x
             y = F.conv2d(x, P["convA%d_weight" % key], P["convA%d_bias" % key], padding=1)

@@ -131,6 +131,10 @@ typedef struct {
 } ap_tensor;
 #define AP_ARCH_SIMPLE 0 /* policy_value_net_mxnet_simple.py:68-92 */
 #define AP_ARCH_RESNET 1 /* policy_value_net_mxnet.py:70-102       */
+/* builder-defined board-sized Inception-ResNet variant (BASELINE configs[3]): 3x3 stem + n_blocks x block35
+ * (inception-resnet-v2.py:41-58) + the reference heads; the reference file itself is an unwired ImageNet symbol.
+ * Parameter names: incep_conv1_*, b35_<i>_{t0,t1a,t1b,t2a,t2b,t2c,up}_* (alphapig_b200/params.py). n_filter = 128. */
+#define AP_ARCH_INCEPTION 2
 /* OR into `arch` (residual net only): every activation and weight is carried as a hi + lo fp16 pair and the
  * tensor cores compute hi*hi + lo*hi + hi*lo (near-fp32 accuracy at 3x the MMA work).  The 10-block net of
  * train_mxnet.py:79-91 needs it to stay within 1e-3 of fp32; plain fp16 operands reach 1.8e-3 there. */

@@ -47,7 +47,19 @@ def trunk_spec(arch, n_blocks=10, n_filter=128):
             spec.append(("res_block", i, cin, n_filter))
             cin = n_filter
         return spec, cin
+    if arch == "inception":  # builder-defined variant, see INCEPTION note below
+        spec = [("conv_act", "incep_conv1", 9, n_filter)]
+        for i in range(1, n_blocks + 1):
+            spec.append(("block35", i, n_filter, n_filter))
+        return spec, n_filter
     raise ValueError(arch)
+
+
+# INCEPTION: the reference's inception-resnet-v2.py is an unwired ImageNet symbol; the board-sized variant
+# restated here is DEFINED BY THIS REPO (alphapig_b200/params.py): 3x3 stem + n_blocks x block35
+# (inception-resnet-v2.py:41-58) with ConvFactory = conv + bias, BatchNorm(fix_gamma=True), ReLU, scale 0.17.
+BLOCK35 = (("t0", None, 32, 1), ("t1a", None, 32, 1), ("t1b", 32, 32, 3), ("t2a", None, 32, 1), ("t2b", 32, 48, 3),
+           ("t2c", 48, 64, 3), ("up", 128, None, 1))
 
 
 def param_shapes(arch, width, height, n_blocks=10, n_filter=128):
@@ -67,6 +79,9 @@ def param_shapes(arch, width, height, n_blocks=10, n_filter=128):
     for item in spec:
         if item[0] == "conv_act":
             conv_act(item[1], item[2], item[3], 3)
+        elif item[0] == "block35":
+            for name, cin, cout, k in BLOCK35:
+                conv_act("b35_%d_%s" % (item[1], name), cin or n_filter, cout or n_filter, k)
         else:
             _, i, cin, cout = item
             for tag, ci in (("A", cin), ("B", cout)):
@@ -132,15 +147,22 @@ def forward(arg, aux, states, arch, n_blocks=10, n_filter=128, dtype=torch.float
     P = {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in list(arg.items()) + list(aux.items())}
     x = torch.as_tensor(np.ascontiguousarray(states)).to(dtype)
 
-    def conv_act(x, name, k):
+    def conv_act(x, name, k, act=True):
         y = F.conv2d(x, P[name + "_weight"], P[name + "_bias"], padding=k // 2)
         y = _bn(y, P[name + "_gamma"], P[name + "_beta"], P[name + "_mean"], P[name + "_var"], True)
-        return F.relu(y)
+        return F.relu(y) if act else y
 
     spec, _ = trunk_spec(arch, n_blocks, n_filter)
     for item in spec:
         if item[0] == "conv_act":
             x = conv_act(x, item[1], 3)
+        elif item[0] == "block35":
+            pre = "b35_%d_" % item[1]
+            t0 = conv_act(x, pre + "t0", 1)
+            t1 = conv_act(conv_act(x, pre + "t1a", 1), pre + "t1b", 3)
+            t2 = conv_act(conv_act(conv_act(x, pre + "t2a", 1), pre + "t2b", 3), pre + "t2c", 3)
+            up = conv_act(torch.cat([t0, t1, t2], dim=1), pre + "up", 1, act=False)
+            x = F.relu(x + 0.17 * up)
         else:
             i = item[1]
             idn = x
@@ -197,6 +219,8 @@ def flop_per_leaf(arch, width, height, n_blocks=10, n_filter=128):
     for item in spec:
         if item[0] == "conv_act":
             mac += 9 * item[2] * item[3] * S
+        elif item[0] == "block35":
+            mac += sum(k * k * (cin or n_filter) * (cout or n_filter) for _, cin, cout, k in BLOCK35) * S
         else:
             mac += 9 * item[2] * item[3] * S + 9 * item[3] * item[3] * S
     mac += cfin * 6 * S + 4 * S * S + 2 * S

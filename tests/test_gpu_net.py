@@ -196,3 +196,45 @@ def test_search_run_compacts_terminal_leaves():
     assert np.array_equal(qa, qb) and np.array_equal(ra, rb)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("W,nblk,nst", [(15, 2, 70), (15, 10, 40), (8, 3, 131)])
+def test_inception_variant_vs_oracle(W, nblk, nst):
+    """Builder-defined Inception-ResNet variant (configs[3]; no reference semantics): the device graph -
+    tower stems merged into one 1x1 layer, slice-reading towers as zero-block 3x3 layers writing channel slices in
+    place, 1x1 up-projection with the 0.17 residual scale folded in - against the repo's own fp32 restatement."""
+    arg, aux = onet.init_params("inception", W, W, seed=4, n_blocks=nblk)
+    boards, st = _states(W, nst, 4321, 31 if W == 15 else 10)
+    ref_p, ref_v = onet.forward(arg, aux, st, "inception", n_blocks=nblk)
+    eng = _engine(width=W, height=W, n_in_row=5, n_games=4)
+    eng.net_load("inception", _merged(arg, aux), n_blocks=nblk)
+    p, v = eng.net_forward(st)
+    dlp = np.abs(np.log(p) - np.log(ref_p)).max()
+    dv = np.abs(v - ref_v).max()
+    print("inception-%d W %d: max|dlogp| %.3e max|dv| %.3e" % (nblk, W, dlp, dv))
+    assert np.allclose(p.sum(1), 1.0, atol=1e-5)
+    assert dlp <= TOL and dv <= TOL
+    # the search runs on it (uncompacted batch: no fused-head instantiation for the 1x1 up-projection)
+    cm = [export_oboard(b) for b in boards[:4]]
+    eng.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+    eng.search_run(20)
+    _, _, visits, _, rootn = eng.search_root()
+    assert (rootn == 20).all() and (visits.sum(1) == 19).all()
+    eng.close()
+
+
+def test_inception_shim_train_step():
+    from alphapig_b200.policy_value_net_inception import PolicyValueNet
+    W = 8
+    net = PolicyValueNet(W, W, batch_size=8, n_blocks=2, seed=0)
+    rs = np.random.RandomState(0)
+    st = (rs.rand(8, 9, W, W) < 0.3).astype(np.float32)
+    pi = rs.dirichlet(np.ones(W * W), size=8)
+    z = rs.choice([-1.0, 1.0], size=8)
+    p0, _ = net.policy_value(st)
+    loss, ent = net.train_step(st, pi, z, 2e-3)
+    p1, _ = net.policy_value(st)
+    assert np.isfinite(loss).all() and not np.array_equal(p0, p1)
+    arg, aux = net.get_policy_param()
+    rp, rv = onet.forward(arg, aux, st, "inception", n_blocks=2)
+    assert np.abs(np.log(p1) - np.log(rp)).max() <= TOL
