@@ -165,3 +165,38 @@ def test_sgf_push_matches_reference_golden(golden_dir):
     assert np.array_equal(st, want)
     assert np.array_equal(pi, z["sgf_pi"].astype(np.float32)) and np.array_equal(zz, z["sgf_z"].astype(np.float32))
     eng.close()
+
+
+def test_replay_error_paths():
+    """The reference raises on misuse (random.sample larger than the deque: ValueError; deque index: IndexError);
+    the ABI reports AP_ERR_BAD_ARG with a message instead of touching memory."""
+    from alphapig_b200._lib import EngineError
+    from alphapig_b200.replay import ReplayBuffer
+    eng = _engine(width=6, height=6, n_in_row=4, n_games=1)
+    with pytest.raises(EngineError):
+        eng.replay_size()                       # no ring yet
+    with pytest.raises(EngineError):
+        eng.replay_create(0)
+    ring = ReplayBuffer(eng, 40)
+    assert len(ring) == 0
+    with pytest.raises(ValueError):
+        ring.sample_indices(1)                  # random.sample on an empty population
+    ring.extend(_game_data(6, 1, 3))
+    assert len(ring) == 24
+    with pytest.raises(EngineError):
+        eng.replay_gather([24])                 # one past the end
+    with pytest.raises(EngineError):
+        eng.replay_gather([-1])
+    with pytest.raises(IndexError):
+        ring[24]
+    assert ring[-1][2] == ring[23][2]
+    ring.extend([])                             # no-op
+    assert len(ring) == 24
+    ring.extend(_game_data(6, 2, 4))            # 24 + 32 > 40: oldest 16 samples evicted
+    assert len(ring) == 40 and eng.replay_size() == (40, 56)
+    # a non-square board cannot be augmented by rot90 (train_mxnet.py:122-126 would mis-shape): rejected at create
+    e2 = _engine(width=7, height=5, n_in_row=4, n_games=1)
+    with pytest.raises(EngineError):
+        e2.replay_create(16)
+    e2.close()
+    eng.close()
