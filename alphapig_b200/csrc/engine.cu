@@ -508,6 +508,7 @@ int ap_search_stats(ap_engine* e, uint64_t* out5) {
 
 int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_mode, int32_t* out_move) {
   if (!e) return AP_ERR_BAD_HANDLE;
+  if (rollout_mode < 0 || rollout_mode > 2) return ap_fail(e, AP_ERR_BAD_ARG, "rollout_mode must be 0, 1 or 2");
   AP_TRY(ap_stage(e, 4 * (size_t)e->geo.G, 0));
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   launch_pure_run(e, n_playout, seed, rollout_mode, (int32_t*)e->d_stage);
@@ -519,7 +520,12 @@ int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_
 }
 
 int ap_rollout_eval(ap_engine* e, uint64_t seed, int8_t* out_value, int16_t* out_plies) {
+  return ap_rollout_eval2(e, seed, 0, out_value, out_plies);
+}
+
+int ap_rollout_eval2(ap_engine* e, uint64_t seed, int32_t impl, int8_t* out_value, int16_t* out_plies) {
   if (!e) return AP_ERR_BAD_HANDLE;
+  if (impl != 0 && impl != 2) return ap_fail(e, AP_ERR_BAD_ARG, "rollout impl must be 0 (permutation) or 2 (ply by ply)");
   const size_t G = e->geo.G;
   AP_TRY(ap_stage(e, 4 * G, 0));
   int8_t* d_v = (int8_t*)e->d_stage;
@@ -527,7 +533,7 @@ int ap_rollout_eval(ap_engine* e, uint64_t seed, int8_t* out_value, int16_t* out
   AP_TRY(ap_stage(e, ((G + 15) & ~15ull) + 2 * G, 0));
   d_v = (int8_t*)e->d_stage;
   d_p = (int16_t*)((char*)e->d_stage + ((G + 15) & ~15ull));
-  launch_rollout_eval(e, seed, d_v, d_p);
+  launch_rollout_eval(e, seed, impl, d_v, d_p);
   AP_LAUNCH_CHECK(e);
   AP_CUDA(e, cudaMemcpyAsync(out_value, d_v, G, cudaMemcpyDeviceToHost, e->stream));
   return d2h_sync(e, out_plies, d_p, 2 * G);

@@ -227,10 +227,11 @@ class Engine(object):
         self._check(self.lib.ap_pure_run(self.h, int(n_playout), int(seed), int(rollout_mode), _ptr(mv)))
         return mv
 
-    def rollout_eval(self, seed=0):
+    def rollout_eval(self, seed=0, impl=0):
+        """impl 0 = permutation rollout (default), 2 = ply-by-ply rollout (cross-check)."""
         v = np.zeros(self.G, np.int8)
         p = np.zeros(self.G, np.int16)
-        self._check(self.lib.ap_rollout_eval(self.h, int(seed), _ptr(v), _ptr(p)))
+        self._check(self.lib.ap_rollout_eval2(self.h, int(seed), int(impl), _ptr(v), _ptr(p)))
         return v.astype(np.int32), p.astype(np.int32)
 
     def rollout_hash(self):

@@ -428,7 +428,7 @@ def run_gpu_pure(args):
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        eng.pure_run(PURE_PLAYOUT, seed=i)
+        eng.pure_run(PURE_PLAYOUT, seed=i, rollout_mode=args.rollout_mode)
     eng.search_stats()
     clocks = ClockSampler(local)
     sync_all()
@@ -436,7 +436,7 @@ def run_gpu_pure(args):
     l0 = eng.launch_count()
     dev_ms = 0.0
     for i in range(args.steps):
-        eng.pure_run(PURE_PLAYOUT, seed=100 + i)
+        eng.pure_run(PURE_PLAYOUT, seed=100 + i, rollout_mode=args.rollout_mode)
         dev_ms += eng.search_timing()[0]
     sync_all()
     launches = eng.launch_count() - l0
@@ -446,7 +446,7 @@ def run_gpu_pure(args):
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         eng.boards_import(pin_cells, pin_meta)
-        mv = eng.pure_run(PURE_PLAYOUT, seed=200 + i)
+        mv = eng.pure_run(PURE_PLAYOUT, seed=200 + i, rollout_mode=args.rollout_mode)
         if i >= args.warmup:
             e2e_s += time.perf_counter() - t0
     sync_all()
@@ -475,6 +475,9 @@ def run_gpu_pure(args):
                           "timing": "CUDA events on the engine stream around the fused k_pure_run launch"},
                "moves_per_s": value / PURE_PLAYOUT,
                "rollout_plies_per_s": stats["rollout_plies"] / (dev_ms / 1000.0),
+               "rollout": ("permutation (one sorted random-key permutation of the empty cells + 8-step bit descent to "
+                           "the first line; plies = length of the random game it decides)" if args.rollout_mode == 0
+                           else "ply by ply"),
                "clocks": clk,
                "e2e": {"value": total / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": int(pin_cells.nbytes + pin_meta.nbytes),
                        "d2h_bytes_per_step": int(mv.nbytes), "timing": "wall clock around boards_import + pure_run"},
@@ -483,7 +486,7 @@ def run_gpu_pure(args):
                             "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src,
                             "traffic": None, "avg_launch_ms": dev_ms / args.steps,
                             "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
-                            "note": "latency/issue bound: ~100 register-resident random plies per playout dominate"}}
+                            "note": "latency/issue bound (register-resident rollouts + dependent node loads), not bandwidth bound"}}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_pure_baseline()
         print(json.dumps(out))
@@ -547,6 +550,8 @@ def main():
     ap.add_argument("--games", type=int, default=G_PER_GPU, help="concurrent games per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--groups", type=int, default=2, help="selfplay workload: pipelined game groups (1 = none)")
+    ap.add_argument("--rollout-mode", type=int, default=0, choices=[0, 2],
+                    help="pure workload: 0 = permutation rollouts (default), 2 = ply-by-ply rollouts (A/B)")
     ap.add_argument("--workload", default="az", choices=["az", "pure", "selfplay"],
                     help="az = BASELINE configs[1] (default, the headline metric); pure = configs[2] (mcts_pure, 1000 playouts)")
     args = ap.parse_args()

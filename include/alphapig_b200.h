@@ -115,11 +115,17 @@ int ap_search_stats(ap_engine* e, uint64_t* out5);
 /* ---- mcts_pure (mcts_pure.py:13-206) ---------------------------------------- */
 /* MCTS.get_move: n_playout x (_playout with uniform priors + random rollout) fully on
  * device, one CTA per game; out_move[g] = first max by visits (:159-169).
- * rollout_mode 0 = uniform random legal moves (rollout_policy_fn, :13-17),
- *              1 = deterministic position hash in {-1,0,1} (bookkeeping-parity tests). */
+ * rollout_mode 0 = uniform random legal moves (rollout_policy_fn, :13-17) drawn as one random permutation of
+ *                  the empty cells per rollout + a bit-descent to the first completed line (same distribution
+ *                  of result and length as playing ply by ply; see csrc/rollout.cu),
+ *              1 = deterministic position hash in {-1,0,1} (bookkeeping-parity tests),
+ *              2 = the same uniform random game played ply by ply (cross-check of mode 0; also used
+ *                  for 16-wide boards). */
 int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_mode, int32_t* out_move /* [G] */);
 /* _evaluate_rollout (:138-157) from every root board: winner-from-leaf-player value and plies played */
 int ap_rollout_eval(ap_engine* e, uint64_t seed, int8_t* out_value /* [G] */, int16_t* out_plies /* [G] */);
+/* same with the rollout implementation chosen: impl 0 = permutation (default), 2 = ply by ply */
+int ap_rollout_eval2(ap_engine* e, uint64_t seed, int32_t impl, int8_t* out_value /* [G] */, int16_t* out_plies /* [G] */);
 /* the deterministic hash used by rollout_mode 1, for the host-side oracle */
 int ap_rollout_hash(ap_engine* e, int8_t* out_value /* [G] */);
 

@@ -249,3 +249,25 @@ def test_bench_synthetic_positions_shape():
         if k >= 4:
             assert all(cells[m] != 0 for m in meta[3:7])
             assert cells[meta[3]] == 2  # last stone was white's
+
+
+def test_permutation_rollout_restatement_equals_play():
+    """oracle/rollout.py: the bit-descent over a random permutation of the empty cells (what the device
+    rollout computes) gives the same (value, plies) as playing that permutation move by move
+    (mcts_pure.py:138-157), on empty, mid-game, nearly full and small boards."""
+    from helpers import oboard_from, synth_position
+    from oracle.rollout import rollout_by_descent, rollout_by_play
+    rs = np.random.RandomState(11)
+    cases = [(15, 15, 5, []), (8, 8, 5, []), (6, 6, 4, []), (15, 15, 5, synth_position(15, 15, 5, 1240)),
+             (15, 15, 5, synth_position(15, 15, 5, 1251)), (8, 8, 5, synth_position(8, 8, 5, 7, max_pairs=10)),
+             (5, 5, 5, []), (6, 5, 3, [0, 7])]
+    ties = 0
+    for W, H, n, moves in cases:
+        b = oboard_from(W, H, n, moves)
+        for _ in range(40):
+            order = rs.permutation(b.availables)
+            got = rollout_by_descent(b, order)
+            want = rollout_by_play(b, order)
+            assert got == want, (W, H, n, moves, list(order))
+            ties += want[0] == 0
+    assert ties > 0  # the 5x5x5 board mostly ties: the t >= E branch is exercised

@@ -207,6 +207,100 @@ def test_rollout_distribution():
     eng.close()
 
 
+def _two_sample_chi2_p(a, b, bins):
+    """p-value of the chi-square homogeneity test of two samples over the given bin edges"""
+    from scipy.stats import chi2_contingency
+    ha, _ = np.histogram(a, bins)
+    hb, _ = np.histogram(b, bins)
+    keep = (ha + hb) >= 20
+    tab = np.stack([np.append(ha[keep], ha[~keep].sum()), np.append(hb[keep], hb[~keep].sum())])
+    tab = tab[:, tab.sum(0) > 0]
+    return chi2_contingency(tab)[1]
+
+
+def test_rollout_permutation_equals_ply_by_ply_distribution():
+    """ap_rollout_eval2: the permutation rollout (impl 0: one random permutation of the empty cells +
+    bit-descent to the first line) and the ply-by-ply rollout (impl 2: mcts_pure.py:138-157 move by move)
+    are the same distribution of (value, plies): 65k samples each from the empty board and from
+    SURVEY 8(d) mid-game positions."""
+    W = H = 15
+    G = 16384
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, n_playout=1, node_capacity=4)
+    for positions in ("empty", "midgame"):
+        if positions == "midgame":
+            cells = np.zeros((G, W * H), np.int8)
+            meta = np.zeros((G, 8), np.int32)
+            uniq = [export_oboard(oboard_from(W, H, 5, synth_position(W, H, 5, 1234 + i))) for i in range(64)]
+            for g in range(G):
+                cells[g], meta[g] = uniq[g % 64]
+            eng.boards_import(cells, meta)
+        va, pa, vb, pb = [], [], [], []
+        for seed in range(4):
+            v, p = eng.rollout_eval(seed=seed, impl=0)
+            va.append(v), pa.append(p)
+            v, p = eng.rollout_eval(seed=1000 + seed, impl=2)
+            vb.append(v), pb.append(p)
+        va, pa, vb, pb = map(np.concatenate, (va, pa, vb, pb))
+        assert pa.min() >= 1 and pa.max() <= 225
+        assert _two_sample_chi2_p(pa, pb, np.arange(0, 232, 4)) > 1e-6, positions
+        assert _two_sample_chi2_p(va, vb, np.array([-1.5, -0.5, 0.5, 1.5])) > 1e-6, positions
+        # joint: plies of the won / lost rollouts separately (who completes the line depends on ply parity)
+        for val in (-1, 1):
+            assert _two_sample_chi2_p(pa[va == val], pb[vb == val], np.arange(0, 232, 4)) > 1e-6, (positions, val)
+        # parity law of the alternating game: the side to move at the leaf wins on odd ply counts only
+        won = va == 1
+        assert np.all(pa[won] % 2 == 1) and np.all(pa[va == -1] % 2 == 0)
+    eng.close()
+
+
+def test_rollout_permutation_exact_small_position():
+    """A position with 6 empty cells: the exact distribution of (value, plies) over all 720 move orders
+    (oracle/rollout.py on the oracle board) vs 16384 device permutation rollouts, and the edge cases
+    E = 1 and an already finished game."""
+    import itertools
+    from collections import Counter
+    from scipy.stats import chisquare
+    from oracle.rollout import rollout_by_play
+    W = H = 6
+    n = 4
+    rs = np.random.RandomState(3)
+    while True:  # random legal play down to 6 empty cells without finishing the game
+        b = oboard_from(W, H, n, [])
+        ok = True
+        for _ in range(W * H - 6):
+            b.do_move(int(b.availables[rs.randint(len(b.availables))]))
+            if b.game_end()[0]:
+                ok = False
+                break
+        if ok and {1, -1} <= {rollout_by_play(b, o)[0] for o in itertools.islice(itertools.permutations(b.availables), 200)}:
+            break
+    exact = Counter(rollout_by_play(b, o) for o in itertools.permutations(b.availables))
+    G = 16384
+    eng = _engine(width=W, height=H, n_in_row=n, n_games=G, n_playout=1, node_capacity=4)
+    c, m = export_oboard(b)
+    eng.boards_import(np.repeat(c[None], G, 0), np.repeat(m[None], G, 0))
+    v, p = eng.rollout_eval(seed=9, impl=0)
+    got = Counter(zip(v.tolist(), p.tolist()))
+    assert set(got) <= set(exact), (got, exact)
+    keys = sorted(exact)
+    f_exp = np.array([exact[k] for k in keys], float) / 720.0 * G
+    f_obs = np.array([got.get(k, 0) for k in keys], float)
+    big = f_exp >= 5
+    if (~big).any():
+        f_exp = np.append(f_exp[big], f_exp[~big].sum())
+        f_obs = np.append(f_obs[big], f_obs[~big].sum())
+    assert chisquare(f_obs, f_exp)[1] > 1e-6, (keys, f_obs, f_exp)
+    # E = 1: one forced ply; finished game: 0 plies and the reference's terminal value
+    while len(b.availables) > 1 and not b.game_end()[0]:
+        b.do_move(b.availables[0])
+    c, m = export_oboard(b)
+    eng.boards_import(np.repeat(c[None], G, 0), np.repeat(m[None], G, 0))
+    v, p = eng.rollout_eval(seed=1, impl=0)
+    want = rollout_by_play(b, list(b.availables))
+    assert set(zip(v.tolist(), p.tolist())) == {want}
+    eng.close()
+
+
 def test_pool_exhaustion_is_reported():
     from alphapig_b200._lib import EngineError
     eng = _engine(width=8, height=8, n_in_row=5, n_games=1, node_capacity=100)

@@ -18,7 +18,15 @@ ap.add_argument("--playouts", type=int, default=6)
 ap.add_argument("--arch", default="simple")
 ap.add_argument("--blocks", type=int, default=10)
 ap.add_argument("--precision", default="auto")
+ap.add_argument("--pure", type=int, default=-1, help="profile ap_pure_run with this rollout mode instead (0 / 2)")
 a = ap.parse_args()
+if a.pure >= 0:
+    eng = Engine(width=15, height=15, n_in_row=5, n_games=a.games, c_puct=5, n_playout=a.playouts,
+                 node_capacity=a.playouts * 225 + 2)
+    bench.synthetic_positions(eng, a.games)
+    eng.pure_run(a.playouts, seed=1, rollout_mode=a.pure)
+    print("pure total ms", eng.search_timing()[0], eng.search_stats())
+    sys.exit(0)
 arg, aux = init_params(a.arch, 15, 15, n_blocks=a.blocks, seed=0, synthetic_stats=True)
 merged = dict(arg)
 merged.update(aux)
