@@ -111,51 +111,49 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 
 // ascending bitonic sort of 256 keys, element i = lane*8 + r.  Mirror formulation: every block size k starts
 // with the flip step (partner i ^ (k-1)) and continues with half-cleaners (partner i ^ j, j = k/4 .. 1), so the
-// lower index always keeps the minimum and every in-lane exchange has a compile-time direction.
+// lower index always keeps the minimum and every in-lane exchange has a compile-time direction.  The block
+// sizes that cross lanes (k = 16 .. 256) run as a ROLLED loop: the kernel's hot loop has to stay inside the
+// 32 KB instruction cache shared by warps that sit at different points of it (first version, fully unrolled:
+// "no instruction" was the top stall reason under ncu).
+__device__ __forceinline__ void cmpx(uint32_t& a, uint32_t& b) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+__device__ __forceinline__ void sort_tail421(uint32_t (&v)[8]) {
+  cmpx(v[0], v[4]); cmpx(v[1], v[5]); cmpx(v[2], v[6]); cmpx(v[3], v[7]);
+  cmpx(v[0], v[2]); cmpx(v[1], v[3]); cmpx(v[4], v[6]); cmpx(v[5], v[7]);
+  cmpx(v[0], v[1]); cmpx(v[2], v[3]); cmpx(v[4], v[5]); cmpx(v[6], v[7]);
+}
 __device__ __forceinline__ void warp_sort256(uint32_t (&v)[8], int lane) {
-#pragma unroll
-  for (int k = 2; k <= 256; k <<= 1) {
-    if (k <= 8) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int r2 = r ^ (k - 1);
-        if (r < r2) {
-          const uint32_t a = min(v[r], v[r2]), b = max(v[r], v[r2]);
-          v[r] = a;
-          v[r2] = b;
-        }
-      }
-    } else {
-      const int m = (k >> 3) - 1;                       // partner lane = lane ^ m, partner register = 7 - r
-      const bool keep_min = (lane & (k >> 4)) == 0;     // this lane is the lower one of the pair
+  // k = 2, 4, 8: inside the lane
+  cmpx(v[0], v[1]); cmpx(v[2], v[3]); cmpx(v[4], v[5]); cmpx(v[6], v[7]);
+  cmpx(v[0], v[3]); cmpx(v[1], v[2]); cmpx(v[4], v[7]); cmpx(v[5], v[6]);
+  cmpx(v[0], v[1]); cmpx(v[2], v[3]); cmpx(v[4], v[5]); cmpx(v[6], v[7]);
+  cmpx(v[0], v[7]); cmpx(v[1], v[6]); cmpx(v[2], v[5]); cmpx(v[3], v[4]);
+  cmpx(v[0], v[2]); cmpx(v[1], v[3]); cmpx(v[4], v[6]); cmpx(v[5], v[7]);
+  cmpx(v[0], v[1]); cmpx(v[2], v[3]); cmpx(v[4], v[5]); cmpx(v[6], v[7]);
+#pragma unroll 1
+  for (int kk = 1; kk <= 16; kk <<= 1) {  // kk = k / 16
+    {
+      const int m = 2 * kk - 1;                  // flip: partner lane = lane ^ m, partner register = 7 - r
+      const bool keep_min = (lane & kk) == 0;    // this lane is the lower one of the pair
       uint32_t o[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) o[r] = __shfl_xor_sync(AP_FULL, v[7 - r], m);
 #pragma unroll
       for (int r = 0; r < 8; ++r) v[r] = keep_min ? min(v[r], o[r]) : max(v[r], o[r]);
     }
+#pragma unroll 1
+    for (int lj = kk >> 1; lj > 0; lj >>= 1) {   // half-cleaners across lanes: j = 8 * lj
+      const bool keep_min = (lane & lj) == 0;
 #pragma unroll
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      if (j >= 8) {
-        const int lj = j >> 3;
-        const bool keep_min = (lane & lj) == 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const uint32_t o = __shfl_xor_sync(AP_FULL, v[r], lj);
-          v[r] = keep_min ? min(v[r], o) : max(v[r], o);
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          if ((r & j) == 0) {
-            const int r2 = r | j;
-            const uint32_t a = min(v[r], v[r2]), b = max(v[r], v[r2]);
-            v[r] = a;
-            v[r2] = b;
-          }
-        }
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t o = __shfl_xor_sync(AP_FULL, v[r], lj);
+        v[r] = keep_min ? min(v[r], o) : max(v[r], o);
       }
     }
+    sort_tail421(v);                             // j = 4, 2, 1
   }
 }
 
@@ -163,6 +161,7 @@ __device__ __forceinline__ void warp_sort256(uint32_t (&v)[8], int lane) {
 // window that would cross from one half into the other contains a clear bit
 __device__ __forceinline__ bool wb_packed_wins(uint32_t x, int n) {
   uint32_t th = x, tv = x, td = x, ta = x;
+#pragma unroll 1
   for (int k = 1; k < n; ++k) {
     const uint32_t up = __shfl_down_sync(AP_FULL, x, k);
     th &= x >> k;
@@ -173,64 +172,65 @@ __device__ __forceinline__ bool wb_packed_wins(uint32_t x, int n) {
   return __any_sync(AP_FULL, (th | tv | td | ta) != 0u);
 }
 
-// bit `bit` of the four bytes of w -> 4-bit nibble (byte 0 -> bit 0)
-__device__ __forceinline__ uint32_t byte_bits(uint32_t w, int bit) {
-  return (((w >> bit) & 0x01010101u) * 0x10204080u) >> 28;
+// s_rank holds the rank of column c of board row h at byte h*16 + rank_slot(c); with that order bit `bit` of the
+// 16 ranks of a row gathers into a 16-bit column mask with a handful of shifts
+__device__ __forceinline__ uint32_t rank_slot(uint32_t c) { return ((c & 3u) << 2) | (c >> 2); }
+__device__ __forceinline__ uint32_t rank_plane(const uint4& rr, int bit) {
+  const uint32_t M = 0x01010101u;
+  const uint32_t a = (rr.x >> bit) & M, b = (rr.y >> bit) & M, c = (rr.z >> bit) & M, d = (rr.w >> bit) & M;
+  const uint32_t s = (a + 2u * b) + 4u * (c + 2u * d);  // byte i: columns 4i .. 4i+3 in bits 0..3
+  const uint32_t t = s | (s >> 4);
+  return __byte_perm(t, 0u, 0x4420);
 }
 
-// MCTS._evaluate_rollout (mcts_pure.py:138-157) by permutation; s_rank: 256 bytes of shared memory of this warp
+// MCTS._evaluate_rollout (mcts_pure.py:138-157) by permutation from a NON-terminal position (the caller has
+// done the game_end() of :143); s_rank: 256 bytes of shared memory of this warp
 __device__ __forceinline__ int rollout_eval_perm(const WBoard& b, Pcg& rng, const Geo& geo, int lane, int& plies,
                                                  uint8_t* s_rank) {
   const int player = b.cur;
-  plies = 0;
-  {
-    int winner;
-    if (wb_game_end(b, geo.n_in_row, geo.S, winner)) return (winner == -1) ? 0 : ((winner == player) ? 1 : -1);
-  }
   const uint32_t e = wb_empty_row(b, geo.W, geo.H, lane);  // lanes >= H: 0
   const int E = geo.S - b.nst;
-  const uint32_t k0 = pcg_next(rng), k1 = pcg_next(rng);
+  const uint32_t k0 = pcg_next(rng);
   // slot (lane, r) starts as cell16 = lane*8 + r = row (lane >> 1), column (lane & 1) * 8 + r
   const uint32_t er = __shfl_sync(AP_FULL, e, lane >> 1) >> ((lane & 1) * 8);
   uint32_t v[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const uint32_t cell = (uint32_t)(lane * 8 + r);
-    const uint32_t h = min((mix32(k0 ^ (cell * 0x9E3779B9u)) + k1) >> 8, 0xFFFFFEu);
+    uint32_t h = (k0 + cell * 0x9E3779B9u) * 0x7feb352du;
+    h ^= h >> 15;
+    h *= 0x846ca68bu;
+    h ^= h >> 16;
+    h = min(h >> 8, 0xFFFFFEu);
     v[r] = ((er >> r) & 1u) ? ((h << 8) | cell) : 0xFFFFFFFFu;
   }
   warp_sort256(v, lane);
   __syncwarp();
 #pragma unroll
   for (int r = 0; r < 8; ++r)
-    if (v[r] != 0xFFFFFFFFu) s_rank[v[r] & 0xFFu] = (uint8_t)(lane * 8 + r);
+    if (v[r] != 0xFFFFFFFFu) s_rank[(v[r] & 0xF0u) | rank_slot(v[r] & 0xFu)] = (uint8_t)(lane * 8 + r);
   __syncwarp();
-  uint32_t pl[8];
-  {
-    uint4 rr = make_uint4(0u, 0u, 0u, 0u);
-    if (lane < AP_ROWS) rr = *reinterpret_cast<const uint4*>(s_rank + lane * 16);
-#pragma unroll
-    for (int bit = 0; bit < 8; ++bit)
-      pl[bit] = byte_bits(rr.x, bit) | (byte_bits(rr.y, bit) << 4) | (byte_bits(rr.z, bit) << 8) |
-                (byte_bits(rr.w, bit) << 12);
-  }
+  uint4 rr = make_uint4(0u, 0u, 0u, 0u);
+  if (lane < AP_ROWS) rr = *reinterpret_cast<const uint4*>(s_rank + lane * 16);
+  const uint32_t odd = rank_plane(rr, 0);  // odd ranks: the opponent of the side to move at the leaf
+  const uint32_t mine_sh = (player == 1) ? 0u : 16u, other_sh = 16u - mine_sh;
   // largest t such that the first t plies complete no line
   uint32_t eq = e, lt = 0u;
   int t = 0;
   const int need = geo.n_in_row + 2 - b.nst;  // has_a_winner looks only at boards with >= n+2 stones (game.py:134)
-#pragma unroll
+#pragma unroll 1
   for (int bit = 7; bit >= 0; --bit) {
-    const uint32_t placed = lt | (eq & ~pl[bit]);          // cells with rank < t | 1 << bit
-    const uint32_t first = placed & ~pl[0], second = placed & pl[0];  // even ranks: the side to move at the leaf
-    const uint32_t x = b.row | ((player == 1) ? (first | (second << 16)) : (second | (first << 16)));
+    const uint32_t plb = rank_plane(rr, bit);
+    const uint32_t placed = lt | (eq & ~plb);  // cells with rank < t | 1 << bit
+    const uint32_t x = b.row | ((placed & ~odd) << mine_sh) | ((placed & odd) << other_sh);
     const int tt = t | (1 << bit);
     const bool line = (min(tt, E) >= need) && wb_packed_wins(x, geo.n_in_row);
     if (!line) {
       t = tt;
       lt = placed;
-      eq &= pl[bit];
+      eq &= plb;
     } else {
-      eq &= ~pl[bit];
+      eq &= ~plb;
     }
   }
   if (t >= E) {
@@ -241,6 +241,17 @@ __device__ __forceinline__ int rollout_eval_perm(const WBoard& b, Pcg& rng, cons
   return (t & 1) ? -1 : 1;  // ply t (0-based) completes the line; even plies belong to `player`
 }
 
+// Board.game_end (game.py:160-167) with one packed line check for both colours (W <= 15); the colour is only
+// resolved when a line exists
+__device__ __forceinline__ bool wb_game_end_packed(const WBoard& b, int n, int S, int& winner) {
+  const bool line = (b.nst >= n + 2) && wb_packed_wins(b.row, n);
+  winner = -1;
+  if (line) winner = wb_colour_wins(b.row & 0xffffu, n) ? 1 : 2;
+  return line || b.nst >= S;
+}
+
+__device__ __noinline__ double ddiv_slow(double x, int d) { return __ddiv_rn(x, (double)d); }
+
 __device__ __forceinline__ int hash_eval(const WBoard& b, const Geo& geo) {
   int winner;
   bool end = wb_game_end(b, geo.n_in_row, geo.S, winner);
@@ -249,52 +260,157 @@ __device__ __forceinline__ int hash_eval(const WBoard& b, const Geo& geo) {
   return (winner == b.cur) ? 1 : -1;
 }
 
+// TreeNode.select (mcts_pure.py:43-49,78-80) for mcts_pure trees.  Every child of a node carries the same prior
+// 1/A (policy_value_fn, mcts_pure.py:20-25; A = child count), so x = (c_puct*P)*sqrt(Np) is shared and
+// u = x/(1+N) depends on the visit count alone: lane L computes the correctly rounded quotient for N = L once
+// and the children fetch theirs by shuffle (own division only for N >= 32) - the same fp64 operations on the
+// same operands as tree_select_child, ~6 instead of ~35 instructions per child and no load of P.
+__device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, int cs, int cc, int np, double c_puct,
+                                                 int lane, int& best_move) {
+  constexpr int PER = AP_MAX_S / 32;
+  double q[PER];
+  int n[PER], m[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lane + 32 * j;
+    const size_t c = base + cs + i;
+    q[j] = 0.0, n[j] = 0, m[j] = -1;
+    if (i < cc) {
+      q[j] = pl.Q[c];
+      n[j] = pl.N[c];
+      m[j] = pl.move[c];
+    }
+  }
+  const double prior = __ddiv_rn(1.0, (double)cc);  // np.ones(A)/A
+  const double x = __dmul_rn(__dmul_rn(c_puct, prior), __dsqrt_rn((double)np));
+  const double ut = __ddiv_rn(x, (double)(1 + lane));
+  double bv = -CUDART_INF;
+  int bi = INT_MAX, bm = -1;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    if (32 * j < cc) {  // warp-uniform
+      const int i = lane + 32 * j;
+      double u = __shfl_sync(AP_FULL, ut, n[j] & 31);
+      if (n[j] >= 32) u = ddiv_slow(x, 1 + n[j]);
+      const double v = __dadd_rn(q[j], u);
+      if (i < cc && (v > bv || bi == INT_MAX)) {  // first element always taken, later only if strictly greater
+        bv = v;
+        bi = i;
+        bm = m[j];
+      }
+    }
+  }
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    double ov = __shfl_xor_sync(AP_FULL, bv, d);
+    int oi = __shfl_xor_sync(AP_FULL, bi, d);
+    int om = __shfl_xor_sync(AP_FULL, bm, d);
+    // python max(): keep the earliest index unless a later one is strictly greater
+    bool take = (oi != INT_MAX) && (bi == INT_MAX || (oi < bi ? !(bv > ov) : (ov > bv)));
+    if (take) {
+      bv = ov;
+      bi = oi;
+      bm = om;
+    }
+  }
+  best_move = bm;
+  return bi;
+}
+
 // MCTS.get_move (mcts_pure.py:159-169): tree reset, n_playout x _playout (:114-136), arg-max visits.
-__global__ void __launch_bounds__(32)
+// P of the children is not stored (implicit 1/child_count, see pure_select_child); the path of a playout is kept
+// in shared memory so that update_recursive (:61-67) touches all its nodes in one memory round trip, one lane each.
+template <int MODE>  // 0 = permutation rollouts (W <= 15), 1 = position hash, 2 = ply-by-ply rollouts
+__global__ void __launch_bounds__(32, 24)
 k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, int n_playout,
-           unsigned long long seed, int mode, int32_t* out_move, int32_t* errflag, unsigned long long* stats) {
+           unsigned long long seed, int32_t* out_move, int32_t* errflag, unsigned long long* stats) {
   __shared__ int16_t s_list[AP_MAX_S];
   __shared__ __align__(16) uint8_t s_rank[256];
+  __shared__ int s_path[AP_MAX_S + 1];
   const int lane = threadIdx.x;
   const int g = blockIdx.x;
-  const bool perm = (mode == 0) && geo.W <= 15;  // mode 2 (and 16-wide boards): ply-by-ply rollout
   const size_t base = (size_t)g * geo.cap;
   const WBoard root = wb_load(rows, meta, g, lane);
+  const uint32_t inv_w = 65536u / (uint32_t)geo.W + 1u;  // (mv * inv_w) >> 16 == mv / W for mv < 256, W <= 16
   Pcg rng = pcg_seed(seed, (unsigned long long)g);
   if (lane == 0) tree_write_root(pl, base, g);
   __syncwarp();
   unsigned long long scanned = 0, written = 0, pathn = 0, plies_total = 0;
+#pragma unroll 1
   for (int it = 0; it < n_playout; ++it) {
     WBoard b = root;
-    int node = 0;
+    int node = 0, depth = 0;
+#pragma unroll 1
     while (true) {
-      int cs = pl.child_start[base + node];
+      const int cs = pl.child_start[base + node];
+      const int cc = pl.child_count[base + node];
+      const int np = pl.N[base + node];
+      if (lane == 0) s_path[depth] = node;
       if (cs < 0) break;
-      int cc = pl.child_count[base + node];
-      int np = pl.N[base + node];
-      int bi = tree_select_child(pl, base, cs, cc, np, geo.c_puct, lane);
-      int mv = pl.move[base + cs + bi];
-      wb_do_move(b, mv, geo.W, lane);
+      int mv;
+      const int bi = pure_select_child(pl, base, cs, cc, np, geo.c_puct, lane, mv);
+      const int h = (int)(((uint32_t)mv * inv_w) >> 16), w = mv - h * geo.W;
+      if (lane == h) b.row |= (1u << w) << ((b.cur == 2) ? 16 : 0);
+      b.hist = (b.hist << 16) | (unsigned long long)(uint16_t)mv;
+      b.nst += 1;
+      b.last = mv;
+      b.cur = 3 - b.cur;
       node = cs + bi;
+      ++depth;
       scanned += cc;
     }
     int winner;
-    bool end = wb_game_end(b, geo.n_in_row, geo.S, winner);
+    const bool end = (MODE == 0) ? wb_game_end_packed(b, geo.n_in_row, geo.S, winner)
+                                 : wb_game_end(b, geo.n_in_row, geo.S, winner);
     if (!end) {
-      int A = wb_legal_list(b, geo.W, geo.H, lane, s_list);
-      double p = __ddiv_rn(1.0, (double)A);  // np.ones(A)/A  (mcts_pure.py:24)
-      bool ok = tree_expand(pl, base, g, geo.cap, node, A, s_list, [&](int, int) { return p; }, lane);
-      if (!ok) {
+      const int A = wb_legal_list(b, geo.W, geo.H, lane, s_list);
+      const int a0 = pl.alloc[g];
+      if (a0 + A > geo.cap) {
         if (lane == 0) errflag[g] = AP_ERR_POOL_EXHAUSTED;
         break;
+      }
+#pragma unroll 1
+      for (int k = lane; k < A; k += 32) {  // TreeNode.expand (mcts_pure.py:34-41), children in list order
+        const size_t c = base + a0 + k;
+        pl.Q[c] = 0.0;
+        pl.N[c] = 0;
+        pl.child_start[c] = -1;
+        pl.child_count[c] = 0;
+        pl.parent[c] = node;
+        pl.move[c] = s_list[k];
+      }
+      if (lane == 0) {
+        pl.child_start[base + node] = a0;
+        pl.child_count[base + node] = (uint16_t)A;
+        pl.alloc[g] = a0 + A;
       }
       written += A;
     }
     int plies = 0;
-    int v = (mode == 1) ? hash_eval(b, geo)
-                        : (perm ? rollout_eval_perm(b, rng, geo, lane, plies, s_rank) : rollout_eval(b, rng, geo, lane, plies));
+    int v;
+    if constexpr (MODE == 1) {
+      v = hash_eval(b, geo);
+    } else if constexpr (MODE == 2) {
+      v = rollout_eval(b, rng, geo, lane, plies);
+    } else {
+      v = end ? ((winner == -1) ? 0 : ((winner == b.cur) ? 1 : -1)) : rollout_eval_perm(b, rng, geo, lane, plies, s_rank);
+    }
     plies_total += plies;
-    if (lane == 0) pathn += tree_backup(pl, base, node, -(double)v);
+    // update_recursive(-leaf_value): the leaf takes -v, its parent +v, ... one lane per path node
+    __syncwarp();
+#pragma unroll 1
+    for (int d0 = 0; d0 <= depth; d0 += 32) {
+      const int d = d0 + lane;
+      if (d <= depth) {
+        const size_t c = base + s_path[d];
+        const double x = ((depth - d) & 1) ? (double)v : -(double)v;
+        const int n = pl.N[c] + 1;
+        const double q = pl.Q[c];
+        pl.N[c] = n;
+        pl.Q[c] = __dadd_rn(q, __ddiv_rn(__dmul_rn(1.0, __dsub_rn(x, q)), (double)n));
+      }
+    }
+    pathn += depth + 1;
     __syncwarp();
   }
   // first max by visit count over root children
@@ -335,8 +451,17 @@ __global__ void k_rollout_eval(Geo geo, const uint32_t* rows, const BoardMeta* m
   WBoard b = wb_load(rows, meta, g, lane);
   Pcg rng = pcg_seed(seed, (unsigned long long)g);
   int plies;
-  int v = (impl == 0 && geo.W <= 15) ? rollout_eval_perm(b, rng, geo, lane, plies, s_rank[threadIdx.x >> 5])
-                                     : rollout_eval(b, rng, geo, lane, plies);
+  int v;
+  if (impl == 0 && geo.W <= 15) {
+    int winner;
+    plies = 0;
+    if (wb_game_end_packed(b, geo.n_in_row, geo.S, winner))
+      v = (winner == -1) ? 0 : ((winner == b.cur) ? 1 : -1);
+    else
+      v = rollout_eval_perm(b, rng, geo, lane, plies, s_rank[threadIdx.x >> 5]);
+  } else {
+    v = rollout_eval(b, rng, geo, lane, plies);
+  }
   if (lane == 0) {
     out_value[g] = (int8_t)v;
     out_plies[g] = (int16_t)plies;
@@ -353,8 +478,9 @@ __global__ void k_rollout_hash(Geo geo, const uint32_t* rows, const BoardMeta* m
 }
 
 void launch_pure_run(ap_engine* e, int n_playout, uint64_t seed, int mode, int32_t* d_move) {
-  k_pure_run<<<e->geo.G, 32, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, n_playout, seed, mode, d_move,
-                                            e->errflag, e->stats);
+  if (mode == 0 && e->geo.W > 15) mode = 2;  // the packed two-colour line check needs a spare column bit
+  auto k = (mode == 0) ? k_pure_run<0> : (mode == 1) ? k_pure_run<1> : k_pure_run<2>;
+  k<<<e->geo.G, 32, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, n_playout, seed, d_move, e->errflag, e->stats);
 }
 void launch_rollout_eval(ap_engine* e, uint64_t seed, int impl, int8_t* d_value, int16_t* d_plies) {
   k_rollout_eval<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->rows, e->meta, seed, impl, d_value, d_plies);

@@ -23,12 +23,13 @@ k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict
   int node = 0, depth = 0;
   unsigned long long scanned = 0;
   while (true) {
-    int cs = pl.child_start[base + node];
+    // the three node fields travel together (one round trip), not cs first and the rest after the leaf test
+    const int cs = pl.child_start[base + node];
+    const int cc = pl.child_count[base + node];
+    const int np = pl.N[base + node];
     if (cs < 0) break;
-    int cc = pl.child_count[base + node];
-    int np = pl.N[base + node];
-    int bi = tree_select_child(pl, base, cs, cc, np, geo.c_puct, lane);
-    int mv = pl.move[base + cs + bi];
+    int mv;
+    int bi = tree_select_child(pl, base, cs, cc, np, geo.c_puct, lane, mv);
     if (lane == 0) lv.path[(size_t)g * geo.S + depth] = (int16_t)mv;
     wb_do_move(b, mv, geo.W, lane);
     node = cs + bi;
