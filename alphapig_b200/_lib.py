@@ -63,6 +63,7 @@ SIGNATURES = {
     "ap_pure_run": (C.c_int, [_P, _I, C.c_uint64, _I, _P]),
     "ap_rollout_eval": (C.c_int, [_P, C.c_uint64, _P, _P]),
     "ap_rollout_eval2": (C.c_int, [_P, C.c_uint64, _I, _P, _P]),
+    "ap_rollout_eval_keys": (C.c_int, [_P, _P, _P, _P]),
     "ap_rollout_hash": (C.c_int, [_P, _P]),
     "ap_net_load": (C.c_int, [_P, _I, _I, _I, C.POINTER(ApTensor), _I]),
     "ap_net_forward": (C.c_int, [_P, _P, _I, _P, _P]),

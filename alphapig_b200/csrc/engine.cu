@@ -533,7 +533,23 @@ int ap_rollout_eval2(ap_engine* e, uint64_t seed, int32_t impl, int8_t* out_valu
   AP_TRY(ap_stage(e, ((G + 15) & ~15ull) + 2 * G, 0));
   d_v = (int8_t*)e->d_stage;
   d_p = (int16_t*)((char*)e->d_stage + ((G + 15) & ~15ull));
-  launch_rollout_eval(e, seed, impl, d_v, d_p);
+  launch_rollout_eval(e, seed, impl, nullptr, d_v, d_p);
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaMemcpyAsync(out_value, d_v, G, cudaMemcpyDeviceToHost, e->stream));
+  return d2h_sync(e, out_plies, d_p, 2 * G);
+}
+
+int ap_rollout_eval_keys(ap_engine* e, const uint32_t* keys, int8_t* out_value, int16_t* out_plies) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!keys || !out_value || !out_plies) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
+  if (e->geo.W > 15) return ap_fail(e, AP_ERR_BAD_ARG, "the permutation rollout needs width <= 15");
+  const size_t G = e->geo.G, kb = G * 256 * sizeof(uint32_t), vb = (G + 15) & ~15ull;
+  AP_TRY(ap_stage(e, kb + vb + 2 * G, 0));
+  uint32_t* d_k = (uint32_t*)e->d_stage;
+  int8_t* d_v = (int8_t*)e->d_stage + kb;
+  int16_t* d_p = (int16_t*)((char*)e->d_stage + kb + vb);
+  AP_TRY(h2d(e, d_k, keys, kb));
+  launch_rollout_eval(e, 0, 0, d_k, d_v, d_p);
   AP_LAUNCH_CHECK(e);
   AP_CUDA(e, cudaMemcpyAsync(out_value, d_v, G, cudaMemcpyDeviceToHost, e->stream));
   return d2h_sync(e, out_plies, d_p, 2 * G);

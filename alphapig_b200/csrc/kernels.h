@@ -30,5 +30,5 @@ size_t scratch_bytes_per_slot(int cap);
 
 // rollout.cu
 void launch_pure_run(ap_engine* e, int n_playout, uint64_t seed, int mode, int32_t* d_move);
-void launch_rollout_eval(ap_engine* e, uint64_t seed, int impl, int8_t* d_value, int16_t* d_plies);
+void launch_rollout_eval(ap_engine* e, uint64_t seed, int impl, const uint32_t* d_keys, int8_t* d_value, int16_t* d_plies);
 void launch_rollout_hash(ap_engine* e, int8_t* d_value);

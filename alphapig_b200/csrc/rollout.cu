@@ -23,6 +23,36 @@ __device__ __forceinline__ Pcg pcg_seed(unsigned long long seed, unsigned long l
   return r;
 }
 
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, every (key, counter) an independent stream - the random
+// bits of the permutation rollouts, addressed by (playout index, draw, game, lane) under the 64-bit seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll 1
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+// 8 x 24 random bits for the 8 board slots of this lane
+__device__ __forceinline__ void perm_draws(unsigned long long seed, uint32_t g, uint32_t lane, uint32_t playout,
+                                           uint32_t (&h)[8]) {
+  uint32_t a[4], b[4];
+  philox4x32_10(playout, 0u, g, lane, (uint32_t)seed, (uint32_t)(seed >> 32), a);
+  philox4x32_10(playout, 1u, g, lane, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = a[i] >> 8;
+    h[4 + i] = b[i] >> 8;
+  }
+}
+
 // FNV-1a over (cur, rows[0..16)); host twin: alphapig_b200.engine.rollout_hash_host
 __device__ __forceinline__ unsigned board_hash(const WBoard& b) {
   unsigned h = 2166136261u;
@@ -99,6 +129,12 @@ __device__ __forceinline__ int rollout_eval(WBoard b, Pcg& rng, const Geo& geo, 
 // Same distribution of (result, plies) as the ply-by-ply loop at ~1/10 of the instructions.
 // Keys are 24 random bits + the cell index (unique); two cells tie in the random part with probability
 // < 2e-3 per rollout and are then ordered by cell index - far below anything the parity statistics resolve.
+// The random bits are Philox4x32-10 outputs (one independent stream per game, lane and playout).  Cheaper
+// sources were tried and REJECTED by the 10^6-rollout comparison with the NumPy reference sample
+// (oracle/rollout.py): a two-multiply hash of (rollout, cell) put a 1 % excess into the spread of game lengths,
+// and PCG32 streams that differ only in their increment are correlated enough across the lanes of one rollout
+// to lengthen the mean game by 0.3 plies.  The algorithm itself is pinned exactly with injected draws
+// (ap_rollout_eval_keys vs the oracle playing the same order move by move).
 // Requires W <= 15 (bit 15 of each colour half stays clear and isolates the two halves in the packed check).
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
@@ -185,24 +221,19 @@ __device__ __forceinline__ uint32_t rank_plane(const uint4& rr, int bit) {
 
 // MCTS._evaluate_rollout (mcts_pure.py:138-157) by permutation from a NON-terminal position (the caller has
 // done the game_end() of :143); s_rank: 256 bytes of shared memory of this warp
-__device__ __forceinline__ int rollout_eval_perm(const WBoard& b, Pcg& rng, const Geo& geo, int lane, int& plies,
-                                                 uint8_t* s_rank) {
+// h: this lane's 8 random draws (24 bits each; slot r = cell16 lane*8 + r)
+__device__ __forceinline__ int rollout_eval_perm(const WBoard& b, const uint32_t (&h)[8], const Geo& geo, int lane,
+                                                 int& plies, uint8_t* s_rank) {
   const int player = b.cur;
   const uint32_t e = wb_empty_row(b, geo.W, geo.H, lane);  // lanes >= H: 0
   const int E = geo.S - b.nst;
-  const uint32_t k0 = pcg_next(rng);
   // slot (lane, r) starts as cell16 = lane*8 + r = row (lane >> 1), column (lane & 1) * 8 + r
   const uint32_t er = __shfl_sync(AP_FULL, e, lane >> 1) >> ((lane & 1) * 8);
   uint32_t v[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const uint32_t cell = (uint32_t)(lane * 8 + r);
-    uint32_t h = (k0 + cell * 0x9E3779B9u) * 0x7feb352du;
-    h ^= h >> 15;
-    h *= 0x846ca68bu;
-    h ^= h >> 16;
-    h = min(h >> 8, 0xFFFFFEu);
-    v[r] = ((er >> r) & 1u) ? ((h << 8) | cell) : 0xFFFFFFFFu;
+    v[r] = ((er >> r) & 1u) ? ((min(h[r], 0xFFFFFEu) << 8) | cell) : 0xFFFFFFFFu;
   }
   warp_sort256(v, lane);
   __syncwarp();
@@ -332,7 +363,7 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
   const size_t base = (size_t)g * geo.cap;
   const WBoard root = wb_load(rows, meta, g, lane);
   const uint32_t inv_w = 65536u / (uint32_t)geo.W + 1u;  // (mv * inv_w) >> 16 == mv / W for mv < 256, W <= 16
-  Pcg rng = pcg_seed(seed, (unsigned long long)g);
+  Pcg rng = pcg_seed(seed, (unsigned long long)g);  // MODE 2 only
   if (lane == 0) tree_write_root(pl, base, g);
   __syncwarp();
   unsigned long long scanned = 0, written = 0, pathn = 0, plies_total = 0;
@@ -393,7 +424,13 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
     } else if constexpr (MODE == 2) {
       v = rollout_eval(b, rng, geo, lane, plies);
     } else {
-      v = end ? ((winner == -1) ? 0 : ((winner == b.cur) ? 1 : -1)) : rollout_eval_perm(b, rng, geo, lane, plies, s_rank);
+      if (end) {
+        v = (winner == -1) ? 0 : ((winner == b.cur) ? 1 : -1);
+      } else {
+        uint32_t h[8];
+        perm_draws(seed, (uint32_t)g, (uint32_t)lane, (uint32_t)it, h);
+        v = rollout_eval_perm(b, h, geo, lane, plies, s_rank);
+      }
     }
     plies_total += plies;
     // update_recursive(-leaf_value): the leaf takes -v, its parent +v, ... one lane per path node
@@ -442,8 +479,9 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
   }
 }
 
+// keys != nullptr: the 24-bit draw of every board slot comes from the caller ([G][256], slot = row*16 + column)
 __global__ void k_rollout_eval(Geo geo, const uint32_t* rows, const BoardMeta* meta, unsigned long long seed, int impl,
-                               int8_t* out_value, int16_t* out_plies) {
+                               const uint32_t* __restrict__ keys, int8_t* out_value, int16_t* out_plies) {
   __shared__ __align__(16) uint8_t s_rank[4][256];
   int lane = threadIdx.x & 31;
   int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -455,10 +493,18 @@ __global__ void k_rollout_eval(Geo geo, const uint32_t* rows, const BoardMeta* m
   if (impl == 0 && geo.W <= 15) {
     int winner;
     plies = 0;
-    if (wb_game_end_packed(b, geo.n_in_row, geo.S, winner))
+    if (wb_game_end_packed(b, geo.n_in_row, geo.S, winner)) {
       v = (winner == -1) ? 0 : ((winner == b.cur) ? 1 : -1);
-    else
-      v = rollout_eval_perm(b, rng, geo, lane, plies, s_rank[threadIdx.x >> 5]);
+    } else {
+      uint32_t h[8];
+      if (keys) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) h[r] = keys[(size_t)g * 256 + lane * 8 + r] & 0xFFFFFFu;
+      } else {
+        perm_draws(seed, (uint32_t)g, (uint32_t)lane, 0u, h);
+      }
+      v = rollout_eval_perm(b, h, geo, lane, plies, s_rank[threadIdx.x >> 5]);
+    }
   } else {
     v = rollout_eval(b, rng, geo, lane, plies);
   }
@@ -482,8 +528,9 @@ void launch_pure_run(ap_engine* e, int n_playout, uint64_t seed, int mode, int32
   auto k = (mode == 0) ? k_pure_run<0> : (mode == 1) ? k_pure_run<1> : k_pure_run<2>;
   k<<<e->geo.G, 32, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, n_playout, seed, d_move, e->errflag, e->stats);
 }
-void launch_rollout_eval(ap_engine* e, uint64_t seed, int impl, int8_t* d_value, int16_t* d_plies) {
-  k_rollout_eval<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->rows, e->meta, seed, impl, d_value, d_plies);
+void launch_rollout_eval(ap_engine* e, uint64_t seed, int impl, const uint32_t* d_keys, int8_t* d_value, int16_t* d_plies) {
+  k_rollout_eval<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->rows, e->meta, seed, impl, d_keys, d_value,
+                                                          d_plies);
 }
 void launch_rollout_hash(ap_engine* e, int8_t* d_value) {
   k_rollout_hash<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->rows, e->meta, d_value);

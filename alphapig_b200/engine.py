@@ -234,6 +234,15 @@ class Engine(object):
         self._check(self.lib.ap_rollout_eval2(self.h, int(seed), int(impl), _ptr(v), _ptr(p)))
         return v.astype(np.int32), p.astype(np.int32)
 
+    def rollout_eval_keys(self, keys):
+        """Permutation rollout with injected draws: keys uint32 [G][256], slot = row*16 + column (low 24 bits)."""
+        keys = np.ascontiguousarray(keys, np.uint32)
+        assert keys.shape == (self.G, 256)
+        v = np.zeros(self.G, np.int8)
+        p = np.zeros(self.G, np.int16)
+        self._check(self.lib.ap_rollout_eval_keys(self.h, _ptr(keys), _ptr(v), _ptr(p)))
+        return v.astype(np.int32), p.astype(np.int32)
+
     def rollout_hash(self):
         v = np.zeros(self.G, np.int8)
         self._check(self.lib.ap_rollout_hash(self.h, _ptr(v)))

@@ -126,6 +126,11 @@ int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_
 int ap_rollout_eval(ap_engine* e, uint64_t seed, int8_t* out_value /* [G] */, int16_t* out_plies /* [G] */);
 /* same with the rollout implementation chosen: impl 0 = permutation (default), 2 = ply by ply */
 int ap_rollout_eval2(ap_engine* e, uint64_t seed, int32_t impl, int8_t* out_value /* [G] */, int16_t* out_plies /* [G] */);
+/* the permutation rollout with INJECTED randomness: keys[g][row*16 + column] (low 24 bits used) is the draw of
+ * that cell; the empty cells are played in ascending (key, cell) order - exactly what the oracle replays move by
+ * move (mcts_pure.py:138-157 with the arg-max draws replaced by this order).  width <= 15. */
+int ap_rollout_eval_keys(ap_engine* e, const uint32_t* keys /* [G][256] */, int8_t* out_value /* [G] */,
+                         int16_t* out_plies /* [G] */);
 /* the deterministic hash used by rollout_mode 1, for the host-side oracle */
 int ap_rollout_hash(ap_engine* e, int8_t* out_value /* [G] */);
 

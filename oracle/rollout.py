@@ -76,3 +76,57 @@ def rollout_by_descent(board, order):
     if t >= E:
         return 0, E
     return (-1 if (t & 1) else 1), t + 1
+
+
+def line_windows(W, H, n):
+    """all n-cell windows (right / up / up-right / up-left, game.py:141-156) as an (n_windows, n) index array"""
+    import numpy as np
+    wins = []
+    for h in range(H):
+        for w in range(W):
+            m = h * W + w
+            if w <= W - n:
+                wins.append([m + k for k in range(n)])
+            if h <= H - n:
+                wins.append([m + k * W for k in range(n)])
+            if w <= W - n and h <= H - n:
+                wins.append([m + k * (W + 1) for k in range(n)])
+            if w >= n - 1 and h <= H - n:
+                wins.append([m + k * (W - 1) for k in range(n)])
+    return np.array(wins)
+
+
+def rollout_sample_numpy(board, n_samples, rs, chunk=20000):
+    """``n_samples`` independent reference rollouts (mcts_pure.py:138-157) from a non-terminal ``board`` whose
+    stone count already passes the ``n_in_row + 2`` early-out of game.py:134 whenever a line can exist,
+    vectorised: the move order of a rollout is a uniformly random permutation of the empty cells (argsort of
+    iid uniforms from ``rs``, a ``numpy.random.RandomState``); a window is completed by the side whose
+    plies all have the window's parity, at its largest ply; the game ends at the earliest completion.
+    Returns (values for the player to move at ``board``, plies played) -- the statistical pin of the device
+    rollouts (tests/test_gpu_tree.py), itself checked against ``rollout_by_play`` in the CPU suite."""
+    import numpy as np
+    W, H, n = board.width, board.height, board.n_in_row
+    S = W * H
+    wins = line_windows(W, H, n)
+    player = board.get_current_player()
+    empties = np.array(board.availables)
+    E = len(empties)
+    base = np.zeros(S, np.int16)
+    for m, p in board.states.items():
+        base[m] = -2 if p == player else -1  # parity 0 = the side to move, parity 1 = its opponent
+    vals, plies = [], []
+    for c0 in range(0, n_samples, chunk):
+        c = min(chunk, n_samples - c0)
+        order = np.argsort(rs.random_sample((c, E)), axis=1)  # order[i, t] = index of the empty cell played at ply t
+        rank = np.empty((c, E), np.int16)
+        np.put_along_axis(rank, order, np.broadcast_to(np.arange(E, dtype=np.int16), (c, E)), axis=1)
+        full = np.broadcast_to(base, (c, S)).copy()
+        full[:, empties] = rank
+        r = full[:, wins]                                      # (c, n_windows, n)
+        par = r & 1
+        same = (par == par[:, :, :1]).all(axis=2)
+        t = np.where(same, r.max(axis=2), 30000).min(axis=1)   # ply index (0-based) that completes the first line
+        tie = t >= 30000
+        plies.append(np.where(tie, E, t + 1))
+        vals.append(np.where(tie, 0, np.where(t % 2 == 0, 1, -1)))
+    return np.concatenate(vals), np.concatenate(plies)

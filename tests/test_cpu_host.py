@@ -271,3 +271,28 @@ def test_permutation_rollout_restatement_equals_play():
             assert got == want, (W, H, n, moves, list(order))
             ties += want[0] == 0
     assert ties > 0  # the 5x5x5 board mostly ties: the t >= E branch is exercised
+
+
+def test_vectorised_rollout_sampler_equals_play():
+    """oracle/rollout.py:rollout_sample_numpy (the statistical pin of the device rollouts) against playing the
+    same move orders one by one on the oracle board (mcts_pure.py:138-157)."""
+    from helpers import oboard_from, synth_position
+    from oracle.rollout import rollout_by_play, rollout_sample_numpy
+
+    class Replay(object):  # RandomState stand-in that records the uniforms it hands out
+        def __init__(self, seed):
+            self.rs = np.random.RandomState(seed)
+            self.keys = None
+
+        def random_sample(self, shape):
+            self.keys = self.rs.random_sample(shape)
+            return self.keys
+
+    for moves in ([], synth_position(15, 15, 5, 1240), synth_position(15, 15, 5, 1251)):
+        b = oboard_from(15, 15, 5, moves)
+        rp = Replay(5)
+        v, p = rollout_sample_numpy(b, 60, rp)
+        empties = np.array(b.availables)
+        for i in range(60):
+            order = empties[np.argsort(rp.keys[i])]
+            assert (int(v[i]), int(p[i])) == rollout_by_play(b, order)

@@ -218,38 +218,74 @@ def _two_sample_chi2_p(a, b, bins):
     return chi2_contingency(tab)[1]
 
 
-def test_rollout_permutation_equals_ply_by_ply_distribution():
-    """ap_rollout_eval2: the permutation rollout (impl 0: one random permutation of the empty cells +
-    bit-descent to the first line) and the ply-by-ply rollout (impl 2: mcts_pure.py:138-157 move by move)
-    are the same distribution of (value, plies): 65k samples each from the empty board and from
-    SURVEY 8(d) mid-game positions."""
+def test_rollout_permutation_exact_with_injected_draws():
+    """ap_rollout_eval_keys: with the per-cell draws supplied by the host (NumPy MT19937) the device permutation
+    rollout must return exactly the (value, plies) of the oracle playing the empty cells in ascending
+    (draw, cell) order move by move (mcts_pure.py:138-157) - 15x15 empty / mid-game / late positions, 8x8."""
+    from oracle.rollout import rollout_by_play
+    rs = np.random.RandomState(21)
+    for W, H, n, G in ((15, 15, 5, 384), (8, 8, 5, 64), (11, 9, 4, 64)):
+        eng = _engine(width=W, height=H, n_in_row=n, n_games=G, n_playout=1, node_capacity=4)
+        boards = []
+        for g in range(G):
+            while True:  # random legal play of random length that leaves the game open
+                b = oboard_from(W, H, n, [])
+                for _ in range(rs.randint(0, W * H - 1) if g % 3 else rs.randint(0, 8)):
+                    b.do_move(int(b.availables[rs.randint(len(b.availables))]))
+                    if b.game_end()[0]:
+                        break
+                if not b.game_end()[0]:
+                    break
+            boards.append(b)
+        ex = [export_oboard(b) for b in boards]
+        eng.boards_import(np.stack([c for c, _ in ex]), np.stack([m for _, m in ex]))
+        keys = rs.randint(0, 1 << 24, size=(G, 256)).astype(np.uint32)
+        keys[::5] &= 0xFF  # every fifth game: 8-bit draws, many ties -> the cell index decides
+        v, p = eng.rollout_eval_keys(keys)
+        for g, b in enumerate(boards):
+            cells16 = [(m // W) * 16 + (m % W) for m in b.availables]
+            order = [m for _, _, m in sorted((int(min(keys[g, c], 0xFFFFFE)), c, m) for c, m in zip(cells16, b.availables))]
+            assert (int(v[g]), int(p[g])) == rollout_by_play(b, order), (W, H, n, g)
+        eng.close()
+
+
+def _moments_agree(dev_v, dev_p, ref_v, ref_p, what, k=4.5):
+    """mean value, mean plies and the spread of plies of two samples agree within k standard errors"""
+    dv, dp, rv, rp = (np.asarray(x, np.float64) for x in (dev_v, dev_p, ref_v, ref_p))
+    se = lambda a, b_: np.sqrt(a.var() / len(a) + b_.var() / len(b_))
+    assert abs(dv.mean() - rv.mean()) < k * se(dv, rv), (what, "value", dv.mean(), rv.mean())
+    assert abs(dp.mean() - rp.mean()) < k * se(dp, rp), (what, "plies", dp.mean(), rp.mean())
+    # standard error of a standard deviation ~ sd * sqrt((kurt - 1) / 4n); kurtosis of these lengths is < 4
+    se_sd = np.sqrt(dp.var() * 0.75 / len(dp) + rp.var() * 0.75 / len(rp))
+    assert abs(dp.std() - rp.std()) < k * se_sd, (what, "sd(plies)", dp.std(), rp.std())
+
+
+def test_rollout_distribution_pinned_to_numpy_reference_sample():
+    """ap_rollout_eval2, both implementations (0 = permutation + bit descent, 2 = ply by ply), against
+    oracle/rollout.py:rollout_sample_numpy (mcts_pure.py:138-157 with NumPy's own generator): ~1M device
+    rollouts vs 300k reference rollouts from the empty board and from two SURVEY 8(d) mid-game positions.
+    Mean value, mean length, spread of the length (4.5 standard errors) and the length histogram."""
+    from oracle.rollout import rollout_sample_numpy
     W = H = 15
     G = 16384
     eng = _engine(width=W, height=H, n_in_row=5, n_games=G, n_playout=1, node_capacity=4)
-    for positions in ("empty", "midgame"):
-        if positions == "midgame":
-            cells = np.zeros((G, W * H), np.int8)
-            meta = np.zeros((G, 8), np.int32)
-            uniq = [export_oboard(oboard_from(W, H, 5, synth_position(W, H, 5, 1234 + i))) for i in range(64)]
-            for g in range(G):
-                cells[g], meta[g] = uniq[g % 64]
-            eng.boards_import(cells, meta)
-        va, pa, vb, pb = [], [], [], []
-        for seed in range(4):
-            v, p = eng.rollout_eval(seed=seed, impl=0)
-            va.append(v), pa.append(p)
-            v, p = eng.rollout_eval(seed=1000 + seed, impl=2)
-            vb.append(v), pb.append(p)
-        va, pa, vb, pb = map(np.concatenate, (va, pa, vb, pb))
-        assert pa.min() >= 1 and pa.max() <= 225
-        assert _two_sample_chi2_p(pa, pb, np.arange(0, 232, 4)) > 1e-6, positions
-        assert _two_sample_chi2_p(va, vb, np.array([-1.5, -0.5, 0.5, 1.5])) > 1e-6, positions
-        # joint: plies of the won / lost rollouts separately (who completes the line depends on ply parity)
-        for val in (-1, 1):
-            assert _two_sample_chi2_p(pa[va == val], pb[vb == val], np.arange(0, 232, 4)) > 1e-6, (positions, val)
-        # parity law of the alternating game: the side to move at the leaf wins on odd ply counts only
-        won = va == 1
-        assert np.all(pa[won] % 2 == 1) and np.all(pa[va == -1] % 2 == 0)
+    for name, moves in (("empty", []), ("mid1240", synth_position(W, H, 5, 1240)), ("mid1251", synth_position(W, H, 5, 1251))):
+        b = oboard_from(W, H, 5, moves)
+        c, m = export_oboard(b)
+        eng.boards_import(np.repeat(c[None], G, 0), np.repeat(m[None], G, 0))
+        ref_v, ref_p = rollout_sample_numpy(b, 300000, np.random.RandomState(77))
+        for impl, n_seeds in ((0, 64), (2, 16)):
+            out = [eng.rollout_eval(seed=1000 * impl + sd, impl=impl) for sd in range(n_seeds)]
+            v = np.concatenate([o[0] for o in out])
+            p = np.concatenate([o[1] for o in out])
+            what = (name, impl)
+            assert p.min() >= 1 and p.max() <= len(b.availables)
+            _moments_agree(v, p, ref_v, ref_p, what)
+            assert _two_sample_chi2_p(p, ref_p, np.arange(0, 232, 3)) > 1e-5, what
+            for val in (-1, 1):
+                assert _two_sample_chi2_p(p[v == val], ref_p[ref_v == val], np.arange(0, 232, 3)) > 1e-5, (what, val)
+            # parity law of the alternating game: the side to move at the leaf wins on odd ply counts only
+            assert np.all(p[v == 1] % 2 == 1) and np.all(p[v == -1] % 2 == 0)
     eng.close()
 
 

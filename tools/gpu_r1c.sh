@@ -1,7 +1,7 @@
 #!/bin/bash
 TAG=${1:-r1c}
 set -x
-timeout 600 python -m pytest tests/test_gpu_tree.py tests/test_gpu_fullsize.py -m gpu -x -q > gpurun_out/${TAG}_pytest_tree.log 2>&1; echo "pytest tree rc=$?"
+timeout 600 python -m pytest tests/test_gpu_tree.py tests/test_gpu_fullsize.py tests/test_gpu_shims.py -m gpu -x -q > gpurun_out/${TAG}_pytest_tree.log 2>&1; echo "pytest tree rc=$?"
 tail -15 gpurun_out/${TAG}_pytest_tree.log
 timeout 300 python tools/rollout_stats.py > gpurun_out/${TAG}_rollout_stats.log 2>&1; echo "stats rc=$?"; cat gpurun_out/${TAG}_rollout_stats.log
 timeout 300 python tools/pure_ab.py > gpurun_out/${TAG}_pure_ab.log 2>&1; echo "ab rc=$?"; cat gpurun_out/${TAG}_pure_ab.log
