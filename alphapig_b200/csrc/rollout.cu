@@ -195,7 +195,21 @@ __device__ __forceinline__ void warp_sort256(uint32_t (&v)[8], int lane) {
 
 // both colours at once: x = player-1 row | player-2 row << 16 with bits 15 and 31 clear (W <= 15), so every
 // window that would cross from one half into the other contains a clear bit
+template <int N>
+__device__ __forceinline__ bool wb_packed_wins_n(uint32_t x) {
+  uint32_t th = x, tv = x, td = x, ta = x;
+#pragma unroll
+  for (int k = 1; k < N; ++k) {
+    const uint32_t up = __shfl_down_sync(AP_FULL, x, k);
+    th &= x >> k;
+    tv &= up;
+    td &= up >> k;
+    ta &= up << k;
+  }
+  return __any_sync(AP_FULL, (th | tv | td | ta) != 0u);
+}
 __device__ __forceinline__ bool wb_packed_wins(uint32_t x, int n) {
+  if (n == 5) return wb_packed_wins_n<5>(x);  // five-in-a-row: immediate shifts, no loop
   uint32_t th = x, tv = x, td = x, ta = x;
 #pragma unroll 1
   for (int k = 1; k < n; ++k) {
@@ -209,8 +223,9 @@ __device__ __forceinline__ bool wb_packed_wins(uint32_t x, int n) {
 }
 
 // s_rank holds the rank of column c of board row h at byte h*16 + rank_slot(c); with that order bit `bit` of the
-// 16 ranks of a row gathers into a 16-bit column mask with a handful of shifts
-__device__ __forceinline__ uint32_t rank_slot(uint32_t c) { return ((c & 3u) << 2) | (c >> 2); }
+// 16 ranks of a row gathers into a 16-bit column mask with a handful of shifts.  rank_slot is an involution.
+// The sort payload of a board slot is this byte offset, so the ranks scatter with one store each.
+__host__ __device__ __forceinline__ uint32_t rank_slot(uint32_t c) { return ((c & 3u) << 2) | (c >> 2); }
 __device__ __forceinline__ uint32_t rank_plane(const uint4& rr, int bit) {
   const uint32_t M = 0x01010101u;
   const uint32_t a = (rr.x >> bit) & M, b = (rr.y >> bit) & M, c = (rr.z >> bit) & M, d = (rr.w >> bit) & M;
@@ -221,25 +236,26 @@ __device__ __forceinline__ uint32_t rank_plane(const uint4& rr, int bit) {
 
 // MCTS._evaluate_rollout (mcts_pure.py:138-157) by permutation from a NON-terminal position (the caller has
 // done the game_end() of :143); s_rank: 256 bytes of shared memory of this warp
-// h: this lane's 8 random draws (24 bits each; slot r = cell16 lane*8 + r)
+// h: this lane's 8 random draws (24 bits each); element r of lane L is the board slot with payload L*8 + r =
+// row (L >> 1), column rank_slot((L & 1) * 8 + r); ties in the draw are ordered by payload
 __device__ __forceinline__ int rollout_eval_perm(const WBoard& b, const uint32_t (&h)[8], const Geo& geo, int lane,
                                                  int& plies, uint8_t* s_rank) {
   const int player = b.cur;
   const uint32_t e = wb_empty_row(b, geo.W, geo.H, lane);  // lanes >= H: 0
   const int E = geo.S - b.nst;
-  // slot (lane, r) starts as cell16 = lane*8 + r = row (lane >> 1), column (lane & 1) * 8 + r
-  const uint32_t er = __shfl_sync(AP_FULL, e, lane >> 1) >> ((lane & 1) * 8);
+  // column of element r: rank_slot((lane & 1) * 8 + r) = (r & 3) * 4 + (r >> 2) + 2 * (lane & 1)
+  const uint32_t er = __shfl_sync(AP_FULL, e, lane >> 1) >> ((lane & 1) * 2);
   uint32_t v[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    const uint32_t cell = (uint32_t)(lane * 8 + r);
-    v[r] = ((er >> r) & 1u) ? ((min(h[r], 0xFFFFFEu) << 8) | cell) : 0xFFFFFFFFu;
+    const uint32_t payload = (uint32_t)(lane * 8 + r);
+    v[r] = ((er >> ((r & 3) * 4 + (r >> 2))) & 1u) ? ((min(h[r], 0xFFFFFEu) << 8) | payload) : 0xFFFFFFFFu;
   }
   warp_sort256(v, lane);
   __syncwarp();
 #pragma unroll
   for (int r = 0; r < 8; ++r)
-    if (v[r] != 0xFFFFFFFFu) s_rank[(v[r] & 0xF0u) | rank_slot(v[r] & 0xFu)] = (uint8_t)(lane * 8 + r);
+    if (v[r] != 0xFFFFFFFFu) s_rank[v[r] & 0xFFu] = (uint8_t)(lane * 8 + r);
   __syncwarp();
   uint4 rr = make_uint4(0u, 0u, 0u, 0u);
   if (lane < AP_ROWS) rr = *reinterpret_cast<const uint4*>(s_rank + lane * 16);
@@ -331,21 +347,19 @@ __device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, i
       }
     }
   }
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    double ov = __shfl_xor_sync(AP_FULL, bv, d);
-    int oi = __shfl_xor_sync(AP_FULL, bi, d);
-    int om = __shfl_xor_sync(AP_FULL, bm, d);
-    // python max(): keep the earliest index unless a later one is strictly greater
-    bool take = (oi != INT_MAX) && (bi == INT_MAX || (oi < bi ? !(bv > ov) : (ov > bv)));
-    if (take) {
-      bv = ov;
-      bi = oi;
-      bm = om;
-    }
-  }
-  best_move = bm;
-  return bi;
+  // python max(): the largest score, the earliest child among equals.  Scores map to order-preserving 64-bit
+  // integers (-0.0 folded into +0.0 first; no NaNs: Q and u are finite), then three warp reductions.
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(__dadd_rn(bv, 0.0));
+  const unsigned long long key = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+  const bool have = bi != INT_MAX;
+  const uint32_t khi = have ? (uint32_t)(key >> 32) : 0u, klo = (uint32_t)key;
+  const uint32_t mhi = __reduce_max_sync(AP_FULL, khi);
+  const bool c1 = have && khi == mhi;
+  const uint32_t mlo = __reduce_max_sync(AP_FULL, c1 ? klo : 0u);
+  const bool c2 = c1 && klo == mlo;
+  const uint32_t best = __reduce_min_sync(AP_FULL, c2 ? (uint32_t)bi : 0xFFFFFFFFu);
+  best_move = __shfl_sync(AP_FULL, bm, (int)(best & 31u));
+  return (int)best;
 }
 
 // MCTS.get_move (mcts_pure.py:159-169): tree reset, n_playout x _playout (:114-136), arg-max visits.
@@ -499,7 +513,8 @@ __global__ void k_rollout_eval(Geo geo, const uint32_t* rows, const BoardMeta* m
       uint32_t h[8];
       if (keys) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) h[r] = keys[(size_t)g * 256 + lane * 8 + r] & 0xFFFFFFu;
+        for (int r = 0; r < 8; ++r)
+          h[r] = keys[(size_t)g * 256 + (lane >> 1) * 16 + rank_slot((uint32_t)((lane & 1) * 8 + r))] & 0xFFFFFFu;
       } else {
         perm_draws(seed, (uint32_t)g, (uint32_t)lane, 0u, h);
       }

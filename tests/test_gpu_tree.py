@@ -243,8 +243,10 @@ def test_rollout_permutation_exact_with_injected_draws():
         keys[::5] &= 0xFF  # every fifth game: 8-bit draws, many ties -> the cell index decides
         v, p = eng.rollout_eval_keys(keys)
         for g, b in enumerate(boards):
-            cells16 = [(m // W) * 16 + (m % W) for m in b.availables]
-            order = [m for _, _, m in sorted((int(min(keys[g, c], 0xFFFFFE)), c, m) for c, m in zip(cells16, b.availables))]
+            # draw of cell (h, w) = keys[g, h*16 + w]; equal draws are ordered by the device's slot index
+            slot = lambda w: ((w & 3) << 2) | (w >> 2)
+            order = [m for _, _, m in sorted((int(min(keys[g, (m // W) * 16 + m % W], 0xFFFFFE)), (m // W) * 16 + slot(m % W), m)
+                                             for m in b.availables)]
             assert (int(v[g]), int(p[g])) == rollout_by_play(b, order), (W, H, n, g)
         eng.close()
 
