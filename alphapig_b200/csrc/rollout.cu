@@ -3,6 +3,14 @@
 #include "kernels.h"
 #include "tree.cuh"
 
+// resident CTAs (= games) per SM the pure kernel is compiled for (register budget 65536 / (32 * N)).  Measured on
+// B200, configs[2]: 24 (80 registers, no spills) 267 M playouts/s; the kernel is issue-bound (71 % issue-active
+// under ncu), so more resident warps at the price of spills do not pay.  A variant that kept the root's children
+// in shared memory executed 16 % more instructions and was 13 % slower - the children blocks are L2-resident anyway.
+#ifndef AP_PURE_MINBLK
+#define AP_PURE_MINBLK 24
+#endif
+
 struct Pcg {
   unsigned long long s, inc;
 };
@@ -366,7 +374,7 @@ __device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, i
 // P of the children is not stored (implicit 1/child_count, see pure_select_child); the path of a playout is kept
 // in shared memory so that update_recursive (:61-67) touches all its nodes in one memory round trip, one lane each.
 template <int MODE>  // 0 = permutation rollouts (W <= 15), 1 = position hash, 2 = ply-by-ply rollouts
-__global__ void __launch_bounds__(32, 24)
+__global__ void __launch_bounds__(32, AP_PURE_MINBLK)
 k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, int n_playout,
            unsigned long long seed, int32_t* out_move, int32_t* errflag, unsigned long long* stats) {
   __shared__ int16_t s_list[AP_MAX_S];
