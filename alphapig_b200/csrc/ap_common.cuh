@@ -128,8 +128,9 @@ int ap_ids(ap_engine* e, const int32_t* game_ids, int32_t n);  // uploads ids (o
 void replay_destroy(ap_engine* e);
 // net.cu
 int net_destroy(ap_engine* e);
-int net_forward_leaves(ap_engine* e, int precise, bool compact = false);
+int net_forward_leaves(ap_engine* e, int precise, bool compact = false, bool compacted_by_select = false);
 int net_emit_features_launch(ap_engine* e, bool compact = false);
 int net_check_err(ap_engine* e);
 int net_phase_count(ap_engine* e);
+bool net_can_compact(ap_engine* e);
 void prof_mark(ap_engine* e);

@@ -410,16 +410,20 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
     }
     e->prof_cursor = 0;
   }
+  // AP_COMPACT_KERNEL=1: separate order-preserving compaction kernel instead of the ticket inside k_select (A/B)
+  static const bool compact_kernel = getenv("AP_COMPACT_KERNEL") && atoi(getenv("AP_COMPACT_KERNEL")) != 0;
+  AP_CUDA(e, cudaMemsetAsync(e->leaves.n_eval, 0, 4, e->stream));
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   prof_mark(e);
+  const bool compact = net_can_compact(e);
   for (int it = 0; it < n_playout; ++it) {
-    launch_select(e);
+    launch_select(e, compact && !compact_kernel);
     AP_LAUNCH_CHECK(e);
     prof_mark(e);
     // only the non-terminal leaves are evaluated (the reference discards the evaluator's answer at a terminal
     // leaf, mcts_alphaZero.py:124-136): the net runs on the compacted batch, expand/backup reads through the slot map
-    AP_TRY(net_forward_leaves(e, 0, true));
-    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values, e->leaves.slot);
+    AP_TRY(net_forward_leaves(e, 0, compact, !compact_kernel));
+    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values, compact ? e->leaves.slot : nullptr);
     AP_LAUNCH_CHECK(e);
     prof_mark(e);
   }

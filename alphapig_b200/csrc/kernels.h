@@ -17,7 +17,7 @@ void launch_boards_import(ap_engine* e, int n, const int8_t* d_cells, const int3
 
 // tree.cu
 void launch_tree_reset_all(ap_engine* e);
-void launch_select(ap_engine* e);
+void launch_select(ap_engine* e, bool compact = false);
 void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* d_acts, const double* d_pri64,
                           const double* d_val64, const float* d_pri32, const float* d_val32,
                           const int32_t* d_slot = nullptr);

@@ -114,38 +114,37 @@ __global__ void k_prep_heads(const float* __restrict__ master, HeadParams h, int
 // ------------------------------------------------------------------------------------------
 // features: leaf bitboards -> fp16 planes [2][mpad][8]  (Board.current_state, game.py:68-94)
 // ------------------------------------------------------------------------------------------
+// One warp per board.  Lane h holds the 8 stone planes of board row h (bitboards with the last i plies dropped);
+// the 16-byte pixel records are then written a tensor row at a time: lanes 0-15 = the 16 pixels of the row in the
+// channel-0..7 plane, lanes 16-31 = the same pixels in the channel-8..15 plane (two contiguous 256-byte runs per
+// store instruction instead of 16 runs of 16 bytes).
 __global__ void k_emit_features(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, int nb,
                                 const int32_t* __restrict__ game_of_slot, const int32_t* __restrict__ nb_dev, __half* feat,
                                 long long mpad) {
-  int lane = threadIdx.x & 31;
-  int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // net tile
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // net tile
   if (b >= (nb_dev ? *nb_dev : nb)) return;
-  WBoard wb = wb_load(rows, meta, game_of_slot ? game_of_slot[b] : b, lane);
+  const WBoard wb = wb_load(rows, meta, game_of_slot ? game_of_slot[b] : b, lane);
   const int W = geo.W, H = geo.H;
-  uint32_t pl[8];
+  // planes 2c, 2c+1 packed as (lo16, hi16): pk[3 - d] = (mine, theirs) with the last d plies dropped
+  uint32_t pk[4];
 #pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    pl[6 - 2 * d] = wb_rows_dropped(wb, wb.cur, d, W, lane);
-    pl[7 - 2 * d] = wb_rows_dropped(wb, 3 - wb.cur, d, W, lane);
-  }
-  const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
-  const __half p8 = (wb.nst % 2 == 0) ? one : zero;
-  if (lane < H) {
-    const int y = H - 1 - lane;  // axis-1 flip
-    long long row = NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + y * 16;
-    for (int x = 0; x < W; ++x) {
-      uint4 g0, g1;
-      __half* h0 = reinterpret_cast<__half*>(&g0);
-      __half* h1 = reinterpret_cast<__half*>(&g1);
+  for (int d = 0; d < 4; ++d)
+    pk[3 - d] = wb_rows_dropped(wb, wb.cur, d, W, lane) | (wb_rows_dropped(wb, 3 - wb.cur, d, W, lane) << 16);
+  const uint32_t p8 = (wb.nst % 2 == 0) ? 0x3C00u : 0u;  // fp16 1.0 in channel 8
+  const int x = lane & 15, grp = lane >> 4;
+  __half* dst = feat + ((long long)grp * mpad + NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + x) * 8;
+  for (int y = 0; y < H; ++y) {
+    const int src = H - 1 - y;  // axis-1 flip
+    uint4 v;
+    uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        h0[c] = ((pl[c] >> x) & 1u) ? one : zero;
-        h1[c] = zero;
-      }
-      h1[0] = p8;
-      *reinterpret_cast<uint4*>(feat + (row + x) * 8) = g0;
-      *reinterpret_cast<uint4*>(feat + (mpad + row + x) * 8) = g1;
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t r = __shfl_sync(AP_FULL, pk[c], src) >> x;
+      vv[c] = ((r & 1u) ? 0x3C00u : 0u) | ((r & 0x10000u) ? 0x3C000000u : 0u);
     }
+    if (grp) v = make_uint4(p8, 0u, 0u, 0u);
+    if (x < W) *reinterpret_cast<uint4*>(dst + (long long)y * 16 * 8) = v;
   }
 }
 
@@ -768,6 +767,8 @@ extern "C" int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, 
 }
 
 // trunk + heads on the first nb boards of the feature planes -> probs/values (device)
+// compacted leaf batches need the fused head path (device-side tile counts in every kernel of the forward)
+bool net_can_compact(ap_engine* e) { return e->net && e->net->head_mode == 2; }
 int net_phase_count(ap_engine* e) { return e->net ? (int)e->net->trunk.size() + 2 : 0; }
 
 // nb_dev != nullptr: the number of boards is read on the device (compacted leaf batch, at most nb)
@@ -848,13 +849,13 @@ int net_emit_features_launch(ap_engine* e, bool compact) {
 }
 
 // leaves of the last select -> e->d_probs / e->d_values
-int net_forward_leaves(ap_engine* e, int precise, bool compact) {
+int net_forward_leaves(ap_engine* e, int precise, bool compact, bool compacted_by_select) {
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
   NetState* n = e->net;
   const int G = e->geo.G;
   if (!precise) {
     compact = compact && n->head_mode == 2;
-    if (compact) {
+    if (compact && !compacted_by_select) {
       launch_compact_leaves(e);
       AP_LAUNCH_CHECK(e);
     }

@@ -12,9 +12,16 @@ __global__ void k_tree_reset_all(Geo geo, Pools pl) {
 }
 
 // MCTS._playout lines 113-121 + the game_end() of :126 for every game.
-__global__ void __launch_bounds__(32 * SEL_WARPS)
+// 7 CTAs x 4 warps per SM: 4096 games are resident at once on 148 SMs (one wave of dependent-load chains)
+// compact != 0: the non-terminal leaves also take a net tile each (slot / game_of_slot / n_eval, the batch the
+// net evaluates); tiles are handed out by an atomic ticket - the order is arbitrary, every board's result is
+// independent of the tile it sits in.  n_eval is zeroed by k_expand_backup (and before the first lock-step).
+#ifndef AP_SEL_MINBLK
+#define AP_SEL_MINBLK 7
+#endif
+__global__ void __launch_bounds__(32 * SEL_WARPS, AP_SEL_MINBLK)
 k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, Leaves lv,
-         unsigned long long* stats) {
+         unsigned long long* stats, int compact) {
   int lane = threadIdx.x & 31;
   int g = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
   if (g >= geo.G) return;
@@ -23,16 +30,17 @@ k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict
   int node = 0, depth = 0;
   unsigned long long scanned = 0;
   while (true) {
-    // the three node fields travel together (one round trip), not cs first and the rest after the leaf test
+    // the node fields travel together (one round trip): child block, visit count and the move that led here
     const int cs = pl.child_start[base + node];
     const int cc = pl.child_count[base + node];
     const int np = pl.N[base + node];
+    const int mv = pl.move[base + node];
+    if (depth > 0) {
+      if (lane == 0) lv.path[(size_t)g * geo.S + depth - 1] = (int16_t)mv;
+      wb_do_move(b, mv, geo.W, lane);
+    }
     if (cs < 0) break;
-    int mv;
-    int bi = tree_select_child(pl, base, cs, cc, np, geo.c_puct, lane, mv);
-    if (lane == 0) lv.path[(size_t)g * geo.S + depth] = (int16_t)mv;
-    wb_do_move(b, mv, geo.W, lane);
-    node = cs + bi;
+    node = cs + tree_select_child(pl, base, cs, cc, np, geo.c_puct, lane);
     ++depth;
     scanned += cc;
   }
@@ -44,6 +52,14 @@ k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict
     lv.terminal[g] = end ? 1 : 0;
     lv.winner[g] = (int8_t)winner;
     lv.depth[g] = depth;
+    if (compact) {
+      int sl = -1;
+      if (!end) {
+        sl = atomicAdd(lv.n_eval, 1);
+        lv.game_of_slot[sl] = g;
+      }
+      lv.slot[g] = sl;
+    }
     atomicAdd(&stats[0], 1ull);
     atomicAdd(&stats[1], scanned);
     atomicAdd(&stats[3], (unsigned long long)(depth + 1));
@@ -96,6 +112,7 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
     v = (winner == -1) ? 0.0 : ((winner == cur) ? 1.0 : -1.0);  // mcts_alphaZero.py:131-136
   }
   if (lane == 0) tree_backup(pl, base, leaf, -v);
+  if (slot && g == 0 && lane == 0) *lv.n_eval = 0;  // next lock-step's ticket counter (nobody reads it in this kernel)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,8 +313,9 @@ static inline dim3 sel_grid(int n) { return dim3((n + SEL_WARPS - 1) / SEL_WARPS
 void launch_tree_reset_all(ap_engine* e) {
   k_tree_reset_all<<<(e->geo.G + 127) / 128, 128, 0, e->stream>>>(e->geo, e->pools);
 }
-void launch_select(ap_engine* e) {
-  k_select<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, e->leaves, e->stats);
+void launch_select(ap_engine* e, bool compact) {
+  k_select<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, e->leaves, e->stats,
+                                                                compact ? 1 : 0);
 }
 void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* d_acts, const double* d_pri64,
                           const double* d_val64, const float* d_pri32, const float* d_val32, const int32_t* d_slot) {

@@ -10,31 +10,30 @@
 
 // TreeNode.select (mcts_alphaZero.py:43-49) over the children block [cs, cs+cc) of a node
 // whose visit count is np:  score = Q + ((c_puct*P)*sqrt(Np))/(1+N)   (:78-80),
-// first maximum in child (insertion) order.  Returns the child offset within the block and its move.
+// first maximum in child (insertion) order.  Returns the child offset within the block.
 // Latency: every lane issues the loads of all its (<= AP_MAX_S/32) children before the first fp64 op, so a
 // level costs one memory round trip instead of one per 32 children (the fp64 division's slow-path branch
-// otherwise keeps the compiler from hoisting the next iteration's loads); the winning move comes back through
-// a shuffle instead of a dependent load.
+// otherwise keeps the compiler from hoisting the next iteration's loads).  The caller reads the winner's move
+// together with its node fields (one more round trip for both).
 __device__ __forceinline__ int tree_select_child(const Pools& pl, size_t base, int cs, int cc, int np, double c_puct,
-                                                 int lane, int& best_move) {
+                                                 int lane) {
   constexpr int PER = AP_MAX_S / 32;
   double p[PER], q[PER];
-  int n[PER], m[PER];
+  int n[PER];
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const int i = lane + 32 * j;
     const size_t c = base + cs + i;
-    p[j] = 0.0, q[j] = 0.0, n[j] = 0, m[j] = -1;
+    p[j] = 0.0, q[j] = 0.0, n[j] = 0;
     if (i < cc) {
       p[j] = pl.P[c];
       q[j] = pl.Q[c];
       n[j] = pl.N[c];
-      m[j] = pl.move[c];
     }
   }
   const double sq = __dsqrt_rn((double)np);
   double bv = -CUDART_INF;
-  int bi = INT_MAX, bm = -1;
+  int bi = INT_MAX;
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const int i = lane + 32 * j;
@@ -44,7 +43,6 @@ __device__ __forceinline__ int tree_select_child(const Pools& pl, size_t base, i
       if (v > bv || bi == INT_MAX) {  // first element always taken, later only if strictly greater
         bv = v;
         bi = i;
-        bm = m[j];
       }
     }
   }
@@ -52,16 +50,13 @@ __device__ __forceinline__ int tree_select_child(const Pools& pl, size_t base, i
   for (int d = 16; d >= 1; d >>= 1) {
     double ov = __shfl_xor_sync(AP_FULL, bv, d);
     int oi = __shfl_xor_sync(AP_FULL, bi, d);
-    int om = __shfl_xor_sync(AP_FULL, bm, d);
     // python max(): keep the earliest index unless a later one is strictly greater
     bool take = (oi != INT_MAX) && (bi == INT_MAX || (oi < bi ? !(bv > ov) : (ov > bv)));
     if (take) {
       bv = ov;
       bi = oi;
-      bm = om;
     }
   }
-  best_move = bm;
   return bi;
 }
 
