@@ -17,6 +17,10 @@
 // B operand (k_prep_fc): [2][Kp/8][Np][8] fp16, one contiguous piece per K chunk.
 // One CTA = 128 boards: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (thread = board row:
 // the softmax over the S logits of a board is thread-local in TMEM).
+// Split K (default 4, AP_FC_KSPLIT): 4096 boards are only 32 tiles, a quarter of the SMs, and every CTA streams
+// the whole 2 MB operand set through one SM's L2 port.  With gridDim.y = 4 each CTA takes a quarter of the K
+// chunks and stores its raw fp32 partial logits ([split][board][np], L2-resident); k_head_fc_finish (one warp
+// per board) adds the partials in fixed order, the bias, and does the softmax / tanh.
 #include "kernels.h"
 #include "net.h"
 #include "ptx.cuh"
@@ -48,6 +52,8 @@ struct FcParams {
   int kg, np, S, nb;
   const int* nb_dev;  // when non-null the number of boards is read from device memory (compacted leaf batches)
   int* errflag;
+  float* partial;    // ksplit > 1: [ksplit][rows][np] raw partial logits
+  int ksplit;
 };
 
 __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
@@ -61,7 +67,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
   uint64_t* acc_full = empty + kFcStages;
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
   float* s_bias = (float*)(tmem_slot + 2);
-  const int nchunks = p.kg / (kFcKC / 8);
+  const int nchunks_all = p.kg / (kFcKC / 8);
+  const int c_begin = (int)((long long)nchunks_all * blockIdx.y / p.ksplit);
+  const int c_end = (int)((long long)nchunks_all * (blockIdx.y + 1) / p.ksplit);
+  const int nchunks = c_end - c_begin;
   const int b0 = blockIdx.x * 128;
   const int nb = p.nb_dev ? *p.nb_dev : p.nb;
   if (b0 >= nb) return;  // whole CTA, before any barrier / TMEM allocation
@@ -101,9 +110,9 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
 #pragma unroll
           for (int j = 0; j < kFcKC / 8; ++j)
             bulk_g2s(smem_u32(sb + part * a_bytes + j * 2048),
-                     p.a + (((long long)part * p.kg + (c * (kFcKC / 8) + j)) * p.rows + b0) * 8, 2048, fb);
+                     p.a + (((long long)part * p.kg + ((c_begin + c) * (kFcKC / 8) + j)) * p.rows + b0) * 8, 2048, fb);
           bulk_g2s(smem_u32(sb + 2 * a_bytes + part * b_bytes),
-                   p.w + ((long long)part * p.kg + c * (kFcKC / 8)) * p.np * 8, b_bytes, fb);
+                   p.w + ((long long)part * p.kg + (c_begin + c) * (kFcKC / 8)) * p.np * 8, b_bytes, fb);
         }
       }
       __syncwarp();
@@ -148,6 +157,17 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
       const int b = b0 + q * 32 + lane;
       const int S = p.S, nch = p.np >> 4;
       uint32_t v[16];
+      if (p.ksplit > 1) {
+        // raw partial logits of this K range; rows beyond nb are padding of the last tile and are not read back
+        float4* dst = reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.y * p.rows + b) * p.np);
+        for (int ch = 0; ch < nch; ++ch) {
+          tmem_ld16(acc + ch * 16, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[ch * 4 + i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      } else {
       float mx = -INFINITY;
       for (int ch = 0; ch < nch; ++ch) {
         tmem_ld16(acc + ch * 16, v);
@@ -180,6 +200,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
           }
         }
       }
+      }
     }
   }
   tc_fence_before();
@@ -187,6 +208,50 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_head_fc_tc(FcParams p) {
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// split-K second half: one warp per board; logits = sum of the partials (fixed order) + bias, softmax over the S
+// policy logits, tanh of the value logit (SoftmaxActivation / tanh of ..._simple.py:84,90)
+__global__ void __launch_bounds__(128) k_head_fc_finish(FcParams p) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int nb = p.nb_dev ? *p.nb_dev : p.nb;
+  if (b >= nb) return;
+  const int S = p.S;
+  float l[8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane + 32 * j;
+    l[j] = 0.f;
+    if (n < p.np) {
+      float a = 0.f;
+      for (int s = 0; s < p.ksplit; ++s) a += p.partial[((size_t)s * p.rows + b) * p.np + n];
+      l[j] = a + p.bias[n];
+      if (n < S) mx = fmaxf(mx, l[j]);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(AP_FULL, mx, d));
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane + 32 * j;
+    if (n < S) {
+      l[j] = expf(l[j] - mx);
+      sum += l[j];
+    } else if (n == S) {
+      p.values[b] = tanhf(l[j]);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(AP_FULL, sum, d);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane + 32 * j;
+    if (n < S) p.probs[(size_t)b * S + n] = l[j] * inv;
   }
 }
 
@@ -248,7 +313,13 @@ int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_val
   p.nb = nb;
   p.nb_dev = nb_dev;
   p.errflag = n->d_err;
-  k_head_fc_tc<<<(nb + 127) / 128, kFcThreads, fc_tc_smem_bytes(n->fc_np), e->stream>>>(p);
+  p.partial = n->fc_partial;
+  p.ksplit = n->fc_ksplit;
+  k_head_fc_tc<<<dim3((nb + 127) / 128, p.ksplit), kFcThreads, fc_tc_smem_bytes(n->fc_np), e->stream>>>(p);
   AP_LAUNCH_CHECK(e);
+  if (p.ksplit > 1) {
+    k_head_fc_finish<<<(nb + 3) / 4, 128, 0, e->stream>>>(p);
+    AP_LAUNCH_CHECK(e);
+  }
   return AP_OK;
 }

@@ -729,6 +729,15 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if ((rc = nalloc(e, n, (void**)&n->fc_a, (size_t)2 * (n->fc_kp / 8) * n->fc_rows * 16)) != AP_OK) return bad(rc);
   if ((rc = nalloc(e, n, (void**)&n->fc_w, (size_t)2 * (n->fc_kp / 8) * n->fc_np * 16)) != AP_OK) return bad(rc);
   if ((rc = nalloc(e, n, (void**)&n->fc_bias, (size_t)n->fc_np * 4)) != AP_OK) return bad(rc);
+  {
+    const char* ks = getenv("AP_FC_KSPLIT");  // 1 = single-pass FC with the softmax in the GEMM epilogue (A/B)
+    n->fc_ksplit = ks ? atoi(ks) : 4;
+    if (n->fc_ksplit < 1 || n->fc_ksplit > 8) n->fc_ksplit = 4;
+    if (n->fc_ksplit > n->fc_kp / 32) n->fc_ksplit = n->fc_kp / 32;  // at least one K stage (32) per split
+  }
+  if (n->fc_ksplit > 1 &&
+      (rc = nalloc(e, n, (void**)&n->fc_partial, (size_t)n->fc_ksplit * n->fc_rows * n->fc_np * 4)) != AP_OK)
+    return bad(rc);
   if ((rc = fc_tc_configure(e, n)) != AP_OK) return bad(rc);
   if (n->head_mode == 2 && !conv_tc_head_supported(n->trunk.back())) n->head_mode = 1;
   if (n->split && n->head_mode != 2)

@@ -82,6 +82,8 @@ struct NetState {
   __half* fc_a = nullptr;    // [2 (hi,lo)][fc_kp/8][fc_rows][8]  head-conv outputs, k = o*S + pixel
   __half* fc_w = nullptr;    // [2][fc_kp/8][fc_np][8]
   float* fc_bias = nullptr;  // [fc_np]
+  float* fc_partial = nullptr;  // [fc_ksplit][fc_rows][fc_np] raw partial logits of the split-K FC
+  int fc_ksplit = 4;
   long long fc_rows = 0;     // bcap rounded up to 128
   int fc_kp = 0, fc_np = 0;  // 6S rounded up to the K stage; S+1 rounded up to 16
   int head_mode = 2;         // 0 = fp32 CUDA-core FC (legacy), 1 = k_head_conv + tensor-core FC, 2 = head convs fused into
