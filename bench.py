@@ -218,7 +218,7 @@ def ncu_conv_traffic(G):
     list of this workload (profiles/, `ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum` on
     tools/profile_step.py --games 4096).  None when the list is missing or the batch differs."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_launches_v5_final.csv")
+    path = os.path.join(ROOT, "profiles", "r1_launches_v6_final.csv")
     if G != 4096 or not os.path.exists(path):
         return None, None
     per = {}
@@ -403,6 +403,21 @@ def cpu_pure_baseline(n_playout=60):
                       % (n_playout, dt)}
 
 
+def ncu_pure_launch(G):
+    """dram bytes (read + write) and issue-slot utilisation of one k_pure_run launch at the bench size, from the
+    committed ncu launch list (profiles/, tools/profile_step.py --pure 0 --games 8192 --playouts 1000)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_pure_launches_v2.csv")
+    if G != PURE_GAMES or not os.path.exists(path):
+        return None, None, None
+    with open(path) as f:
+        rows = [r for r in csv.reader(f) if len(r) > 5]
+    h = {k: i for i, k in enumerate(rows[0])}
+    m = {r[h["Metric Name"]]: float(r[h["Metric Value"]].replace(",", "")) for r in rows[1:]}
+    return (m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0),
+            m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"), os.path.relpath(path, ROOT))
+
+
 def run_gpu_pure(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -465,6 +480,7 @@ def run_gpu_pure(args):
         tree_bytes = 20 * stats["children_scanned"] + 20 * stats["children_written"] + 24 * stats["path_nodes"] + \
             64 * stats["playouts"]
         ach = tree_bytes / (dev_ms / 1000.0) / 1e9
+        traffic, issue_pct, traffic_src = ncu_pure_launch(G)
         out = {"metric": "mcts_pure_playouts_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64 tree / u32 bitboards", "data": "synthetic",
@@ -484,9 +500,12 @@ def run_gpu_pure(args):
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "kernel": "k_pure_run (one launch = one move search for every game)",
                             "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src,
-                            "traffic": None, "avg_launch_ms": dev_ms / args.steps,
+                            "traffic": traffic, "traffic_source": traffic_src,
+                            "issue_active_pct_ncu": issue_pct, "avg_launch_ms": dev_ms / args.steps,
+                            "algorithmic_bytes_per_launch": tree_bytes / args.steps,
                             "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
-                            "note": "latency/issue bound (register-resident rollouts + dependent node loads), not bandwidth bound"}}
+                            "note": "issue bound (68 % issue-active under ncu): register-resident rollouts and warp-level select; "
+                                    "children blocks are re-read from L2, so DRAM traffic is below the algorithmic bytes"}}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_pure_baseline()
         print(json.dumps(out))

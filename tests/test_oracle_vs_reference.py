@@ -74,6 +74,48 @@ def test_pure_player_live():
     assert ma == mb
 
 
+def test_rollout_restatements_live(monkeypatch):
+    """oracle/rollout.py against the reference's own MCTS._evaluate_rollout (mcts_pure.py:138-157): the reference's
+    np.random.rand(A) draws are replaced by the uniforms of a given move order (so its arg-max plays exactly that
+    order); value and game length must equal rollout_by_play / rollout_by_descent / rollout_sample_numpy for the
+    same order."""
+    from oracle.rollout import rollout_by_descent, rollout_by_play, rollout_sample_numpy
+    ref = refimport.load()
+    rs = np.random.RandomState(9)
+    for W, H, n, pre in ((15, 15, 5, 0), (15, 15, 5, 40), (8, 8, 5, 6), (6, 6, 4, 0)):
+        for trial in range(12):
+            while True:
+                a = ref.Board(width=W, height=H, n_in_row=n)
+                b = OBoard(W, H, n)
+                a.init_board()
+                b.init_board()
+                for _ in range(pre):
+                    m = int(a.availables[rs.randint(len(a.availables))])
+                    a.do_move(m)
+                    b.do_move(m)
+                    if a.game_end()[0]:
+                        break
+                if not a.game_end()[0]:
+                    break
+            keys = rs.random_sample(len(b.availables))         # one uniform per empty cell
+            order = np.array(b.availables)[np.argsort(keys)]    # ascending keys = the order the cells are played in
+            key_of = {int(m): 1.0 - float(k) for m, k in zip(b.availables, keys)}  # arg-max picks the smallest key left
+            monkeypatch.setattr(ref.mcts_pure.np.random, "rand", lambda A, s=a: np.array([key_of[m] for m in s.availables]))
+            stones0 = len(a.states)
+            value = ref.mcts_pure.MCTS(ref.mcts_pure.policy_value_fn)._evaluate_rollout(a)
+            plies = len(a.states) - stones0
+            assert rollout_by_play(b, order) == (value, plies)
+            assert rollout_by_descent(b, order) == (value, plies)
+
+            class Fixed(object):
+                def random_sample(self, shape, k=keys):
+                    return np.asarray(k)[None, :]
+
+            v, p = rollout_sample_numpy(b, 1, Fixed())
+            assert (int(v[0]), int(p[0])) == (value, plies)
+    monkeypatch.undo()
+
+
 def test_self_play_live():
     from oracle import selfplay as osp
     ref = refimport.load()
