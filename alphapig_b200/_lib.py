@@ -14,6 +14,7 @@ AP_ERR_CUDA, AP_ERR_NO_NET, AP_ERR_BAD_HANDLE = -4, -5, -6
 AP_META_INTS = 8
 AP_ARCH_SIMPLE, AP_ARCH_RESNET, AP_ARCH_INCEPTION = 0, 1, 2
 AP_NET_SPLIT = 0x100  # OR into arch: hi + lo fp16 operand pairs (near-fp32), residual net only
+AP_NET_SPLIT_ACT = 0x200  # OR into arch: hi + lo activations x error-diffusion-rounded fp16 weights, residual net only
 
 
 class EngineError(RuntimeError):

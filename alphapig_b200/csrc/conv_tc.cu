@@ -299,10 +299,14 @@ struct EpiCfg {
 };
 
 // TAPS = 9: 3x3 conv; TAPS = 1: 1x1 conv (only the centre tap of the same slab)
-template <int COUT, int KC, bool RESID, bool HEAD, bool SPLIT = false, int TAPS = 9>
+// SPLITM: 0 = fp16 operands; 1 = hi + lo pairs for activations AND weights (three products per K step);
+//         2 = hi + lo activations x fp16 weights rounded by error diffusion along K (two products, net.cu)
+template <int COUT, int KC, bool RESID, bool HEAD, int SPLITM = 0, int TAPS = 9>
 __global__ void __launch_bounds__(EpiCfg<HEAD>::THREADS, 1)
 k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadArg<HEAD> hw) {
   using Cfg = ConvCfg<COUT>;
+  constexpr bool SPLIT = SPLITM != 0;    // activations travel as hi + lo
+  constexpr bool SPLITW = SPLITM == 1;   // weights too
   constexpr int EPI = EpiCfg<HEAD>::WARPS;
   constexpr int NTHR = EpiCfg<HEAD>::THREADS;
   constexpr int TPS = TAPS == 1 ? 1 : Cfg::TPS;
@@ -314,7 +318,7 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
   constexpr uint32_t SLAB_STRIDE = (SLAB_BYTES + 127u) & ~127u;
   constexpr uint32_t TAP_BYTES = (uint32_t)KC * COUT * 2;
   constexpr uint32_t STAGE_HALF = TPS * TAP_BYTES;
-  constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * STAGE_HALF;       // SPLIT: [hi taps][lo taps]
+  constexpr uint32_t STAGE_BYTES = (SPLITW ? 2 : 1) * STAGE_HALF;      // SPLITW: [hi taps][lo taps]
 
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(AP_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -401,7 +405,7 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
             mbar_expect_tx(bb, STAGE_BYTES);
             bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES),
                      p.wimg + (size_t)(kc * TAPS + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
-            if constexpr (SPLIT)
+            if constexpr (SPLITW)
               bulk_g2s(smem_u32(bstage0 + (size_t)bs * STAGE_BYTES + STAGE_HALF),
                        p.wimg_lo + (size_t)(kc * TAPS + ts * TPS) * ((size_t)KC * COUT), STAGE_HALF, bb);
           }
@@ -455,10 +459,10 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
                   const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(off + half * 128 + 2 * j * (int)A_LBO));
                   const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(t * (int)(TAP_BYTES >> 4) + 2 * j * (int)B_LBO));
                   tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad, bd, IDESC, (kc | tap | j) != 0);
-                  if constexpr (SPLIT) {  // + a_lo * b_hi + a_hi * b_lo (lo * lo is below fp32 round-off)
+                  if constexpr (SPLIT)   // + a_lo * b_hi
                     tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad + (SLAB_HALF >> 4), bd, IDESC, 1);
+                  if constexpr (SPLITW)  // + a_hi * b_lo (lo * lo is below fp32 round-off)
                     tc_mma_f16(acc_base + (uint32_t)(half * COUT), ad, bd + (STAGE_HALF >> 4), IDESC, 1);
-                  }
                 }
               }
             }
@@ -1152,11 +1156,11 @@ struct SmemPlan {
 constexpr int head_smem_bytes(int) { return 2 * 128 * 6 * 4; }
 
 // slabs + B ring + barriers + TMEM slot + bias inside the 227 KB opt-in limit
-SmemPlan plan_smem(int cout, int kc, int nkc, bool head, bool split = false, int taps = 9) {
+SmemPlan plan_smem(int cout, int kc, int nkc, bool head, int split = 0, int taps = 9) {
   const int tps = (cout == 256 || taps == 1) ? 1 : 3;
-  const int mul = split ? 2 : 1;
+  const int mul = split ? 2 : 1, mulw = split == 1 ? 2 : 1;  // split 2: hi + lo activations, fp16 weights
   const int slab = ((mul * (kc >> 3) * kSlabGroupBytes) + 127) & ~127;
-  const int stage = mul * tps * kc * cout * 2;
+  const int stage = mulw * tps * kc * cout * 2;
   const int fixed = (2 * kMaxSlabs + 2 * kMaxStages + 4) * 8 + 16 + cout * 4 + 128 + (head ? head_smem_bytes(cout) : 0);
   const int budget = 227 * 1024 - fixed;
   const int all = nkc * (taps / tps);  // stages that hold the whole layer
@@ -1252,21 +1256,38 @@ cudaError_t optin_t() {
 }
 
 // SPLIT instantiations (residual net at near-fp32 accuracy): stem, convA, convB (+residual), last convB with heads
-cudaError_t optin_split() {
+template <int M>
+cudaError_t optin_split_m() {
   const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
   const int lim = 227 * 1024;
-  cudaError_t r = cudaFuncSetAttribute(k_conv3x3_tc<128, 16, false, false, true>, a, lim);
-  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, false, false, true>, a, lim);
-  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, true, false, true>, a, lim);
-  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, true, true, true>, a, lim);
+  cudaError_t r = cudaFuncSetAttribute(k_conv3x3_tc<128, 16, false, false, M>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, false, false, M>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, true, false, M>, a, lim);
+  if (r == cudaSuccess) r = cudaFuncSetAttribute(k_conv3x3_tc<128, 32, true, true, M>, a, lim);
   return r;
 }
+cudaError_t optin_split() {
+  cudaError_t r = optin_split_m<1>();
+  return r == cudaSuccess ? optin_split_m<2>() : r;
+}
 
-template <int COUT, int KC, bool RESID, bool HEAD>
+template <int COUT, int KC, bool RESID, bool HEAD, int M>
 int launch1s(ap_engine* e, const ConvParams& p, const HeadArg<HEAD>& hw, int grid, int smem) {
-  k_conv3x3_tc<COUT, KC, RESID, HEAD, true><<<grid, EpiCfg<HEAD>::THREADS, smem, e->stream>>>(p, hw);
+  k_conv3x3_tc<COUT, KC, RESID, HEAD, M><<<grid, EpiCfg<HEAD>::THREADS, smem, e->stream>>>(p, hw);
   AP_LAUNCH_CHECK(e);
   return AP_OK;
+}
+template <int M>
+int launch_split(ap_engine* e, const ConvParams& p, const NetHeadW* head_w, bool resid, int kc, int grid, int smem) {
+  const HeadArg<false> none{};
+  if (head_w) {
+    HeadArg<true> hw;
+    hw.h = *head_w;
+    return launch1s<128, 32, true, true, M>(e, p, hw, grid, smem);
+  }
+  if (kc == 16) return launch1s<128, 16, false, false, M>(e, p, none, grid, smem);
+  return resid ? launch1s<128, 32, true, false, M>(e, p, none, grid, smem)
+               : launch1s<128, 32, false, false, M>(e, p, none, grid, smem);
 }
 
 // 1x1 instantiations (Inception-ResNet variant: tower stems and the up-projection, 128 -> 128)
@@ -1306,7 +1327,7 @@ bool conv_tc_supported(int cin_pad, int cout) {
 
 // can this layer run the fused head epilogue?
 // K chunk of a layer: the split-precision kernels stage hi + lo of both operands, so they use half the chunk
-int conv_tc_kc(const ConvLayer& L, bool split) { return L.cin_pad < 64 ? L.cin_pad : (split ? 32 : 64); }
+int conv_tc_kc(const ConvLayer& L, int split) { return L.cin_pad < 64 ? L.cin_pad : (split ? 32 : 64); }
 
 bool conv_tc_split_supported(const ConvLayer& L) { return L.cout == 128 && (L.cin_pad == 16 || L.cin_pad % 32 == 0); }
 
@@ -1336,7 +1357,7 @@ int conv_tc_configure(ap_engine* e) {
 }
 
 int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, const int* n_boards_dev, bool head) {
-  const bool split = n->split;
+  const int split = n->split;  // 0 fp16, 1 split both operands, 2 split activations only
   ConvParams p;
   p.in = (L.in_buf < 0) ? n->feat : n->act[L.in_buf];
   p.out = n->act[L.out_buf];
@@ -1379,20 +1400,14 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   if (split) {
     // near-fp32 path of the residual net: single-CTA kernel, three products per K step
     if (!conv_tc_split_supported(L)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: no split-precision instantiation for this layer");
-    const SmemPlan s = plan_smem(L.cout, kc, p.nkc, head, true);
+    const SmemPlan s = plan_smem(L.cout, kc, p.nkc, head, split);
     p.ns = s.ns;
     p.nb = s.nb;
     const int grid = n_boards < n->sm_count ? n_boards : n->sm_count;
-    const HeadArg<false> none{};
-    if (head) {
-      if (!resid || kc != 32) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: split fused head needs a residual 128-channel layer");
-      HeadArg<true> hw;
-      hw.h = n->head_w;
-      return launch1s<128, 32, true, true>(e, p, hw, grid, s.bytes);
-    }
-    if (kc == 16) return launch1s<128, 16, false, false>(e, p, none, grid, s.bytes);
-    return resid ? launch1s<128, 32, true, false>(e, p, none, grid, s.bytes)
-                 : launch1s<128, 32, false, false>(e, p, none, grid, s.bytes);
+    if (head && (!resid || kc != 32))
+      return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: split fused head needs a residual 128-channel layer");
+    return split == 1 ? launch_split<1>(e, p, head ? &n->head_w : nullptr, resid, kc, grid, s.bytes)
+                      : launch_split<2>(e, p, head ? &n->head_w : nullptr, resid, kc, grid, s.bytes);
   }
   // 256-channel layers without a fused head: two boards per CTA pair, 128-column tiles (AP_CONV4=0 disables)
   if (n->conv4_128 && !L.force_single && L.cout == 128 && kc == 64 && n->conv_mode == 0 && !head && (n->conv4_128 > 1 || L.cin_pad == 64)) {

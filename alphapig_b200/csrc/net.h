@@ -111,7 +111,7 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
                    bool head = false);
 bool conv_tc_head_supported(const ConvLayer& L);
 bool conv_tc_split_supported(const ConvLayer& L);
-int conv_tc_kc(const ConvLayer& L, bool split);
+int conv_tc_kc(const ConvLayer& L, int split);
 bool conv_tc_supported(int cin_pad, int cout);
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb);
 int conv_tc_configure(ap_engine* e);

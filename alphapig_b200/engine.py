@@ -254,13 +254,15 @@ class Engine(object):
         (arg and aux params merged; policy_value_net_mxnet.py:125-138).
 
         precision: "fp16" = fp16 tensor-core operands (fp32 accumulate); "split" = hi + lo fp16 pairs for
-        activations and weights, three products per K step (residual net only, near-fp32); "auto" = split for
-        a residual net deeper than 3 blocks (plain fp16 measures 8.9e-4 at 3 blocks and 1.8e-3 at 10, against
-        the 1e-3 parity budget), fp16 otherwise."""
-        if precision not in ("auto", "fp16", "split"):
-            raise ValueError("precision must be 'auto', 'fp16' or 'split'")
-        split = precision == "split" or (precision == "auto" and arch == "resnet" and int(n_blocks) > 3)
-        self.net_precision = "split" if split else "fp16"
+        activations and weights, three products per K step (residual net only, near-fp32); "split_act" = hi + lo
+        activations x fp16 weights rounded by error diffusion along K, two products per K step (residual net
+        only); "auto" = split_act for a residual net deeper than 3 blocks (plain fp16 measures 8.9e-4 at 3 blocks
+        and 1.8e-3 at 10, against the 1e-3 parity budget; split_act 4.7e-4 at 10), fp16 otherwise."""
+        if precision not in ("auto", "fp16", "split", "split_act"):
+            raise ValueError("precision must be 'auto', 'fp16', 'split' or 'split_act'")
+        if precision == "auto":
+            precision = "split_act" if (arch == "resnet" and int(n_blocks) > 3) else "fp16"
+        self.net_precision = precision
         names = list(params.keys())
         keep = [np.ascontiguousarray(params[k], dtype=np.float32) for k in names]
         arr = (L.ApTensor * len(names))()
@@ -269,8 +271,7 @@ class Engine(object):
             arr[i].data = a.ctypes.data
             arr[i].numel = a.size
         code = {"simple": L.AP_ARCH_SIMPLE, "resnet": L.AP_ARCH_RESNET, "inception": L.AP_ARCH_INCEPTION}[arch]
-        if split:
-            code |= L.AP_NET_SPLIT
+        code |= {"fp16": 0, "split": L.AP_NET_SPLIT, "split_act": L.AP_NET_SPLIT_ACT}[precision]
         self._check(self.lib.ap_net_load(self.h, code, int(n_blocks), int(n_filter), arr, len(names)))
         self.net_names = names
 

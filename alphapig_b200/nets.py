@@ -43,7 +43,7 @@ class PolicyValueNetBase(object):
         self._n_blocks = n_blocks
         self._n_filter = n_filter
         self._device = device
-        self._precision = precision  # see Engine.net_load: "auto" | "fp16" | "split"
+        self._precision = precision  # see Engine.net_load: "auto" | "fp16" | "split" | "split_act"
         if model_params:
             arg, aux = model_params
             arg = OrderedDict((k, _to_numpy(v)) for k, v in arg.items())

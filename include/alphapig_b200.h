@@ -150,6 +150,10 @@ typedef struct {
  * tensor cores compute hi*hi + lo*hi + hi*lo (near-fp32 accuracy at 3x the MMA work).  The 10-block net of
  * train_mxnet.py:79-91 needs it to stay within 1e-3 of fp32; plain fp16 operands reach 1.8e-3 there. */
 #define AP_NET_SPLIT 0x100
+/* OR into `arch` instead of AP_NET_SPLIT (residual net only): activations as hi + lo fp16 pairs, weights as ONE fp16
+ * value rounded by error diffusion along K (the rounding errors of an output channel sum to < 1 ulp): hi*w + lo*w,
+ * 2x the MMA work; 4.7e-4 on the 10-block net.  The default of the Python shims for deep residual nets. */
+#define AP_NET_SPLIT_ACT 0x200
 /* set_params(arg_params, aux_params)                 policy_value_net_mxnet_simple.py:33-37 */
 int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t n_filter, const ap_tensor* tensors, int32_t n_tensors);
 /* PolicyValueNet.policy_value(state_batch): host fp32 states [B][9][H][W] -> probs [B][S], values [B]   (:178-188) */

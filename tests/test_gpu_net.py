@@ -75,17 +75,19 @@ def test_net_head_modes(monkeypatch, mode, W, arch, nblk, nst):
     eng.close()
 
 
-@pytest.mark.parametrize("nblk,precision,tol", [(10, "split", 5e-5), (10, "auto", 5e-5), (3, "split", 5e-5), (10, "fp16", 4e-3)])
+@pytest.mark.parametrize("nblk,precision,tol", [(10, "split", 5e-5), (10, "split_act", 8e-4), (10, "auto", 8e-4),
+                                                (3, "split", 5e-5), (3, "split_act", 8e-4), (10, "fp16", 4e-3)])
 def test_resnet_split_precision(nblk, precision, tol):
     """The as-trained residual net (10 blocks x 128, train_mxnet.py:79-91): plain fp16 operands drift to ~1.8e-3,
-    the split-precision kernels (hi + lo fp16 pairs, three tensor-core products) stay at fp32 round-off."""
+    the split-precision kernels (hi + lo fp16 pairs, three tensor-core products) stay at fp32 round-off, and
+    hi + lo activations x error-diffusion-rounded fp16 weights (two products, the "auto" choice) stay under 8e-4."""
     W = 15
     arg, aux = onet.init_params("resnet", W, W, seed=0, n_blocks=nblk)
     boards, st = _states(W, 150, 1234, 31)
     ref_p, ref_v = onet.forward(arg, aux, st, "resnet", n_blocks=nblk)
     eng = _engine(width=W, height=W, n_in_row=5, n_games=4)
     eng.net_load("resnet", _merged(arg, aux), n_blocks=nblk, precision=precision)
-    assert eng.net_precision == ("fp16" if precision == "fp16" else "split")
+    assert eng.net_precision == {"auto": "split_act"}.get(precision, precision)
     p, v = eng.net_forward(st)
     dlp = np.abs(np.log(p) - np.log(ref_p)).max()
     dv = np.abs(v - ref_v).max()
