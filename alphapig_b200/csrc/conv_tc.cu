@@ -46,6 +46,7 @@ struct ConvParams {
   const __half* wimg_lo;
   const float* bias;  // folded BN shift; the BN scale is folded into the fp16 weights
   long long mpad;
+  int in_goff;      // first 8-channel group of the input planes this layer reads (single-CTA kernel only)
   int out_coff;     // the COUT output channels land at channels [out_coff, out_coff + cout_store) of the output planes
   int cout_store;   // channels actually stored (a multiple of 8; the rest are zero-weight padding)
   int nkc, relu;
@@ -384,12 +385,12 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
 #pragma unroll
           for (int j = 0; j < KG; ++j)
             bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + j * kSlabGroupBytes),
-                     p.in + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+                     p.in + ((long long)(p.in_goff + kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
           if constexpr (SPLIT) {
 #pragma unroll
             for (int j = 0; j < KG; ++j)
               bulk_g2s(smem_u32(slab0 + sl * SLAB_STRIDE + SLAB_HALF + j * kSlabGroupBytes),
-                       p.in_lo + ((long long)(kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
+                       p.in_lo + ((long long)(p.in_goff + kc * KG + j) * p.mpad + row0) * 8, kSlabGroupBytes, fb);
           }
         }
         __syncwarp();
@@ -1314,20 +1315,26 @@ cudaError_t optin_head() {
 }  // namespace
 
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb) {
-  const int kc = L.cin_pad < 64 ? L.cin_pad : 64;
+  const int kc = conv_tc_kc(L, 0);
   SmemPlan s = plan_smem(L.cout, kc, L.cin_pad / kc, false);
   if (out_nb) *out_nb = s.nb;
   return s.bytes;
 }
 
+// K chunk: 64 channels where the layer has them, else 32 (narrow tower layers of the inception variant, 64 outputs
+// only) or 16
+static int kc_of(int cin_pad) { return cin_pad % 64 == 0 ? 64 : (cin_pad % 32 == 0 ? 32 : 16); }
 bool conv_tc_supported(int cin_pad, int cout) {
-  const int kc = cin_pad < 64 ? cin_pad : 64;
-  return (cout == 64 || cout == 128 || cout == 256) && (kc == 16 || kc == 64) && cin_pad % kc == 0;
+  const int kc = kc_of(cin_pad);
+  return (cout == 64 || cout == 128 || cout == 256) && cin_pad % kc == 0 && (kc != 32 || cout == 64);
 }
 
 // can this layer run the fused head epilogue?
 // K chunk of a layer: the split-precision kernels stage hi + lo of both operands, so they use half the chunk
-int conv_tc_kc(const ConvLayer& L, int split) { return L.cin_pad < 64 ? L.cin_pad : (split ? 32 : 64); }
+int conv_tc_kc(const ConvLayer& L, int split) {
+  const int kc = kc_of(L.cin_pad);
+  return (split && kc == 64) ? 32 : kc;
+}
 
 bool conv_tc_split_supported(const ConvLayer& L) { return L.cout == 128 && (L.cin_pad == 16 || L.cin_pad % 32 == 0); }
 
@@ -1348,6 +1355,7 @@ int conv_tc_configure(ap_engine* e) {
   AP_CUDA(e, optin_split());
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc<128, 64, false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc<128, 64, true, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+  AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc<64, 32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   AP_CUDA(e, (cudaFuncSetAttribute(k_conv3x3_tc4<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
@@ -1369,6 +1377,7 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   p.wimg_lo = L.wimg_lo;
   p.bias = L.shift;
   p.mpad = n->mpad;
+  p.in_goff = L.in_coff / 8;
   p.out_coff = L.out_coff;
   p.cout_store = L.cout_store > 0 ? L.cout_store : L.cout;
   const int kc = conv_tc_kc(L, split);
@@ -1388,6 +1397,8 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   if (!conv_tc_supported(L.cin_pad, L.cout)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: unsupported channel counts");
   if (head && !conv_tc_head_supported(L)) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: no fused-head instantiation for this layer");
   const bool resid = p.resid != nullptr;
+  if (L.in_coff && (!L.force_single || (L.in_coff & 7)))
+    return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: input channel slices need the single-CTA kernel and a multiple of 8");
   if (L.ksz == 1) {
     // 1x1 conv: single-CTA kernel, centre tap only
     if (split || head || L.cout != 128 || kc != 64) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: 1x1 convs are built for 128 output channels");
@@ -1459,6 +1470,11 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
     if (L.cout == 256)
       return pair ? launch2<256, 64, false, true>(e, p, hw, grid, s.bytes) : launch1<256, 64, false, true>(e, p, hw, grid, s.bytes);
     return pair ? launch2<128, 64, true, true>(e, p, hw, grid, s.bytes) : launch1<128, 64, true, true>(e, p, hw, grid, s.bytes);
+  }
+  if (kc == 32) {  // narrow tower layers (inception variant): single-CTA kernel, 64 output columns
+    const HeadArg<false> none{};
+    if (pair || resid || L.cout != 64) return ap_fail(e, AP_ERR_BAD_ARG, "conv_tc: K chunk 32 is built for plain 64-output layers");
+    return launch1<64, 32, false, false>(e, p, none, grid, s.bytes);
   }
   switch (L.cout * 100 + kc) {
     case 64 * 100 + 16: return launch_t<64, 16>(e, p, resid, pair, grid, s.bytes);

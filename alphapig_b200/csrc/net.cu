@@ -639,8 +639,9 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
     auto valloc = [&](long long cnt) { long long o = vtot; vtot += (cnt + 3) & ~3ll; return o; };
     struct Piece { const char* name; int cout, cin, oo, io; };
     auto vlayer = [&](int blk, int cin_v, int cout_v, int ksz, std::vector<Piece> pieces, int in_buf, int out_buf,
-                      int out_coff, int cout_store, int resid_buf, int relu, float post) -> int {
+                      int out_coff, int cout_store, int resid_buf, int relu, float post, int in_coff = 0) -> int {
       ConvLayer V{};
+      V.in_coff = in_coff;
       V.cin = cin_v; V.cout = cout_v; V.ksz = ksz; V.relu = relu; V.in_buf = in_buf; V.out_buf = out_buf;
       V.resid_buf = resid_buf; V.out_coff = out_coff; V.cout_store = cout_store; V.force_single = 1; V.virt = 1;
       V.fix_gamma = 1; V.post_scale = post;
@@ -672,10 +673,11 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
     int x = 0;  // buffers: 0 / 1 = block input / output (ping-pong), 2 = T0, 3 = T1
     for (int i = 1; i <= n_blocks; ++i) {
       const int y = 1 - x;
-      if ((rc = vlayer(i, 128, 128, 1, {{"t0", 32, 128, 0, 0}, {"t1a", 32, 128, 32, 0}, {"t2a", 32, 128, 64, 0}}, x, 2, 0, 128, -1, 1, 1.f)) != AP_OK) return bad(rc);
-      if ((rc = vlayer(i, 128, 64, 3, {{"t1b", 32, 32, 0, 32}}, 2, 2, 32, 32, -1, 1, 1.f)) != AP_OK) return bad(rc);
-      if ((rc = vlayer(i, 128, 64, 3, {{"t2b", 48, 32, 0, 64}}, 2, 3, 0, 64, -1, 1, 1.f)) != AP_OK) return bad(rc);
-      if ((rc = vlayer(i, 64, 64, 3, {{"t2c", 64, 48, 0, 0}}, 3, 2, 64, 64, -1, 1, 1.f)) != AP_OK) return bad(rc);
+      if ((rc = vlayer(i, 128, 128, 1, {{"t0", 32, 128, 0, 0}, {"t1a", 32, 128, 32, 0}, {"t2a", 32, 128, 64, 0}}, x, 2, 0, 96, -1, 1, 1.f)) != AP_OK) return bad(rc);
+      // tower layers read only their own channel slice (in_coff) - K = 9 * 32 / 9 * 48 instead of 9 * 128
+      if ((rc = vlayer(i, 32, 64, 3, {{"t1b", 32, 32, 0, 0}}, 2, 2, 32, 32, -1, 1, 1.f, 32)) != AP_OK) return bad(rc);
+      if ((rc = vlayer(i, 32, 64, 3, {{"t2b", 48, 32, 0, 0}}, 2, 3, 0, 48, -1, 1, 1.f, 64)) != AP_OK) return bad(rc);
+      if ((rc = vlayer(i, 48, 64, 3, {{"t2c", 64, 48, 0, 0}}, 3, 2, 64, 64, -1, 1, 1.f)) != AP_OK) return bad(rc);
       if ((rc = vlayer(i, 128, 128, 1, {{"up", 128, 128, 0, 0}}, 2, y, 0, 128, x, 1, 0.17f)) != AP_OK) return bad(rc);
       x = y;
     }

@@ -18,6 +18,7 @@ struct ConvLayer {
   // Inception-ResNet variant: 1x1 convs, channel-slice outputs and composite (block-assembled) weight tensors
   int ksz = 3;            // 3 or 1
   int out_coff = 0;       // output channel offset inside the output planes
+  int in_coff = 0;        // input channel offset inside the input planes (multiple of 8): a tower reads its slice only
   int cout_store = 0;     // channels stored (0 = cout)
   int force_single = 0;   // always the single-CTA kernel (the slice stores / 1x1 taps live there)
   int virt = 0;           // parameter offsets index NetState::vmaster (assembled by k_build_virtual) instead of master
