@@ -30,9 +30,16 @@ METRIC = "mcts_playouts_per_s"
 UNIT = "playouts/s"
 
 
-def workload_name(G):
-    return ("15x15 five-in-a-row batched MCTS move search, policy_value_net_mxnet_simple (6-conv net), "
-            "%d concurrent games per GPU, n_playout=%d, c_puct=%d" % (G, N_PLAYOUT, C_PUCT))
+NETS = {  # --net: BASELINE configs[1] (default), the residual net train_mxnet.py:79-91 trains, configs[3]
+    "simple": ("policy_value_net_mxnet_simple", "policy_value_net_mxnet_simple (6-conv net)", 0),
+    "resnet": ("policy_value_net_mxnet", "policy_value_net_mxnet (residual net, 10 blocks x 128, as trained by the reference)", 10),
+    "inception": ("policy_value_net_inception", "builder-defined Inception-ResNet variant (3x3 stem + 10 x block35, BASELINE configs[3])", 10),
+}
+
+
+def workload_name(G, net="simple"):
+    return ("15x15 five-in-a-row batched MCTS move search, %s, "
+            "%d concurrent games per GPU, n_playout=%d, c_puct=%d" % (NETS[net][1], G, N_PLAYOUT, C_PUCT))
 
 
 # ------------------------------------------------------------------------------------------
@@ -245,13 +252,17 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    import importlib
     from alphapig_b200.params import flop_per_leaf, init_params
-    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
     from alphapig_b200 import dist as apdist
 
     G = args.games
-    arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
-    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=local)
+    arch = args.net
+    n_blocks = NETS[arch][2]
+    PolicyValueNet = importlib.import_module("alphapig_b200." + NETS[arch][0]).PolicyValueNet
+    arg, aux = init_params(arch, W, H, n_blocks=n_blocks, seed=0, synthetic_stats=True)
+    kw = {} if arch == "simple" else {"n_blocks": n_blocks}
+    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=local, **kw)
     cap = N_PLAYOUT * W * H + 2
     eng = net.search_engine(n_in_row=N_IN_ROW, c_puct=C_PUCT, n_playout=N_PLAYOUT, n_games=G, node_capacity=cap)
     if world > 1:
@@ -326,15 +337,16 @@ def run_gpu(args):
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         n_conv = len(phase_ms) - 4
         conv_ms = float(phase_ms[2:2 + n_conv].sum())
-        conv_flop_leaf = 2 * sum(9 * ci * co for ci, co in ((9, 64), (64, 64), (64, 128), (128, 128), (128, 256),
-                                                          (256, 256))) * W * H
+        cfin = 256 if arch == "simple" else 128
+        head_flop = 2 * (cfin * 6 * W * H + 4 * (W * H) ** 2 + 2 * W * H)
+        conv_flop_leaf = flop_per_leaf(arch, W, H, n_blocks=n_blocks) - head_flop  # trunk convs only
         lockstep = args.steps * N_PLAYOUT
         conv_launches = lockstep * n_conv
         # terminal leaves never reach the net (compacted out on the device): only evaluated leaves count as work
         evaluated = stats["playouts"] - stats["terminal_leaves"]
         achieved = conv_flop_leaf * evaluated / (conv_ms / 1000.0) / 1e12
-        traffic, traffic_src = ncu_conv_traffic(G)
-        roof = {"bound": "tensor", "kernel": "k_conv3x3_tc (6 launches per lock-step, all trunk layers)",
+        traffic, traffic_src = ncu_conv_traffic(G) if arch == "simple" else (None, None)
+        roof = {"bound": "tensor", "kernel": "k_conv3x3_tc (%d launches per lock-step, all trunk layers)" % n_conv,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": pk_src, "traffic": traffic, "traffic_source": traffic_src,
                 "avg_launch_ms": conv_ms / conv_launches,
@@ -354,14 +366,16 @@ def run_gpu(args):
                                 "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
                                 "terminal_leaf_frac": stats["terminal_leaves"] / max(1, stats["playouts"])}
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and arch == "simple":
             cpu = cpu_baseline_single((arg, aux), n_moves=2)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-               "config": {"workload": workload_name(G), "games_per_gpu": G, "n_playout": N_PLAYOUT,
-                          "net": "policy_value_net_mxnet_simple", "flop_per_leaf": flop_per_leaf(ARCH, W, H),
-                          "arithmetic": "fp16 operands, fp32 TMEM accumulate (net); fp64 (tree)",
+               "config": {"workload": workload_name(G, arch), "games_per_gpu": G, "n_playout": N_PLAYOUT,
+                          "net": NETS[arch][0], "flop_per_leaf": flop_per_leaf(arch, W, H, n_blocks=n_blocks),
+                          "arithmetic": ("fp16 operands, fp32 TMEM accumulate (net); fp64 (tree)" if arch != "resnet" else
+                                         "hi + lo fp16 activations x error-diffusion-rounded fp16 weights, two products per K "
+                                         "step, fp32 TMEM accumulate (net, precision=%s); fp64 (tree)" % eng.net_precision),
                           "l2": "working set (node pools + activation planes, >10 GB) is larger than L2; no flush needed",
                           "timing": "CUDA events on the engine stream around each ap_search_run, summed over steps, max over ranks"},
                "moves_per_s": value / N_PLAYOUT,
@@ -571,6 +585,9 @@ def main():
     ap.add_argument("--groups", type=int, default=2, help="selfplay workload: pipelined game groups (1 = none)")
     ap.add_argument("--rollout-mode", type=int, default=0, choices=[0, 2],
                     help="pure workload: 0 = permutation rollouts (default), 2 = ply-by-ply rollouts (A/B)")
+    ap.add_argument("--net", default="simple", choices=sorted(NETS),
+                    help="az workload: simple = BASELINE configs[1] (default, the headline); resnet = the 10-block net the "
+                         "reference trains; inception = configs[3] (builder-defined variant)")
     ap.add_argument("--workload", default="az", choices=["az", "pure", "selfplay"],
                     help="az = BASELINE configs[1] (default, the headline metric); pure = configs[2] (mcts_pure, 1000 playouts)")
     args = ap.parse_args()
