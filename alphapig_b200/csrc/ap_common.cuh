@@ -133,4 +133,6 @@ int net_emit_features_launch(ap_engine* e, bool compact = false);
 int net_check_err(ap_engine* e);
 int net_phase_count(ap_engine* e);
 bool net_can_compact(ap_engine* e);
+void net_feature_planes(ap_engine* e, __half** feat, long long* mpad);
+void net_fc_finish_args(ap_engine* e, const float** partial, const float** bias, long long* rows, int* np, int* ksplit);
 void prof_mark(ap_engine* e);

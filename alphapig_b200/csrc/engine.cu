@@ -410,7 +410,8 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
     }
     e->prof_cursor = 0;
   }
-  // AP_COMPACT_KERNEL=1: separate order-preserving compaction kernel instead of the ticket inside k_select (A/B)
+  // AP_COMPACT_KERNEL=1: the unfused lock-step (A/B): separate order-preserving compaction kernel, features kernel
+  // and FC finish kernel instead of the ticket + feature emission inside k_select and the softmax inside k_expand_backup
   static const bool compact_kernel = getenv("AP_COMPACT_KERNEL") && atoi(getenv("AP_COMPACT_KERNEL")) != 0;
   AP_CUDA(e, cudaMemsetAsync(e->leaves.n_eval, 0, 4, e->stream));
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
@@ -423,7 +424,8 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
     // only the non-terminal leaves are evaluated (the reference discards the evaluator's answer at a terminal
     // leaf, mcts_alphaZero.py:124-136): the net runs on the compacted batch, expand/backup reads through the slot map
     AP_TRY(net_forward_leaves(e, 0, compact, !compact_kernel));
-    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values, compact ? e->leaves.slot : nullptr);
+    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values, compact ? e->leaves.slot : nullptr,
+                         compact && !compact_kernel);
     AP_LAUNCH_CHECK(e);
     prof_mark(e);
   }

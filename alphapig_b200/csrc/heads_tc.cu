@@ -21,6 +21,7 @@
 // the whole 2 MB operand set through one SM's L2 port.  With gridDim.y = 4 each CTA takes a quarter of the K
 // chunks and stores its raw fp32 partial logits ([split][board][np], L2-resident); k_head_fc_finish (one warp
 // per board) adds the partials in fixed order, the bias, and does the softmax / tanh.
+#include "fc_finish.cuh"
 #include "kernels.h"
 #include "net.h"
 #include "ptx.cuh"
@@ -218,40 +219,14 @@ __global__ void __launch_bounds__(128) k_head_fc_finish(FcParams p) {
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int nb = p.nb_dev ? *p.nb_dev : p.nb;
   if (b >= nb) return;
-  const int S = p.S;
-  float l[8];
-  float mx = -INFINITY;
+  const FcFinish f{p.partial, p.bias, p.rows, p.np, p.ksplit};
+  float pr[8];
+  const float v = fc_finish_warp(f, b, p.S, lane, pr);
+  if (lane == 0) p.values[b] = v;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int n = lane + 32 * j;
-    l[j] = 0.f;
-    if (n < p.np) {
-      float a = 0.f;
-      for (int s = 0; s < p.ksplit; ++s) a += p.partial[((size_t)s * p.rows + b) * p.np + n];
-      l[j] = a + p.bias[n];
-      if (n < S) mx = fmaxf(mx, l[j]);
-    }
-  }
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(AP_FULL, mx, d));
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int n = lane + 32 * j;
-    if (n < S) {
-      l[j] = expf(l[j] - mx);
-      sum += l[j];
-    } else if (n == S) {
-      p.values[b] = tanhf(l[j]);
-    }
-  }
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(AP_FULL, sum, d);
-  const float inv = 1.f / sum;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int n = lane + 32 * j;
-    if (n < S) p.probs[(size_t)b * S + n] = l[j] * inv;
+    if (n < p.S) p.probs[(size_t)b * p.S + n] = pr[j];
   }
 }
 
@@ -299,7 +274,8 @@ int fc_tc_prep(ap_engine* e, NetState* n) {
   return AP_OK;
 }
 
-int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_values, const int* nb_dev) {
+// skip_finish: the caller consumes the partial logits itself (k_expand_backup, see fc_finish.cuh / net_fc_finish_args)
+int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_values, const int* nb_dev, bool skip_finish) {
   FcParams p;
   p.a = n->fc_a;
   p.w = n->fc_w;
@@ -317,7 +293,7 @@ int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_val
   p.ksplit = n->fc_ksplit;
   k_head_fc_tc<<<dim3((nb + 127) / 128, p.ksplit), kFcThreads, fc_tc_smem_bytes(n->fc_np), e->stream>>>(p);
   AP_LAUNCH_CHECK(e);
-  if (p.ksplit > 1) {
+  if (p.ksplit > 1 && !skip_finish) {
     k_head_fc_finish<<<(nb + 3) / 4, 128, 0, e->stream>>>(p);
     AP_LAUNCH_CHECK(e);
   }

@@ -20,7 +20,7 @@ void launch_tree_reset_all(ap_engine* e);
 void launch_select(ap_engine* e, bool compact = false);
 void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* d_acts, const double* d_pri64,
                           const double* d_val64, const float* d_pri32, const float* d_val32,
-                          const int32_t* d_slot = nullptr);
+                          const int32_t* d_slot = nullptr, bool fuse_fc_finish = false);
 void launch_compact_leaves(ap_engine* e);
 void launch_advance(ap_engine* e, int n, const int32_t* d_moves);
 void launch_root(ap_engine* e, const int32_t* d_ids, int n, int32_t* d_count, int16_t* d_acts, int32_t* d_visits,

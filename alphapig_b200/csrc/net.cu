@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "board.cuh"
+#include "features.cuh"
 #include "kernels.h"
 #include "net.h"
 #include "ptx.cuh"
@@ -152,10 +153,6 @@ __global__ void k_prep_heads(const float* __restrict__ master, HeadParams h, int
 // ------------------------------------------------------------------------------------------
 // features: leaf bitboards -> fp16 planes [2][mpad][8]  (Board.current_state, game.py:68-94)
 // ------------------------------------------------------------------------------------------
-// One warp per board.  Lane h holds the 8 stone planes of board row h (bitboards with the last i plies dropped);
-// the 16-byte pixel records are then written a tensor row at a time: lanes 0-15 = the 16 pixels of the row in the
-// channel-0..7 plane, lanes 16-31 = the same pixels in the channel-8..15 plane (two contiguous 256-byte runs per
-// store instruction instead of 16 runs of 16 bytes).
 __global__ void k_emit_features(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, int nb,
                                 const int32_t* __restrict__ game_of_slot, const int32_t* __restrict__ nb_dev, __half* feat,
                                 long long mpad) {
@@ -163,27 +160,7 @@ __global__ void k_emit_features(Geo geo, const uint32_t* __restrict__ rows, cons
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // net tile
   if (b >= (nb_dev ? *nb_dev : nb)) return;
   const WBoard wb = wb_load(rows, meta, game_of_slot ? game_of_slot[b] : b, lane);
-  const int W = geo.W, H = geo.H;
-  // planes 2c, 2c+1 packed as (lo16, hi16): pk[3 - d] = (mine, theirs) with the last d plies dropped
-  uint32_t pk[4];
-#pragma unroll
-  for (int d = 0; d < 4; ++d)
-    pk[3 - d] = wb_rows_dropped(wb, wb.cur, d, W, lane) | (wb_rows_dropped(wb, 3 - wb.cur, d, W, lane) << 16);
-  const uint32_t p8 = (wb.nst % 2 == 0) ? 0x3C00u : 0u;  // fp16 1.0 in channel 8
-  const int x = lane & 15, grp = lane >> 4;
-  __half* dst = feat + ((long long)grp * mpad + NET_PAD_ROWS + (long long)b * NET_TILE_ROWS + x) * 8;
-  for (int y = 0; y < H; ++y) {
-    const int src = H - 1 - y;  // axis-1 flip
-    uint4 v;
-    uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t r = __shfl_sync(AP_FULL, pk[c], src) >> x;
-      vv[c] = ((r & 1u) ? 0x3C00u : 0u) | ((r & 0x10000u) ? 0x3C000000u : 0u);
-    }
-    if (grp) v = make_uint4(p8, 0u, 0u, 0u);
-    if (x < W) *reinterpret_cast<uint4*>(dst + (long long)y * 16 * 8) = v;
-  }
+  emit_features_warp(wb, geo.W, geo.H, b, feat, mpad, lane);
 }
 
 // host fp32 states [B][9][H][W] (already on device) -> fp16 planes
@@ -826,10 +803,25 @@ extern "C" int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, 
 // trunk + heads on the first nb boards of the feature planes -> probs/values (device)
 // compacted leaf batches need the fused head path (device-side tile counts in every kernel of the forward)
 bool net_can_compact(ap_engine* e) { return e->net && e->net->head_mode == 2; }
+// partial logits of the split-K FC for a consumer that finishes them itself (partial == nullptr: not available)
+void net_fc_finish_args(ap_engine* e, const float** partial, const float** bias, long long* rows, int* np, int* ksplit) {
+  NetState* n = e->net;
+  const bool on = n && n->head_mode == 2 && n->fc_ksplit > 1;
+  *partial = on ? n->fc_partial : nullptr;
+  *bias = on ? n->fc_bias : nullptr;
+  *rows = on ? n->fc_rows : 0;
+  *np = on ? n->fc_np : 0;
+  *ksplit = on ? n->fc_ksplit : 0;
+}
+void net_feature_planes(ap_engine* e, __half** feat, long long* mpad) {
+  *feat = e->net->feat;
+  *mpad = e->net->mpad;
+}
 int net_phase_count(ap_engine* e) { return e->net ? (int)e->net->trunk.size() + 2 : 0; }
 
 // nb_dev != nullptr: the number of boards is read on the device (compacted leaf batch, at most nb)
-static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values, const int32_t* nb_dev = nullptr) {
+static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values, const int32_t* nb_dev = nullptr,
+                    bool skip_finish = false) {
   NetState* n = e->net;
   const size_t last = n->trunk.size() - 1;
   if (nb_dev && n->head_mode != 2) return ap_fail(e, AP_ERR_BAD_ARG, "compacted batches need the fused head path");
@@ -851,7 +843,7 @@ static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values, const
     AP_LAUNCH_CHECK(e);
     return AP_OK;
   }
-  return fc_tc_launch(e, n, nb, d_probs, d_values, nb_dev);
+  return fc_tc_launch(e, n, nb, d_probs, d_values, nb_dev, skip_finish);
 }
 
 // fp32 path on dense NCHW states (device) for nb <= bcap_ref boards
@@ -916,9 +908,12 @@ int net_forward_leaves(ap_engine* e, int precise, bool compact, bool compacted_b
       launch_compact_leaves(e);
       AP_LAUNCH_CHECK(e);
     }
-    AP_TRY(net_emit_features_launch(e, compact));
+    // compacted_by_select: k_select also wrote the feature planes of its leaves (the board was still in registers)
+    if (!(compact && compacted_by_select)) AP_TRY(net_emit_features_launch(e, compact));
     prof_mark(e);
-    AP_TRY(run_fast(e, G, e->d_probs, e->d_values, compact ? e->leaves.n_eval : nullptr));
+    // compacted_by_select = the fused lock-step of ap_search_run: k_expand_backup finishes the split-K FC itself
+    AP_TRY(run_fast(e, G, e->d_probs, e->d_values, compact ? e->leaves.n_eval : nullptr,
+                    compact && compacted_by_select && n->fc_ksplit > 1));
     prof_mark(e);
     return AP_OK;
   }

@@ -120,4 +120,5 @@ int conv_tc_configure(ap_engine* e);
 void fc_tc_dims(int S, int* kp, int* np);
 int fc_tc_configure(ap_engine* e, NetState* n);
 int fc_tc_prep(ap_engine* e, NetState* n);
-int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_values, const int* nb_dev = nullptr);
+int fc_tc_launch(ap_engine* e, NetState* n, int nb, float* d_probs, float* d_values, const int* nb_dev = nullptr,
+                 bool skip_finish = false);

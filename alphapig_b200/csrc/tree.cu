@@ -1,5 +1,7 @@
 // Lock-step MCTS kernels for G concurrent games (one warp per game; re-root: one CTA per game).
 // Replaces reference MCTS._playout / get_move_probs / update_with_move (mcts_alphaZero.py:108-167).
+#include "fc_finish.cuh"
+#include "features.cuh"
 #include "kernels.h"
 #include "tree.cuh"
 
@@ -21,7 +23,7 @@ __global__ void k_tree_reset_all(Geo geo, Pools pl) {
 #endif
 __global__ void __launch_bounds__(32 * SEL_WARPS, AP_SEL_MINBLK)
 k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, Leaves lv,
-         unsigned long long* stats, int compact) {
+         unsigned long long* stats, int compact, __half* feat, long long mpad) {
   int lane = threadIdx.x & 31;
   int g = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
   if (g >= geo.G) return;
@@ -52,18 +54,23 @@ k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict
     lv.terminal[g] = end ? 1 : 0;
     lv.winner[g] = (int8_t)winner;
     lv.depth[g] = depth;
-    if (compact) {
-      int sl = -1;
+    atomicAdd(&stats[0], 1ull);
+    atomicAdd(&stats[1], scanned);
+    atomicAdd(&stats[3], (unsigned long long)(depth + 1));
+    if (end) atomicAdd(&stats[4], 1ull);
+  }
+  if (compact) {
+    int sl = -1;
+    if (lane == 0) {
       if (!end) {
         sl = atomicAdd(lv.n_eval, 1);
         lv.game_of_slot[sl] = g;
       }
       lv.slot[g] = sl;
     }
-    atomicAdd(&stats[0], 1ull);
-    atomicAdd(&stats[1], scanned);
-    atomicAdd(&stats[3], (unsigned long long)(depth + 1));
-    if (end) atomicAdd(&stats[4], 1ull);
+    // the leaf board is still in registers: write its net input planes straight into its tile (no features kernel)
+    sl = __shfl_sync(AP_FULL, sl, 0);
+    if (feat && sl >= 0) emit_features_warp(b, geo.W, geo.H, sl, feat, mpad, lane);
   }
 }
 
@@ -73,8 +80,9 @@ __global__ void __launch_bounds__(32 * SEL_WARPS)
 k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts, const int16_t* __restrict__ acts,
                 const double* __restrict__ pri64, const double* __restrict__ val64, const float* __restrict__ pri32,
                 const float* __restrict__ val32, const int32_t* __restrict__ slot, int32_t* errflag,
-                unsigned long long* stats) {
+                unsigned long long* stats, FcFinish fin) {
   __shared__ int16_t s_list[SEL_WARPS][AP_MAX_S];
+  __shared__ float s_prob[SEL_WARPS][AP_MAX_S];
   int lane = threadIdx.x & 31;
   int w = threadIdx.x >> 5;
   int g = blockIdx.x * SEL_WARPS + w;
@@ -82,6 +90,7 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
   size_t base = (size_t)g * geo.cap;
   int leaf = lv.node[g];
   double v;
+  float fused_v = 0.f;
   if (!lv.terminal[g]) {
     int A;
     const int src = slot ? slot[g] : g;  // compacted net batch: row of this game's priors / value
@@ -96,7 +105,17 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
     } else {
       WBoard b = wb_load(lv.rows, lv.meta, g, lane);
       A = wb_legal_list(b, geo.W, geo.H, lane, s_list[w]);
-      if (pri64)
+      if (fin.partial) {
+        // fused lock-step: softmax / tanh of the split-K FC partial logits of this game's net tile, priors from
+        // shared memory (same arithmetic as k_head_fc_finish, no probability matrix in HBM)
+        float pr[8];
+        fused_v = fc_finish_warp(fin, src, geo.S, lane, pr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_prob[w][lane + 32 * j] = pr[j];
+        __syncwarp();
+        ok = tree_expand(pl, base, g, geo.cap, leaf, A, s_list[w],
+                         [&](int k, int mv) { return (double)s_prob[w][mv]; }, lane);
+      } else if (pri64)
         ok = tree_expand(pl, base, g, geo.cap, leaf, A, s_list[w],
                          [&](int k, int mv) { return pri64[row + mv]; }, lane);
       else
@@ -105,7 +124,7 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
     }
     if (!ok && lane == 0) errflag[g] = AP_ERR_POOL_EXHAUSTED;
     if (ok && lane == 0) atomicAdd(&stats[2], (unsigned long long)A);
-    v = val64 ? val64[src] : (double)val32[src];
+    v = (fin.partial && !acts) ? (double)fused_v : (val64 ? val64[src] : (double)val32[src]);
   } else {
     int winner = lv.winner[g];
     int cur = lv.meta[g].cur;
@@ -314,14 +333,20 @@ void launch_tree_reset_all(ap_engine* e) {
   k_tree_reset_all<<<(e->geo.G + 127) / 128, 128, 0, e->stream>>>(e->geo, e->pools);
 }
 void launch_select(ap_engine* e, bool compact) {
+  __half* feat = nullptr;
+  long long mpad = 0;
+  if (compact) net_feature_planes(e, &feat, &mpad);
   k_select<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, e->leaves, e->stats,
-                                                                compact ? 1 : 0);
+                                                                compact ? 1 : 0, feat, mpad);
 }
 void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* d_acts, const double* d_pri64,
-                          const double* d_val64, const float* d_pri32, const float* d_val32, const int32_t* d_slot) {
+                          const double* d_val64, const float* d_pri32, const float* d_val32, const int32_t* d_slot,
+                          bool fuse_fc_finish) {
+  FcFinish fin{nullptr, nullptr, 0, 0, 0};
+  if (fuse_fc_finish) net_fc_finish_args(e, &fin.partial, &fin.bias, &fin.rows, &fin.np, &fin.ksplit);
   k_expand_backup<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, e->leaves, d_counts, d_acts,
                                                                        d_pri64, d_val64, d_pri32, d_val32, d_slot,
-                                                                       e->errflag, e->stats);
+                                                                       e->errflag, e->stats, fin);
 }
 
 // Order-preserving compaction of the non-terminal leaves: slot[g] = number of non-terminal leaves before game g
