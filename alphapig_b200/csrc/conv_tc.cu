@@ -239,6 +239,7 @@ __device__ __forceinline__ void head_finish(const ConvParams& p, const HeadArg<t
       for (int o = 0; o < 6; ++o)
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (uint32_t)((r * 6 + o) * 4)), "f"(hacc[r][o]) : "memory");
   }
+  __syncwarp();  // bar.sync is the .aligned form: the warp must arrive converged (the predicated blocks above may have split it)
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NCG) : "memory");
   if (cg == 0) {
     const int S = p.W * p.H;
@@ -270,6 +271,7 @@ __device__ __forceinline__ void head_finish(const ConvParams& p, const HeadArg<t
       }
     }
   }
+  __syncwarp();  // bar.sync is the .aligned form: the warp must arrive converged (the predicated blocks above may have split it)
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NCG) : "memory");
 }
 
