@@ -90,6 +90,10 @@ struct ap_engine {
   ReplayState* replay = nullptr;
   float* d_probs = nullptr;   // [G][S] fp32
   float* d_values = nullptr;  // [G]
+  // ap_pure_run leaves lazily materialised trees (only the root's child block is complete, see rollout.cu); the
+  // reference's mcts_pure never reuses a tree (get_action ends with update_with_move(-1), mcts_pure.py:196-203), so
+  // the next tree operation other than reading the root starts from fresh roots
+  bool pure_tree = false;
   float last_total_ms = 0.f, last_net_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // optional per-phase timing of ap_search_run (ap_search_profile): events after every phase of every lock-step

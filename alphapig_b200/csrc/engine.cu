@@ -337,8 +337,19 @@ int ap_boards_import(ap_engine* e, const int32_t* game_ids, int32_t n, const int
 
 // ---- search -------------------------------------------------------------------------------
 
+// trees left behind by ap_pure_run are never continued (see ap_engine::pure_tree)
+static int drop_pure_trees(ap_engine* e) {
+  if (e->pure_tree) {
+    launch_tree_reset_all(e);
+    AP_LAUNCH_CHECK(e);
+    e->pure_tree = false;
+  }
+  return AP_OK;
+}
+
 int ap_search_select(ap_engine* e, uint8_t* out_terminal, int32_t* out_depth, int16_t* out_path) {
   if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(drop_pure_trees(e));
   launch_select(e);
   AP_LAUNCH_CHECK(e);
   const int G = e->geo.G;
@@ -399,6 +410,7 @@ int ap_search_expand_backup_dense(ap_engine* e, const float* priors, const float
 int ap_search_run(ap_engine* e, int32_t n_playout) {
   if (!e) return AP_ERR_BAD_HANDLE;
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "ap_search_run: no net loaded (ap_net_load)");
+  AP_TRY(drop_pure_trees(e));
   // phases per lock-step: select, features, one per trunk conv, heads, expand/backup
   const int phases = net_phase_count(e) + 2;
   if (e->profile) {
@@ -493,6 +505,7 @@ int ap_search_root_probs(ap_engine* e, double temp, double* out) {
 
 int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves) {
   if (!e) return AP_ERR_BAD_HANDLE;
+  AP_TRY(drop_pure_trees(e));
   AP_TRY(ap_ids(e, game_ids, n));
   AP_TRY(ap_stage(e, sizeof(int32_t) * n, 0));
   AP_TRY(h2d(e, e->d_stage, moves, sizeof(int32_t) * n));
@@ -519,6 +532,7 @@ int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   launch_pure_run(e, n_playout, seed, rollout_mode, (int32_t*)e->d_stage);
   AP_LAUNCH_CHECK(e);
+  e->pure_tree = true;
   AP_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   AP_TRY(d2h_sync(e, out_move, e->d_stage, 4 * (size_t)e->geo.G));
   cudaEventElapsedTime(&e->last_total_ms, e->ev0, e->ev1);

@@ -320,8 +320,18 @@ __device__ __forceinline__ int hash_eval(const WBoard& b, const Geo& geo) {
 // u = x/(1+N) depends on the visit count alone: lane L computes the correctly rounded quotient for N = L once
 // and the children fetch theirs by shuffle (own division only for N >= 32) - the same fp64 operations on the
 // same operands as tree_select_child, ~6 instead of ~35 instructions per child and no load of P.
-__device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, int cs, int cc, int np, double c_puct,
-                                                 int lane, int& best_move) {
+//
+// LAZY CHILDREN.  All unvisited children of a node score exactly 0.0 + x/(1+0) and Python's max() takes the first
+// maximum, so an unvisited child is only ever chosen as the LOWEST-index unvisited one: the visited children of a
+// node are always the prefix [0, nv) of its (ascending-move) child list.  The kernel therefore reserves the child
+// block at expansion but writes nothing; select scans the nv visited records plus ONE virtual candidate (index nv,
+// score 0.0 + u[0]), and a record is materialised (move = nv-th legal move of the node's position, which the
+// descent holds in registers) only when that candidate wins.  Same visit counts, Q and moves as the eager tree
+// (golden and oracle tests in rollout_mode 1), ~200x fewer child records written, no legal-move list per playout.
+// nv lives in the node's `parent` field (the path is kept in shared memory, parents are not needed during the
+// search); the root's block is completed and the parents restored before the kernel returns.
+__device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, int cs, int cc, int nv, int np,
+                                                 double c_puct, int lane, int& best_move) {
   constexpr int PER = AP_MAX_S / 32;
   double q[PER];
   int n[PER], m[PER];
@@ -330,7 +340,7 @@ __device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, i
     const int i = lane + 32 * j;
     const size_t c = base + cs + i;
     q[j] = 0.0, n[j] = 0, m[j] = -1;
-    if (i < cc) {
+    if (i < nv) {
       q[j] = pl.Q[c];
       n[j] = pl.N[c];
       m[j] = pl.move[c];
@@ -343,16 +353,25 @@ __device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, i
   int bi = INT_MAX, bm = -1;
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
-    if (32 * j < cc) {  // warp-uniform
+    if (32 * j < nv) {  // warp-uniform
       const int i = lane + 32 * j;
       double u = __shfl_sync(AP_FULL, ut, n[j] & 31);
       if (n[j] >= 32) u = ddiv_slow(x, 1 + n[j]);
       const double v = __dadd_rn(q[j], u);
-      if (i < cc && (v > bv || bi == INT_MAX)) {  // first element always taken, later only if strictly greater
+      if (i < nv && (v > bv || bi == INT_MAX)) {  // first element always taken, later only if strictly greater
         bv = v;
         bi = i;
         bm = m[j];
       }
+    }
+  }
+  {
+    // the first unvisited child (Q = 0, N = 0): index nv is larger than every index this lane has seen
+    const double v0 = __dadd_rn(0.0, __shfl_sync(AP_FULL, ut, 0));
+    if (nv < cc && lane == (nv & 31) && (v0 > bv || bi == INT_MAX)) {
+      bv = v0;
+      bi = nv;
+      bm = -1;
     }
   }
   // python max(): the largest score, the earliest child among equals.  Scores map to order-preserving 64-bit
@@ -370,9 +389,28 @@ __device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, i
   return (int)best;
 }
 
+// k-th (0-based) legal move in ascending order of position b (k < number of empty cells)
+__device__ __forceinline__ int wb_kth_legal(const WBoard& b, int k, int W, int H, int lane) {
+  const uint32_t e = wb_empty_row(b, W, H, lane);
+  const int c = __popc(e);
+  int pre = c;
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const int t = __shfl_up_sync(AP_FULL, pre, d);
+    if (lane >= d) pre += t;
+  }
+  const bool mine = (lane < AP_ROWS) && (k >= pre - c) && (k < pre);
+  const int h = __ffs(__ballot_sync(AP_FULL, mine)) - 1;
+  int w = 0;
+  if (mine) w = (int)__fns(e, 0, k - (pre - c) + 1);
+  w = __shfl_sync(AP_FULL, w, h);
+  return h * W + w;
+}
+
 // MCTS.get_move (mcts_pure.py:159-169): tree reset, n_playout x _playout (:114-136), arg-max visits.
-// P of the children is not stored (implicit 1/child_count, see pure_select_child); the path of a playout is kept
-// in shared memory so that update_recursive (:61-67) touches all its nodes in one memory round trip, one lane each.
+// P of the children is not stored (implicit 1/child_count) and children are materialised lazily (see
+// pure_select_child); the path of a playout is kept in shared memory so that update_recursive (:61-67) touches all
+// its nodes in one memory round trip, one lane each.
 template <int MODE>  // 0 = permutation rollouts (W <= 15), 1 = position hash, 2 = ply-by-ply rollouts
 __global__ void __launch_bounds__(32, AP_PURE_MINBLK)
 k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, int n_playout,
@@ -387,56 +425,73 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
   const uint32_t inv_w = 65536u / (uint32_t)geo.W + 1u;  // (mv * inv_w) >> 16 == mv / W for mv < 256, W <= 16
   Pcg rng = pcg_seed(seed, (unsigned long long)g);  // MODE 2 only
   if (lane == 0) tree_write_root(pl, base, g);
+  int a_next = 1;  // allocation cursor of this game's pool (node 0 = root)
   __syncwarp();
-  unsigned long long scanned = 0, written = 0, pathn = 0, plies_total = 0;
+  // counters keep SURVEY 8(d)'s algorithmic meaning (the reference scans / creates all A children of a node)
+  unsigned int scanned = 0, written = 0, pathn = 0, plies_total = 0;  // < 2^32 per game for n_playout <= 10^6
+  bool failed = false;
 #pragma unroll 1
   for (int it = 0; it < n_playout; ++it) {
     WBoard b = root;
     int node = 0, depth = 0;
+    auto play = [&](int mv) {
+      const int h = (int)(((uint32_t)mv * inv_w) >> 16), w = mv - h * geo.W;
+      if (lane == h) b.row |= (1u << w) << ((b.cur == 2) ? 16 : 0);
+      b.nst += 1;
+      b.last = mv;
+      b.cur = 3 - b.cur;
+    };
 #pragma unroll 1
     while (true) {
       const int cs = pl.child_start[base + node];
       const int cc = pl.child_count[base + node];
       const int np = pl.N[base + node];
+      const int nv = pl.parent[base + node];  // visited (= materialised) children of an expanded node
       if (lane == 0) s_path[depth] = node;
       if (cs < 0) break;
       int mv;
-      const int bi = pure_select_child(pl, base, cs, cc, np, geo.c_puct, lane, mv);
-      const int h = (int)(((uint32_t)mv * inv_w) >> 16), w = mv - h * geo.W;
-      if (lane == h) b.row |= (1u << w) << ((b.cur == 2) ? 16 : 0);
-      b.hist = (b.hist << 16) | (unsigned long long)(uint16_t)mv;
-      b.nst += 1;
-      b.last = mv;
-      b.cur = 3 - b.cur;
+      const int bi = pure_select_child(pl, base, cs, cc, nv, np, geo.c_puct, lane, mv);
+      scanned += cc;
+      if (bi == nv) {
+        // first visit of child nv: materialise its record; it is the (unexpanded) leaf of this playout
+        mv = wb_kth_legal(b, nv, geo.W, geo.H, lane);
+        if (lane == 0) {
+          const size_t c = base + cs + nv;
+          pl.Q[c] = 0.0;
+          pl.N[c] = 0;
+          pl.child_start[c] = -1;
+          pl.child_count[c] = 0;
+          pl.parent[c] = 0;
+          pl.move[c] = (int16_t)mv;
+          pl.parent[base + node] = nv + 1;
+          s_path[depth + 1] = cs + nv;
+        }
+        play(mv);
+        node = cs + nv;
+        ++depth;
+        break;
+      }
+      play(mv);
       node = cs + bi;
       ++depth;
-      scanned += cc;
     }
     int winner;
     const bool end = (MODE == 0) ? wb_game_end_packed(b, geo.n_in_row, geo.S, winner)
                                  : wb_game_end(b, geo.n_in_row, geo.S, winner);
     if (!end) {
-      const int A = wb_legal_list(b, geo.W, geo.H, lane, s_list);
-      const int a0 = pl.alloc[g];
-      if (a0 + A > geo.cap) {
+      // TreeNode.expand (mcts_pure.py:34-41): reserve the block of the A = |availables| children
+      const int A = geo.S - b.nst;
+      if (a_next + A > geo.cap) {
         if (lane == 0) errflag[g] = AP_ERR_POOL_EXHAUSTED;
+        failed = true;
         break;
       }
-#pragma unroll 1
-      for (int k = lane; k < A; k += 32) {  // TreeNode.expand (mcts_pure.py:34-41), children in list order
-        const size_t c = base + a0 + k;
-        pl.Q[c] = 0.0;
-        pl.N[c] = 0;
-        pl.child_start[c] = -1;
-        pl.child_count[c] = 0;
-        pl.parent[c] = node;
-        pl.move[c] = s_list[k];
-      }
       if (lane == 0) {
-        pl.child_start[base + node] = a0;
+        pl.child_start[base + node] = a_next;
         pl.child_count[base + node] = (uint16_t)A;
-        pl.alloc[g] = a0 + A;
+        pl.parent[base + node] = 0;
       }
+      a_next += A;
       written += A;
     }
     int plies = 0;
@@ -472,9 +527,32 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
     pathn += depth + 1;
     __syncwarp();
   }
+  // complete the root's child block (the unvisited children as fresh records), restore the parent fields the search
+  // used as visited counters, publish the allocation cursor
+  const int cs = pl.child_start[base];
+  const int cc = (cs >= 0) ? pl.child_count[base] : 0;
+  const int nv_root = (cs >= 0) ? pl.parent[base] : 0;
+  __syncwarp();
+  if (cc > 0) {
+    wb_legal_list(root, geo.W, geo.H, lane, s_list);
+    for (int k = lane; k < cc; k += 32) {
+      const size_t c = base + cs + k;
+      if (k >= nv_root) {
+        pl.Q[c] = 0.0;
+        pl.N[c] = 0;
+        pl.child_start[c] = -1;
+        pl.child_count[c] = 0;
+        pl.move[c] = s_list[k];
+      }
+      pl.parent[c] = 0;
+    }
+  }
+  if (lane == 0) {
+    pl.parent[base] = -1;
+    pl.alloc[g] = a_next;
+  }
+  __syncwarp();
   // first max by visit count over root children
-  int cs = pl.child_start[base];
-  int cc = (cs >= 0) ? pl.child_count[base] : 0;
   int bn = -1, bi = INT_MAX;
   for (int k = lane; k < cc; k += 32) {
     int n = pl.N[base + cs + k];
@@ -491,13 +569,14 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
       bi = oi;
     }
   }
+  (void)failed;
   if (lane == 0) {
     out_move[g] = (bi != INT_MAX) ? (int)pl.move[base + cs + bi] : -1;
     atomicAdd(&stats[0], (unsigned long long)n_playout);
-    atomicAdd(&stats[1], scanned);
-    atomicAdd(&stats[2], written);
-    atomicAdd(&stats[3], pathn);
-    atomicAdd(&stats[5], plies_total);
+    atomicAdd(&stats[1], (unsigned long long)scanned);
+    atomicAdd(&stats[2], (unsigned long long)written);
+    atomicAdd(&stats[3], (unsigned long long)pathn);
+    atomicAdd(&stats[5], (unsigned long long)plies_total);
   }
 }
 
