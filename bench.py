@@ -421,7 +421,7 @@ def ncu_pure_launch(G):
     """dram bytes (read + write) and issue-slot utilisation of one k_pure_run launch at the bench size, from the
     committed ncu launch list (profiles/, tools/profile_step.py --pure 0 --games 8192 --playouts 1000)."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_pure_launches_v2.csv")
+    path = os.path.join(ROOT, "profiles", "r1_pure_launches_v3.csv")
     if G != PURE_GAMES or not os.path.exists(path):
         return None, None, None
     with open(path) as f:
@@ -518,8 +518,10 @@ def run_gpu_pure(args):
                             "issue_active_pct_ncu": issue_pct, "avg_launch_ms": dev_ms / args.steps,
                             "algorithmic_bytes_per_launch": tree_bytes / args.steps,
                             "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
-                            "note": "issue bound (68 % issue-active under ncu): register-resident rollouts and warp-level select; "
-                                    "children blocks are re-read from L2, so DRAM traffic is below the algorithmic bytes"}}
+                            "note": "issue bound (73 % issue-active under ncu): register-resident rollouts and warp-level select.  "
+                                    "achieved = SURVEY 8(d)'s algorithmic bytes (what the reference's tree touches: every "
+                                    "child of every scanned / expanded node) over the launch time; the kernel itself keeps "
+                                    "children lazy and re-reads hot blocks from L2, so its DRAM traffic is ~2 % of that"}}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_pure_baseline()
         print(json.dumps(out))
