@@ -330,8 +330,9 @@ __device__ __forceinline__ int hash_eval(const WBoard& b, const Geo& geo) {
 // (golden and oracle tests in rollout_mode 1), ~200x fewer child records written, no legal-move list per playout.
 // nv lives in the node's `parent` field (the path is kept in shared memory, parents are not needed during the
 // search); the root's block is completed and the parents restored before the kernel returns.
+// s_prior[A] = 1.0 / A (np.ones(A)/A), filled once per kernel
 __device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, int cs, int cc, int nv, int np,
-                                                 double c_puct, int lane, int& best_move) {
+                                                 double c_puct, const double* s_prior, int lane, int& best_move) {
   constexpr int PER = AP_MAX_S / 32;
   double q[PER];
   int n[PER], m[PER];
@@ -346,8 +347,7 @@ __device__ __forceinline__ int pure_select_child(const Pools& pl, size_t base, i
       m[j] = pl.move[c];
     }
   }
-  const double prior = __ddiv_rn(1.0, (double)cc);  // np.ones(A)/A
-  const double x = __dmul_rn(__dmul_rn(c_puct, prior), __dsqrt_rn((double)np));
+  const double x = __dmul_rn(__dmul_rn(c_puct, s_prior[cc]), __dsqrt_rn((double)np));
   const double ut = __ddiv_rn(x, (double)(1 + lane));
   double bv = -CUDART_INF;
   int bi = INT_MAX, bm = -1;
@@ -418,12 +418,14 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
   __shared__ int16_t s_list[AP_MAX_S];
   __shared__ __align__(16) uint8_t s_rank[256];
   __shared__ int s_path[AP_MAX_S + 1];
+  __shared__ double s_prior[AP_MAX_S + 1];
   const int lane = threadIdx.x;
   const int g = blockIdx.x;
   const size_t base = (size_t)g * geo.cap;
   const WBoard root = wb_load(rows, meta, g, lane);
   const uint32_t inv_w = 65536u / (uint32_t)geo.W + 1u;  // (mv * inv_w) >> 16 == mv / W for mv < 256, W <= 16
   Pcg rng = pcg_seed(seed, (unsigned long long)g);  // MODE 2 only
+  for (int a = lane; a <= AP_MAX_S; a += 32) s_prior[a] = __ddiv_rn(1.0, (double)(a > 0 ? a : 1));
   if (lane == 0) tree_write_root(pl, base, g);
   int a_next = 1;  // allocation cursor of this game's pool (node 0 = root)
   __syncwarp();
@@ -450,7 +452,7 @@ k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restri
       if (lane == 0) s_path[depth] = node;
       if (cs < 0) break;
       int mv;
-      const int bi = pure_select_child(pl, base, cs, cc, nv, np, geo.c_puct, lane, mv);
+      const int bi = pure_select_child(pl, base, cs, cc, nv, np, geo.c_puct, s_prior, lane, mv);
       scanned += cc;
       if (bi == nv) {
         // first visit of child nv: materialise its record; it is the (unexpanded) leaf of this playout
