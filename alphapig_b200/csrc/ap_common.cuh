@@ -94,6 +94,12 @@ struct ap_engine {
   // reference's mcts_pure never reuses a tree (get_action ends with update_with_move(-1), mcts_pure.py:196-203), so
   // the next tree operation other than reading the root starts from fresh roots
   bool pure_tree = false;
+  // small batches (interactive play: one game) are launch-latency bound: the n_playout lock-steps of ap_search_run are
+  // captured once into a CUDA graph and replayed; rebuilt when n_playout or the prepared weights change
+  cudaGraphExec_t run_graph = nullptr;
+  int run_graph_playouts = 0;
+  uint64_t run_graph_gen = 0, run_graph_launches = 0;
+  uint64_t net_generation = 0;  // bumped by every weight preparation (kernel-parameter copies of the head weights)
   float last_total_ms = 0.f, last_net_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // optional per-phase timing of ap_search_run (ap_search_profile): events after every phase of every lock-step

@@ -180,6 +180,10 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
 }
 
 int ap_engine_destroy(ap_engine* e) {
+  if (e && e->run_graph) {
+    cudaGraphExecDestroy(e->run_graph);
+    e->run_graph = nullptr;
+  }
   if (!e) return AP_ERR_BAD_HANDLE;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
@@ -425,21 +429,54 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
   // AP_COMPACT_KERNEL=1: the unfused lock-step (A/B): separate order-preserving compaction kernel, features kernel
   // and FC finish kernel instead of the ticket + feature emission inside k_select and the softmax inside k_expand_backup
   static const bool compact_kernel = getenv("AP_COMPACT_KERNEL") && atoi(getenv("AP_COMPACT_KERNEL")) != 0;
-  AP_CUDA(e, cudaMemsetAsync(e->leaves.n_eval, 0, 4, e->stream));
+  // AP_GRAPH_MAX_GAMES: largest batch that replays the lock-steps as a CUDA graph (default 256; 0 disables)
+  static const int graph_max_games = getenv("AP_GRAPH_MAX_GAMES") ? atoi(getenv("AP_GRAPH_MAX_GAMES")) : 256;
+  const bool compact = net_can_compact(e);
+  auto enqueue = [&]() -> int {
+    AP_CUDA(e, cudaMemsetAsync(e->leaves.n_eval, 0, 4, e->stream));
+    for (int it = 0; it < n_playout; ++it) {
+      launch_select(e, compact && !compact_kernel);
+      AP_LAUNCH_CHECK(e);
+      prof_mark(e);
+      // only the non-terminal leaves are evaluated (the reference discards the evaluator's answer at a terminal
+      // leaf, mcts_alphaZero.py:124-136): the net runs on the compacted batch, expand/backup reads through the slot map
+      AP_TRY(net_forward_leaves(e, 0, compact, !compact_kernel));
+      launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values,
+                           compact ? e->leaves.slot : nullptr, compact && !compact_kernel);
+      AP_LAUNCH_CHECK(e);
+      prof_mark(e);
+    }
+    return AP_OK;
+  };
+  const bool use_graph = !e->profile && e->geo.G <= graph_max_games && n_playout >= 4;
+  if (use_graph && (!e->run_graph || e->run_graph_playouts != n_playout || e->run_graph_gen != e->net_generation)) {
+    if (e->run_graph) cudaGraphExecDestroy(e->run_graph);
+    e->run_graph = nullptr;
+    const uint64_t l0 = e->launches;
+    cudaGraph_t g = nullptr;
+    AP_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    if (rc != AP_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    AP_CUDA(e, ce);
+    const cudaError_t ci = cudaGraphInstantiate(&e->run_graph, g, 0);
+    cudaGraphDestroy(g);
+    AP_CUDA(e, ci);
+    e->run_graph_launches = e->launches - l0;
+    e->launches = l0;  // counted per replay below
+    e->run_graph_playouts = n_playout;
+    e->run_graph_gen = e->net_generation;
+  }
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   prof_mark(e);
-  const bool compact = net_can_compact(e);
-  for (int it = 0; it < n_playout; ++it) {
-    launch_select(e, compact && !compact_kernel);
-    AP_LAUNCH_CHECK(e);
-    prof_mark(e);
-    // only the non-terminal leaves are evaluated (the reference discards the evaluator's answer at a terminal
-    // leaf, mcts_alphaZero.py:124-136): the net runs on the compacted batch, expand/backup reads through the slot map
-    AP_TRY(net_forward_leaves(e, 0, compact, !compact_kernel));
-    launch_expand_backup(e, nullptr, nullptr, nullptr, nullptr, e->d_probs, e->d_values, compact ? e->leaves.slot : nullptr,
-                         compact && !compact_kernel);
-    AP_LAUNCH_CHECK(e);
-    prof_mark(e);
+  if (use_graph) {
+    AP_CUDA(e, cudaGraphLaunch(e->run_graph, e->stream));
+    e->launches += e->run_graph_launches;
+  } else {
+    AP_TRY(enqueue());
   }
   AP_CUDA(e, cudaEventRecord(e->ev1, e->stream));
   AP_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -459,6 +459,7 @@ int net_destroy(ap_engine* e) {
 
 static int net_prep(ap_engine* e) {
   NetState* n = e->net;
+  e->net_generation++;  // captured lock-step graphs hold copies of the prepared head weights
   if (n->vmaster) {
     AP_CUDA(e, cudaMemsetAsync(n->vmaster, 0, (size_t)n->vmaster_numel * 4, e->stream));
     for (size_t i = 0; i + 1 < n->vvar_ranges.size(); i += 2) {
