@@ -225,7 +225,7 @@ def ncu_conv_traffic(G):
     list of this workload (profiles/, `ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum` on
     tools/profile_step.py --games 4096).  None when the list is missing or the batch differs."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_launches_v6_final.csv")
+    path = os.path.join(ROOT, "profiles", "r1_launches_v7_final.csv")
     if G != 4096 or not os.path.exists(path):
         return None, None
     per = {}
@@ -421,7 +421,7 @@ def ncu_pure_launch(G):
     """dram bytes (read + write) and issue-slot utilisation of one k_pure_run launch at the bench size, from the
     committed ncu launch list (profiles/, tools/profile_step.py --pure 0 --games 8192 --playouts 1000)."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_pure_launches_v3.csv")
+    path = os.path.join(ROOT, "profiles", "r1_pure_launches_v4.csv")
     if G != PURE_GAMES or not os.path.exists(path):
         return None, None, None
     with open(path) as f:
