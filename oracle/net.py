@@ -1,6 +1,8 @@
 """Oracle restatement of the reference policy/value nets (PyTorch-CPU, fp32/fp64).
 
-TEST INFRASTRUCTURE — see ``oracle/__init__.py``.  **PARITY UNPINNED** at the
+TEST INFRASTRUCTURE — see ``oracle/__init__.py``.  STRUCTURE PINNED (``symbol_ops``
+equals the reference's committed symbol file ``policy_value_loss.json`` node for
+node, tests/test_oracle_golden.py); arithmetic **PARITY UNPINNED** at the
 MXNet boundary: the arithmetic of the reference lives in MXNet
 (``requirements.txt:8`` -> mxnet==1.6.0; graph file written by 1.5.1), which is
 not present in ``/root/reference`` nor installable here.  This module restates
@@ -225,3 +227,81 @@ def flop_per_leaf(arch, width, height, n_blocks=10, n_filter=128):
             mac += 9 * item[2] * item[3] * S + 9 * item[3] * item[3] * S
     mac += cfin * 6 * S + 4 * S * S + 2 * S
     return 2 * mac
+
+
+def symbol_ops(arch="resnet", n_blocks=10, n_filter=128, width=15, height=15):
+    """The op list of the reference's TRAIN symbol (create_policy_value_train, policy_value_net_mxnet.py:173-212 /
+    ..._simple.py:121-159) as THIS restatement understands it - derived from the same ``trunk_spec`` / head
+    constants ``forward`` and ``alphapig_b200.train`` use - in MXNet's node order and naming:
+    [{"op", "name", "attrs", "inputs"}].  ``tests/test_oracle_golden.py`` compares it with the op list of the
+    reference's committed symbol file (``policy_value_loss.json`` -> ``tests/golden/res10_symbol_ops.json``): the
+    structural pin of this module (layer order, kernel / pad / filters, which BatchNorms train gamma, residual adds,
+    heads, Dropout, tanh / SoftmaxActivation, loss and entropy outputs)."""
+    S = width * height
+    ops = []
+
+    def add(op, name, inputs, **attrs):
+        ops.append({"op": op, "name": name, "attrs": {k: str(v) for k, v in attrs.items()}, "inputs": list(inputs)})
+        return name
+
+    def conv_act(x, name, nf, k, act="relu"):
+        pad = k // 2
+        c = add("Convolution", name, [x, name + "_weight", name + "_bias"], kernel="(%d, %d)" % (k, k), num_filter=nf,
+                pad="(%d, %d)" % (pad, pad))
+        # conv_act BatchNorms keep MXNet's default fix_gamma=True (no attr in the symbol file)
+        b = add("BatchNorm", name + "_bn", [c, name + "_gamma", name + "_beta", name + "_mean", name + "_var"])
+        return add("Activation", name + "_act", [b], act_type=act)
+
+    spec, _ = trunk_spec(arch, n_blocks, n_filter)
+    x = "input_states"
+    plus = 0
+    for item in spec:
+        if item[0] == "conv_act":
+            x = conv_act(x, item[1], item[3], 3)
+        elif item[0] == "res_block":
+            i = item[1]
+            idn = x
+            for half in ("A", "B"):
+                cn, bn = "conv%s%d" % (half, i), "bn%s%d" % (half, i)
+                c = add("Convolution", cn, [x, cn + "_weight", cn + "_bias"], kernel="(3, 3)", num_filter=item[3], pad="(1, 1)")
+                x = add("BatchNorm", bn, [c, bn + "_gamma", bn + "_beta", bn + "_moving_mean", bn + "_moving_var"],
+                        fix_gamma="False")
+                if half == "A":
+                    x = add("Activation", "actA%d" % i, [x], act_type="relu")
+            x = add("elemwise_add", "_plus%d" % plus, [x, idn])
+            plus += 1
+            x = add("Activation", "actB%d" % i, [x], act_type="relu")
+        else:
+            raise ValueError("no reference symbol for " + item[0])
+    trunk = x
+    # value head + value loss (policy_value_net_mxnet.py:93-97,190-193)
+    v = conv_act(trunk, "conv3_2_1", 2, 1)
+    v = add("Flatten", "flatten1", [v])
+    v = add("Dropout", "dropout1", [v], p=0.5)
+    v = add("FullyConnected", "fc_3_2_1", [v, "fc_3_2_1_weight", "fc_3_2_1_bias"], num_hidden=1)
+    v = add("Activation", "activation0", [v], act_type="tanh")
+    d = add("elemwise_sub", "_minus0", ["input_labels", v])
+    d = add("square", "square0", [d])
+    vloss = add("mean", "mean1", [d])
+    # policy head + policy loss (:85-91,194-199)
+    p = conv_act(trunk, "conv3_1_1", 4, 1)
+    p = add("Flatten", "flatten0", [p])
+    p = add("Dropout", "dropout0", [p], p=0.5)
+    p = add("FullyConnected", "fc_3_1_1", [p, "fc_3_1_1_weight", "fc_3_1_1_bias"], num_hidden=S)
+    p = add("SoftmaxActivation", "Act_SILER", [p])
+    lp = add("log", "log0", [p])
+    m = add("elemwise_mul", "_mul0", [lp, "mcts_probs"])
+    m = add("sum", "sum0", [m], axis=1)
+    m = add("_mul_scalar", "_mulscalar0", [m], scalar=-1.0)
+    ploss = add("mean", "mean0", [m])
+    tot = add("elemwise_add", "_plus%d" % plus, [vloss, ploss])
+    add("MakeLoss", "makeloss0", [tot])
+    # entropy output (monitoring only, :200-204)
+    n1 = add("_mul_scalar", "_mulscalar1", [p], scalar=-1.0)
+    l1 = add("log", "log1", [p])
+    e = add("elemwise_mul", "_mul1", [n1, l1])
+    e = add("sum", "sum1", [e], axis=1)
+    e = add("mean", "mean2", [e])
+    e = add("BlockGrad", "blockgrad0", [e])
+    add("MakeLoss", "makeloss1", [e])
+    return ops

@@ -177,3 +177,30 @@ def test_sgf_golden():
 
 def _packed_state_arr(s):
     return np.packbits(np.ascontiguousarray(s).astype(np.uint8).ravel())
+
+
+def test_resnet_symbol_matches_reference_graph():
+    """Structural pin of oracle/net.py: the op list it derives from its own trunk / head spec equals, node for node
+    (op, MXNet name, attrs, input names), the reference's committed train symbol of the 10-block residual net
+    (policy_value_loss.json, fixture written by tests/golden/make_graph_golden.py): layer order, kernels / pads /
+    filters, which BatchNorms train gamma, the residual adds, Dropout(0.5), tanh / SoftmaxActivation, the loss
+    mean((z - v)^2) + mean(-sum(pi * log p)) and the BlockGrad entropy output.  Parameter names and the declared
+    input shape too."""
+    from oracle import net as onet
+    gold = json.load(open(os.path.join(GOLDEN, "res10_symbol_ops.json")))
+    mine = onet.symbol_ops("resnet", n_blocks=10, n_filter=128, width=15, height=15)
+    assert len(mine) == len(gold["ops"]) == 104
+    for a, b in zip(mine, gold["ops"]):
+        assert a == b, (a, b)
+    assert gold["heads"] == ["makeloss0", "makeloss1"]
+    nulls = {n["name"]: n["attrs"] for n in gold["nulls"]}
+    arg, aux = onet.param_shapes("resnet", 15, 15, 10, 128)
+    assert set(arg) | set(aux) == set(nulls) - {"input_states", "input_labels", "mcts_probs"}
+    assert nulls["input_states"]["__shape__"] == "(128, 9, 15, 15)"  # (batch, 9 planes, H, W): train_mxnet.py batch 128
+    for name in aux:  # moving statistics start at mean 0 / var 1 (oracle init_params without synthetic stats)
+        want = '["zero", {}]' if name.endswith("mean") else '["one", {}]'
+        assert nulls[name]["__init__"] == want, name
+    for name, shp in arg.items():  # the 3x3 trunk weights are (128, cin, 3, 3), the heads 1x1
+        if name.endswith("_weight") and len(shp) == 4:
+            k = 1 if name.startswith("conv3_") else 3
+            assert shp[2:] == (k, k), name

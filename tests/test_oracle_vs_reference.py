@@ -255,3 +255,17 @@ def test_policy_evaluate_live():
     it = iter(seq)
     rb, cnt = opl.policy_evaluate(lambda a, b, sp: next(it), None, None, 10)
     assert ra == rb == (6 + 0.5 * 2) / 10 and calls == [0, 1] * 5
+
+
+def test_symbol_fixture_is_current_live():
+    """tests/golden/res10_symbol_ops.json is exactly what tests/golden/make_graph_golden.py extracts from the
+    reference's committed policy_value_loss.json today."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_graph_golden", os.path.join(here, "golden", "make_graph_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    live = mod.extract(os.path.join(refimport.REF, "policy_value_loss.json"))
+    assert live == json.load(open(os.path.join(here, "golden", "res10_symbol_ops.json")))
