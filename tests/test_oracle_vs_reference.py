@@ -269,3 +269,15 @@ def test_symbol_fixture_is_current_live():
     spec.loader.exec_module(mod)
     live = mod.extract(os.path.join(refimport.REF, "policy_value_loss.json"))
     assert live == json.load(open(os.path.join(here, "golden", "res10_symbol_ops.json")))
+
+
+def test_train_config_defaults_live():
+    """The TrainPipeline shim's DEFAULT_CONF carries exactly the keys and values of the reference's own
+    conf/train_config.yaml (everything except the logging section), so `TrainPipeline({})` trains with the
+    reference's hyper-parameters (train_mxnet.py:37-75 reads the same keys)."""
+    import os
+    import yaml
+    from alphapig_b200.train_mxnet import DEFAULT_CONF
+    ref = yaml.safe_load(open(os.path.join(refimport.REF, "conf", "train_config.yaml"), encoding="utf-8"))
+    ref.pop("train_logging")
+    assert ref == DEFAULT_CONF
