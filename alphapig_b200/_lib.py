@@ -61,6 +61,7 @@ SIGNATURES = {
     "ap_search_root_probs": (C.c_int, [_P, C.c_double, _P]),
     "ap_search_advance": (C.c_int, [_P, _P, _I, _P]),
     "ap_search_stats": (C.c_int, [_P, _P]),
+    "ap_selfplay_pick": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32, _P, _P, _P]),
     "ap_pure_run": (C.c_int, [_P, _I, C.c_uint64, _I, _P]),
     "ap_rollout_eval": (C.c_int, [_P, C.c_uint64, _P, _P]),
     "ap_rollout_eval2": (C.c_int, [_P, C.c_uint64, _I, _P, _P]),

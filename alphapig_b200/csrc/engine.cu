@@ -540,6 +540,24 @@ int ap_search_root_probs(ap_engine* e, double temp, double* out) {
   return d2h_sync(e, out, e->d_stage, bytes);
 }
 
+int ap_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64_t seed, uint32_t ply, int32_t* out_moves,
+                     float* out_pi, double* out_noise) {
+  if (!e) return AP_ERR_BAD_HANDLE;
+  if (!(temp > 0) || eps < 0 || eps > 1 || !(alpha > 0)) return ap_fail(e, AP_ERR_BAD_ARG, "temp > 0, 0 <= eps <= 1, alpha > 0");
+  if (!out_moves || !out_pi) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
+  const size_t G = e->geo.G, S = e->geo.S;
+  const size_t mb = (4 * G + 15) & ~15ull, pb = 4 * G * S, nb = out_noise ? 8 * G * S : 0;
+  AP_TRY(ap_stage(e, mb + pb + nb, 0));
+  int32_t* d_m = (int32_t*)e->d_stage;
+  float* d_p = (float*)((char*)e->d_stage + mb);
+  double* d_n = out_noise ? (double*)((char*)e->d_stage + mb + pb) : nullptr;
+  launch_selfplay_pick(e, temp, eps, alpha, seed, ply, d_m, d_p, d_n);
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaMemcpyAsync(out_moves, d_m, 4 * G, cudaMemcpyDeviceToHost, e->stream));
+  if (out_noise) AP_CUDA(e, cudaMemcpyAsync(out_noise, d_n, nb, cudaMemcpyDeviceToHost, e->stream));
+  return d2h_sync(e, out_pi, d_p, pb);
+}
+
 int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves) {
   if (!e) return AP_ERR_BAD_HANDLE;
   AP_TRY(drop_pure_trees(e));

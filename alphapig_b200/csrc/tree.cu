@@ -327,6 +327,151 @@ __global__ void k_root_probs(Geo geo, Pools pl, double temp, double* out) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MCTSPlayer.get_action in self-play (mcts_alphaZero.py:187-215) for every game, on the device:
+//   pi = softmax(1/temp * log(visits + 1e-10)); move ~ (1 - eps) * pi + eps * Dirichlet(alpha * ones(A)); the
+//   returned pi is the un-noised one, scattered by move index (fp32, the training record).
+// The reference draws from NumPy's global generator; here every (game, ply) owns a Philox4x32-10 stream, the
+// Dirichlet sample is normalised Gamma(alpha) variates (Marsaglia-Tsang, boosted for alpha < 1) and the move is the
+// first child whose running sum exceeds u * total (np.random.choice's inverse-cdf rule).  Distributional parity
+// (tests/test_gpu_shims.py): move frequencies vs pi and vs the uniform mean of the noise, the noise marginals vs
+// Beta(alpha, (A - 1) alpha).  One warp per game.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_pick(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                            uint32_t (&out)[4]) {
+#pragma unroll 1
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // 53-bit uniform in (0, 1)
+  const unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+}
+// Gamma(alpha, 1): Marsaglia & Tsang (2000) for alpha + 1 >= 1, times U^(1/alpha) when alpha < 1
+__device__ double gamma_variate(double alpha, unsigned long long seed, uint32_t g, uint32_t child, uint32_t ply) {
+  const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  uint32_t r[4];
+  double out = 0.0;
+  for (uint32_t trial = 0; trial < 64; ++trial) {
+    philox_pick(ply, (child << 8) | trial, g, 0x5e1fu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+    const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);  // Box-Muller
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    philox_pick(ply, (child << 8) | trial, g, 0xacce97u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u = u01(r[0], r[1]);
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+      out = d * v;
+      if (alpha < 1.0) out *= pow(u01(r[2], r[3]), 1.0 / alpha);
+      break;
+    }
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+k_selfplay_pick(Geo geo, Pools pl, double temp, double eps, double alpha, unsigned long long seed, uint32_t ply,
+                int32_t* __restrict__ out_move, float* __restrict__ out_pi, double* __restrict__ out_noise) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+  if (g >= geo.G) return;
+  const size_t base = (size_t)g * geo.cap;
+  const int cs = pl.child_start[base];
+  const int cc = (cs >= 0) ? pl.child_count[base] : 0;
+  for (int k = lane; k < geo.S; k += 32) {
+    out_pi[(size_t)g * geo.S + k] = 0.f;
+    if (out_noise) out_noise[(size_t)g * geo.S + k] = 0.0;
+  }
+  __syncwarp();
+  if (cc == 0) {  // "WARNING: the board is full" (mcts_alphaZero.py:217-218)
+    if (lane == 0) out_move[g] = -1;
+    return;
+  }
+  constexpr int PER = AP_MAX_S / 32;
+  double p[PER], nz[PER];
+  const double inv = 1.0 / temp;
+  double mx = -CUDART_INF;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int k = lane + 32 * j;
+    p[j] = -CUDART_INF;
+    nz[j] = 0.0;
+    if (k < cc) {
+      p[j] = inv * log((double)pl.N[base + cs + k] + 1e-10);
+      mx = fmax(mx, p[j]);
+      if (eps > 0.0) nz[j] = gamma_variate(alpha, seed, (uint32_t)g, (uint32_t)k, ply);
+    }
+  }
+  for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(AP_FULL, mx, d));
+  double sum = 0.0, nsum = 0.0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    p[j] = (lane + 32 * j < cc) ? exp(p[j] - mx) : 0.0;
+    sum += p[j];
+    nsum += nz[j];
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    sum += __shfl_xor_sync(AP_FULL, sum, d);
+    nsum += __shfl_xor_sync(AP_FULL, nsum, d);
+  }
+  if (!(nsum > 0.0)) nsum = 1.0;
+  // sampling weights in child order; the running sum walks j-major (k = lane + 32 j), so accumulate per j
+  uint32_t r[4];
+  philox_pick(ply, 0xffffffffu, (uint32_t)g, 0x9a3eu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const double u = u01(r[0], r[1]);
+  double w[PER], total = 0.0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    p[j] /= sum;
+    nz[j] /= nsum;
+    w[j] = (1.0 - eps) * p[j] + eps * nz[j];
+    double t = w[j];
+    for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(AP_FULL, t, d);
+    total += t;
+  }
+  const double target = u * total;
+  // first child (in child order) whose inclusive prefix sum exceeds the target
+  double before = 0.0;
+  int chosen = cc - 1;
+  bool found = false;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    double incl = w[j];
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_up_sync(AP_FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    incl += before;
+    const unsigned hit = __ballot_sync(AP_FULL, (lane + 32 * j < cc) && (incl > target));
+    if (!found && hit) {
+      chosen = 32 * j + (__ffs(hit) - 1);
+      found = true;
+    }
+    before = __shfl_sync(AP_FULL, incl, 31);
+  }
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int k = lane + 32 * j;
+    if (k < cc) {
+      const int mv = pl.move[base + cs + k];
+      out_pi[(size_t)g * geo.S + mv] = (float)p[j];
+      if (out_noise) out_noise[(size_t)g * geo.S + mv] = nz[j];
+    }
+  }
+  if (lane == 0) out_move[g] = pl.move[base + cs + chosen];
+}
+
 static inline dim3 sel_grid(int n) { return dim3((n + SEL_WARPS - 1) / SEL_WARPS); }
 
 void launch_tree_reset_all(ap_engine* e) {
@@ -394,6 +539,11 @@ void launch_root(ap_engine* e, const int32_t* d_ids, int n, int32_t* d_count, in
                  double* d_q, int32_t* d_rootn) {
   k_root<<<sel_grid(n), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, d_ids, n, d_count, d_acts, d_visits, d_q,
                                                        d_rootn);
+}
+void launch_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64_t seed, uint32_t ply,
+                          int32_t* d_move, float* d_pi, double* d_noise) {
+  k_selfplay_pick<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, temp, eps, alpha, seed, ply,
+                                                                       d_move, d_pi, d_noise);
 }
 void launch_root_probs(ap_engine* e, double temp, double* d_out) {
   k_root_probs<<<sel_grid(e->geo.G), 32 * SEL_WARPS, 0, e->stream>>>(e->geo, e->pools, temp, d_out);

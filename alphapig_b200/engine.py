@@ -209,6 +209,16 @@ class Engine(object):
         self._check(self.lib.ap_search_root_probs(self.h, float(temp), _ptr(out)))
         return out
 
+    def selfplay_pick(self, temp=1.0, eps=0.25, alpha=0.3, seed=0, ply=0, want_noise=False):
+        """Device-side MCTSPlayer.get_action(temp, return_prob=1) in self-play for every game:
+        returns (moves int32 [G], pi float32 [G][S]) (+ the Dirichlet sample when want_noise)."""
+        mv = np.zeros(self.G, np.int32)
+        pi = np.zeros((self.G, self.S), np.float32)
+        nz = np.zeros((self.G, self.S), np.float64) if want_noise else None
+        self._check(self.lib.ap_selfplay_pick(self.h, float(temp), float(eps), float(alpha), int(seed), int(ply),
+                                              _ptr(mv), _ptr(pi), _ptr(nz) if want_noise else None))
+        return (mv, pi, nz) if want_noise else (mv, pi)
+
     def search_advance(self, moves, game_ids=None):
         ids = _ids(game_ids)
         n = self._n(ids)

@@ -22,8 +22,17 @@ def visit_softmax(visits, counts, temp):
 
 class BatchedSelfPlay(object):
     def __init__(self, net, n_games, n_playout=400, c_puct=5, temp=1.0, n_in_row=5, seed=0,
-                 noise_eps=0.25, dirichlet_alpha=0.3, node_capacity=0, record_states=True, tag=0):
+                 noise_eps=0.25, dirichlet_alpha=0.3, node_capacity=0, record_states=True, tag=0, device_pick=False):
+        """device_pick: sample the moves on the device (``ap_selfplay_pick``: pi, Dirichlet noise and the inverse-cdf
+        draw per game from Philox streams instead of NumPy's global generator) and run the NEXT ply's search in a
+        background thread while this ply's records are assembled on the host - one group of games then keeps the GPU
+        busy (``PipelinedSelfPlay`` needs two half-size groups for that)."""
         self.net = net
+        self.device_pick = device_pick
+        self._seed = int(seed)
+        self._pool = None
+        self._fut = None           # device_pick: the search of the next ply, running in the background thread
+        self._search_done = False  # ... or already joined by drain()
         self.G = n_games
         self.n_playout = n_playout
         self.temp = temp
@@ -49,14 +58,83 @@ class BatchedSelfPlay(object):
 
     def load_positions(self, cells, meta):
         """Start every slot from a given position (benchmark's synthetic positions)."""
+        self.drain()
+        self._search_done = False
         self.eng.boards_import(cells, meta)
         self.eng.search_advance(-1)
         self._reset_history()
+
+    def _finish(self, done, winner):
+        """records of the games that just ended (rows of the per-ply history), slots restarted by the caller"""
+        out = []
+        for g in done:
+            t_first = int(self._start[g])
+            if self.record_states and self._ply >= t_first:
+                plies = range(t_first, self._ply + 1)
+                players = np.array([self._rec[t][2][g] for t in plies])
+                z = np.zeros(len(players))
+                if winner[g] != -1:
+                    z[players == winner[g]] = 1.0
+                    z[players != winner[g]] = -1.0
+                out.append((int(winner[g]), np.stack([self._rec[t][0][g] for t in plies]),
+                            np.stack([self._rec[t][1][g] for t in plies]).astype(np.float64), z))
+            else:
+                out.append((int(winner[g]), None, None, None))
+            self._start[g] = self._ply + 1
+        return out
+
+    def _step_device_pick(self):
+        import time
+        from concurrent.futures import ThreadPoolExecutor
+        eng = self.eng
+        if self._fut is not None:
+            self._fut.result()          # the search of this ply, started at the end of the previous step
+            self._fut = None
+        elif not self._search_done:
+            eng.search_run(self.n_playout)
+        self._search_done = False
+        t0 = time.perf_counter()
+        moves, pi = eng.selfplay_pick(self.temp, self.eps, self.alpha, seed=self._seed, ply=self._ply)
+        if self.record_states:
+            feats = eng.boards_features_packed()
+            _, meta = eng.boards_export()
+        eng.search_advance(moves)
+        eng.boards_do_move(moves)
+        end, winner = eng.boards_status()
+        done = np.nonzero(end)[0].astype(np.int32)
+        if len(done):
+            eng.boards_reset(done)
+            eng.search_advance(np.full(len(done), -1, np.int32), done)
+        # the device is ready for the next ply: search it while the host assembles the records of this one
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(1)
+        self._fut = self._pool.submit(eng.search_run, self.n_playout)
+        if self.record_states:
+            self._rec[self._ply] = (feats, pi, meta[:, 0].astype(np.int8))
+        self.plies += self.G
+        out = self._finish(done, winner)
+        self.finished_games += len(done)
+        self._ply += 1
+        if self.record_states and self._rec:
+            oldest = int(self._start.min())
+            for t in [t for t in self._rec if t < oldest]:
+                del self._rec[t]
+        self.host_seconds += time.perf_counter() - t0
+        return out
+
+    def drain(self):
+        """Wait for the search in flight (device_pick) before touching the engine from outside."""
+        if self._fut is not None:
+            self._fut.result()
+            self._fut = None
+            self._search_done = True
 
     def step(self):
         """One ply for every game.  Returns the list of finished-game records
         [(winner, states uint8[n][ceil(9S/8)] bit-packed, pis float64[n][S], z float64[n])]."""
         import time
+        if self.device_pick:
+            return self._step_device_pick()
         eng, G, S = self.eng, self.G, self.S
         eng.search_run(self.n_playout)
         t0 = time.perf_counter()

@@ -544,6 +544,9 @@ def run_gpu_selfplay(args):
     arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
     net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=local)
     kw = dict(n_playout=N_PLAYOUT, c_puct=C_PUCT, temp=1.0, n_in_row=N_IN_ROW, seed=0, node_capacity=2 * N_PLAYOUT * W * H + 2)
+    if args.device_pick:
+        args.groups = 1
+        kw["device_pick"] = True
     sp = PipelinedSelfPlay(net, G, n_groups=args.groups, **kw) if args.groups > 1 else BatchedSelfPlay(net, G, **kw)
     parts = sp.groups if args.groups > 1 else [sp]
     cm, k = [], 0
@@ -564,13 +567,15 @@ def run_gpu_selfplay(args):
         games += len(sp.step())
         moves += sp.last_moves if args.groups > 1 else G
     dt = time.perf_counter() - t0
-    if args.groups > 1:
+    if args.groups > 1 or args.device_pick:
         sp.drain()
     print(json.dumps({"metric": "selfplay_moves_per_s", "value": moves / dt, "unit": "moves/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
                       "higher_is_better": True, "data": "synthetic start positions, then real self-play with tree reuse",
                       "playouts_per_s": moves * N_PLAYOUT / dt,
                       "host_ms_per_step": 1000 * (sp.host_seconds - host0) / args.steps, "groups": args.groups,
+                      "move_sampling": "device (ap_selfplay_pick), next search overlapped with the host bookkeeping"
+                                       if args.device_pick else "host (numpy)",
                       "games_finished": games,
                       "config": {"workload": "BatchedSelfPlay.step: %d games, n_playout=%d, temp=1.0, Dirichlet noise, records kept"
                                              % (G, N_PLAYOUT)}}))
@@ -585,6 +590,8 @@ def main():
     ap.add_argument("--games", type=int, default=G_PER_GPU, help="concurrent games per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--groups", type=int, default=2, help="selfplay workload: pipelined game groups (1 = none)")
+    ap.add_argument("--device-pick", action="store_true",
+                    help="selfplay workload: one group, moves sampled on the device, next search overlapped with the host phase")
     ap.add_argument("--rollout-mode", type=int, default=0, choices=[0, 2],
                     help="pure workload: 0 = permutation rollouts (default), 2 = ply-by-ply rollouts (A/B)")
     ap.add_argument("--net", default="simple", choices=sorted(NETS),

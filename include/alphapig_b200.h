@@ -107,6 +107,13 @@ int ap_search_root(ap_engine* e, const int32_t* game_ids, int32_t n, int32_t* ou
                    int32_t* out_visits /* [n][S] */, double* out_q /* [n][S] or NULL */, int32_t* out_root_n /* [n] or NULL */);
 /* softmax(1/temp * log(visits + 1e-10)) scattered by move index, fp64        (:13-16,155) */
 int ap_search_root_probs(ap_engine* e, double temp, double* out /* [G][S] */);
+/* MCTSPlayer.get_action(board, temp, return_prob=1) with is_selfplay=1 for EVERY game, sampled on the device
+ * (:187-215): move ~ (1-eps) * pi + eps * Dirichlet(alpha) with pi = softmax(1/temp * log(visits + 1e-10));
+ * out_pi [G][S] fp32 is the un-noised pi scattered by move index (the training record); out_noise (nullable, tests)
+ * the Dirichlet sample.  Randomness: Philox streams keyed by (seed, game, ply); the reference uses eps 0.25,
+ * alpha 0.3.  A full board gives move -1.  Does not advance the tree (ap_search_advance does). */
+int ap_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64_t seed, uint32_t ply,
+                     int32_t* out_moves /* [G] */, float* out_pi /* [G][S] */, double* out_noise /* [G][S] or NULL */);
 /* MCTS.update_with_move(move): re-root on the child (subtree kept) or fresh root (-1 / absent)  (:159-167) */
 int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves);
 /* counters since the last call: playouts, sum of children scanned, children written, path nodes, terminal leaves */

@@ -301,3 +301,81 @@ def test_pipelined_self_play_groups():
         assert states.shape == (n, (9 * S + 7) // 8) and np.allclose(pis.sum(1), 1.0)
         planes = np.unpackbits(states, axis=1)[:, :9 * S].reshape(n, 9, W, W)
         assert list(planes[:, 6].sum((1, 2)) + planes[:, 7].sum((1, 2))) == list(range(n))
+
+
+def test_selfplay_pick_distribution():
+    """ap_selfplay_pick (MCTSPlayer.get_action in self-play, mcts_alphaZero.py:187-215, sampled on the device):
+    pi equals softmax(1/temp * log(visits + 1e-10)) scattered by move; with eps = 0 the chosen moves follow pi, with
+    eps = 1 they follow the Dirichlet sample whose marginals are Beta(alpha, (A - 1) alpha); full boards give -1."""
+    from scipy import stats
+    from alphapig_b200.engine import Engine
+    from helpers import export_oboard, oboard_from
+    W, G = 6, 4096
+    eng = Engine(width=W, height=W, n_in_row=4, n_games=G, c_puct=5, n_playout=48)
+    b = oboard_from(W, W, 4, [14, 15, 20])
+    c, m = export_oboard(b)
+    eng.boards_import(np.repeat(c[None], G, 0), np.repeat(m[None], G, 0))
+    # identical trees in every game, grown with the uniform evaluator through the dense device path
+    for _ in range(48):
+        term, depth, path = eng.search_select()
+        eng.search_expand_backup_dense(np.full((G, W * W), 1.0 / (W * W), np.float32), np.zeros(G, np.float32))
+    count, acts, visits, _, _ = eng.search_root()
+    assert (count == count[0]).all() and (visits == visits[0]).all()
+    A = int(count[0])
+    temp = 1.0
+    x = np.log(visits[0, :A].astype(np.float64) + 1e-10) / temp
+    pi_ref = np.exp(x - x.max())
+    pi_ref /= pi_ref.sum()
+    dense = np.zeros(W * W)
+    dense[acts[0, :A]] = pi_ref
+    # eps = 0: moves ~ pi
+    mv, pi = eng.selfplay_pick(temp=temp, eps=0.0, alpha=0.3, seed=5, ply=0)
+    assert np.allclose(pi, dense[None], atol=1e-7)
+    cnt = np.bincount(mv, minlength=W * W)[acts[0, :A]]
+    keep = pi_ref * G >= 5
+    f_obs = np.append(cnt[keep], cnt[~keep].sum())
+    f_exp = np.append(pi_ref[keep], pi_ref[~keep].sum()) * G
+    if f_exp[-1] == 0:
+        f_obs, f_exp = f_obs[:-1], f_exp[:-1]
+    assert stats.chisquare(f_obs, f_exp)[1] > 1e-6
+    # eps = 1: moves ~ Dirichlet sample; the sample's marginals are Beta(alpha, (A-1) alpha), rows sum to 1
+    mv, pi, nz = eng.selfplay_pick(temp=temp, eps=1.0, alpha=0.3, seed=6, ply=3, want_noise=True)
+    d = nz[:, acts[0, :A]]
+    assert np.allclose(d.sum(1), 1.0, atol=1e-9) and d.min() >= 0
+    for k in (0, A // 2, A - 1):
+        assert stats.kstest(d[:, k], "beta", args=(0.3, (A - 1) * 0.3))[1] > 1e-6, k
+    cnt = np.bincount(mv, minlength=W * W)[acts[0, :A]]
+    assert stats.chisquare(cnt, np.full(A, G / A))[1] > 1e-6   # E[Dirichlet] is uniform
+    # reproducible per (seed, ply); different plies differ
+    mv2, _ = eng.selfplay_pick(temp=temp, eps=1.0, alpha=0.3, seed=6, ply=3)
+    mv3, _ = eng.selfplay_pick(temp=temp, eps=1.0, alpha=0.3, seed=6, ply=4)
+    assert np.array_equal(mv, mv2) and not np.array_equal(mv, mv3)
+    eng.close()
+
+
+def test_batched_selfplay_device_pick_records():
+    """BatchedSelfPlay(device_pick=True): same record contract as the host-sampling path (game_ai.py:113-139):
+    one (state, pi, z) row per ply of a finished game, z = +1 / -1 by the winner from the mover's side, pi rows sum
+    to 1 over legal moves only; the next ply's search runs in the background while records are assembled."""
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    from alphapig_b200.selfplay import BatchedSelfPlay
+    W = 6
+    net = PolicyValueNet(W, W, batch_size=32, seed=0)
+    sp = BatchedSelfPlay(net, n_games=64, n_playout=24, n_in_row=4, seed=3, device_pick=True)
+    games = []
+    for _ in range(40):
+        games.extend(sp.step())
+    sp.drain()
+    assert len(games) >= 64 and sp.finished_games == len(games)
+    for winner, states, pis, z in games:
+        n = len(z)
+        assert states.shape == (n, (9 * W * W + 7) // 8) and pis.shape == (n, W * W)
+        assert np.allclose(pis.sum(1), 1.0, atol=1e-5)
+        planes = np.unpackbits(states, axis=1)[:, :9 * W * W].reshape(n, 9, W, W)
+        occupied = (planes[:, 6] + planes[:, 7]) > 0           # stones of both sides before the move
+        assert (pis.reshape(n, W, W)[:, ::-1][occupied] == 0).all()  # no mass on occupied cells (planes are row-flipped)
+        if winner == -1:
+            assert (z == 0).all()
+        else:
+            assert set(np.unique(z)) <= {-1.0, 1.0} and z[-1] == 1.0   # the last mover made the line
+            assert (z[::-1][::2] == 1.0).all() and (z[::-1][1::2] == -1.0).all()
