@@ -109,6 +109,14 @@ struct ap_engine {
   int prof_cursor = 0;
 };
 
+// every C-ABI entry point: validate the handle and make its device current for the calling thread (worker threads
+// of the Python drivers start on device 0)
+#define AP_ENTER(e)                           \
+  do {                                        \
+    if (!(e)) return AP_ERR_BAD_HANDLE;       \
+    cudaSetDevice((e)->cfg.device);           \
+  } while (0)
+
 #define AP_CUDA(e, call)                                                                  \
   do {                                                                                    \
     cudaError_t _st = (call);                                                             \

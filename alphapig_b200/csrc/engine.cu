@@ -184,7 +184,7 @@ int ap_engine_destroy(ap_engine* e) {
     cudaGraphExecDestroy(e->run_graph);
     e->run_graph = nullptr;
   }
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   net_destroy(e);
@@ -201,7 +201,7 @@ int ap_engine_destroy(ap_engine* e) {
 }
 
 int ap_sync(ap_engine* e) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_CUDA(e, cudaStreamSynchronize(e->stream));
   return AP_OK;
 }
@@ -221,7 +221,7 @@ int ap_launch_count(const ap_engine* e, uint64_t* out) {
 // ---- boards -------------------------------------------------------------------------------
 
 int ap_boards_reset(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* start_player) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   int32_t* d_start = nullptr;
   if (start_player) {
@@ -238,7 +238,7 @@ int ap_boards_reset(ap_engine* e, const int32_t* game_ids, int32_t n, const int3
 }
 
 int ap_boards_do_move(ap_engine* e, const int32_t* game_ids, const int32_t* moves, int32_t n, int32_t* out_status) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   AP_TRY(ap_stage(e, sizeof(int32_t) * 2 * n, 0));
   int32_t* d_moves = (int32_t*)e->d_stage;
@@ -260,7 +260,7 @@ int ap_boards_do_move(ap_engine* e, const int32_t* game_ids, const int32_t* move
 }
 
 int ap_boards_status(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* out_end, int8_t* out_winner) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   AP_TRY(ap_stage(e, 2 * (size_t)n, 0));
   uint8_t* d_end = (uint8_t*)e->d_stage;
@@ -272,7 +272,7 @@ int ap_boards_status(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* 
 }
 
 int ap_boards_legal(ap_engine* e, const int32_t* game_ids, int32_t n, uint32_t* out_mask) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   AP_TRY(ap_stage(e, 32 * (size_t)n, 0));
   launch_boards_legal(e, e->d_ids, n, (uint32_t*)e->d_stage);
@@ -281,7 +281,7 @@ int ap_boards_legal(ap_engine* e, const int32_t* game_ids, int32_t n, uint32_t* 
 }
 
 int ap_boards_features(ap_engine* e, const int32_t* game_ids, int32_t n, float* out) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   size_t bytes = (size_t)n * 9 * e->geo.S * 4;
   AP_TRY(ap_stage(e, bytes, 0));
@@ -293,7 +293,7 @@ int ap_boards_features(ap_engine* e, const int32_t* game_ids, int32_t n, float* 
 
 // Board.current_state() bit-packed (np.packbits of the 9xWxH planes): what the replay ring stores
 int ap_boards_features_packed(ap_engine* e, const int32_t* game_ids, int32_t n, uint8_t* out) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   const int nbits = 9 * e->geo.S, sb = (nbits + 7) / 8;
   const size_t fb = ((size_t)n * nbits * 4 + 15) & ~(size_t)15;
@@ -320,13 +320,13 @@ static int export_common(ap_engine* e, const uint32_t* rows, const BoardMeta* me
 }
 
 int ap_boards_export(ap_engine* e, const int32_t* game_ids, int32_t n, int8_t* out_cells, int32_t* out_meta) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   return export_common(e, e->rows, e->meta, e->d_ids, n, out_cells, out_meta);
 }
 
 int ap_boards_import(ap_engine* e, const int32_t* game_ids, int32_t n, const int8_t* cells, const int32_t* meta) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   size_t cb = ((size_t)n * e->geo.S + 15) & ~(size_t)15, mb = (size_t)n * AP_META_INTS * 4;
   AP_TRY(ap_stage(e, cb + mb, 0));
@@ -352,7 +352,7 @@ static int drop_pure_trees(ap_engine* e) {
 }
 
 int ap_search_select(ap_engine* e, uint8_t* out_terminal, int32_t* out_depth, int16_t* out_path) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(drop_pure_trees(e));
   launch_select(e);
   AP_LAUNCH_CHECK(e);
@@ -365,12 +365,12 @@ int ap_search_select(ap_engine* e, uint8_t* out_terminal, int32_t* out_depth, in
 }
 
 int ap_search_leaf_export(ap_engine* e, int8_t* out_cells, int32_t* out_meta) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   return export_common(e, e->leaves.rows, e->leaves.meta, nullptr, e->geo.G, out_cells, out_meta);
 }
 
 int ap_search_leaf_features(ap_engine* e, float* out) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   size_t bytes = (size_t)e->geo.G * 9 * e->geo.S * 4;
   AP_TRY(ap_stage(e, bytes, 0));
   launch_boards_features(e, e->leaves.rows, e->leaves.meta, nullptr, e->geo.G, (float*)e->d_stage);
@@ -381,7 +381,7 @@ int ap_search_leaf_features(ap_engine* e, float* out) {
 
 int ap_search_expand_backup(ap_engine* e, const int32_t* counts, const int16_t* acts, const double* priors,
                             const double* values) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!counts || !acts || !priors || !values) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
   const size_t G = e->geo.G, S = e->geo.S;
   for (size_t g = 0; g < G; ++g)
@@ -401,7 +401,7 @@ int ap_search_expand_backup(ap_engine* e, const int32_t* counts, const int16_t* 
 }
 
 int ap_search_expand_backup_dense(ap_engine* e, const float* priors, const float* values) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!priors || !values) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
   const size_t G = e->geo.G, S = e->geo.S;
   AP_TRY(h2d(e, e->d_probs, priors, G * S * 4));
@@ -412,7 +412,7 @@ int ap_search_expand_backup_dense(ap_engine* e, const float* priors, const float
 }
 
 int ap_search_run(ap_engine* e, int32_t n_playout) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "ap_search_run: no net loaded (ap_net_load)");
   AP_TRY(drop_pure_trees(e));
   // phases per lock-step: select, features, one per trunk conv, heads, expand/backup
@@ -495,7 +495,7 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
 }
 
 int ap_search_profile(ap_engine* e, int32_t enable, float* out_ms, int32_t cap) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   e->profile = enable;
   int n = (int)e->prof_ms.size();
   if (out_ms)
@@ -504,7 +504,7 @@ int ap_search_profile(ap_engine* e, int32_t enable, float* out_ms, int32_t cap) 
 }
 
 int ap_search_timing(ap_engine* e, float* out_total_ms, float* out_net_ms) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (out_total_ms) *out_total_ms = e->last_total_ms;
   if (out_net_ms) *out_net_ms = e->last_net_ms;
   return AP_OK;
@@ -512,7 +512,7 @@ int ap_search_timing(ap_engine* e, float* out_total_ms, float* out_net_ms) {
 
 int ap_search_root(ap_engine* e, const int32_t* game_ids, int32_t n, int32_t* out_count, int16_t* out_acts,
                    int32_t* out_visits, double* out_q, int32_t* out_root_n) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_ids(e, game_ids, n));
   const size_t S = e->geo.S, nn = n;
   size_t o_cnt = 0, o_rn = o_cnt + ((nn * 4 + 15) & ~15ull), o_acts = o_rn + ((nn * 4 + 15) & ~15ull),
@@ -531,7 +531,7 @@ int ap_search_root(ap_engine* e, const int32_t* game_ids, int32_t n, int32_t* ou
 }
 
 int ap_search_root_probs(ap_engine* e, double temp, double* out) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!(temp > 0)) return ap_fail(e, AP_ERR_BAD_ARG, "temp must be > 0");
   size_t bytes = (size_t)e->geo.G * e->geo.S * 8;
   AP_TRY(ap_stage(e, bytes, 0));
@@ -542,7 +542,7 @@ int ap_search_root_probs(ap_engine* e, double temp, double* out) {
 
 int ap_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64_t seed, uint32_t ply, int32_t* out_moves,
                      float* out_pi, double* out_noise) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!(temp > 0) || eps < 0 || eps > 1 || !(alpha > 0)) return ap_fail(e, AP_ERR_BAD_ARG, "temp > 0, 0 <= eps <= 1, alpha > 0");
   if (!out_moves || !out_pi) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
   const size_t G = e->geo.G, S = e->geo.S;
@@ -559,7 +559,7 @@ int ap_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64
 }
 
 int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(drop_pure_trees(e));
   AP_TRY(ap_ids(e, game_ids, n));
   AP_TRY(ap_stage(e, sizeof(int32_t) * n, 0));
@@ -570,7 +570,7 @@ int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const in
 }
 
 int ap_search_stats(ap_engine* e, uint64_t* out5) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   unsigned long long h[8];
   AP_TRY(d2h_sync(e, h, e->stats, sizeof(h)));
   for (int i = 0; i < 6; ++i) out5[i] = h[i];
@@ -581,7 +581,7 @@ int ap_search_stats(ap_engine* e, uint64_t* out5) {
 // ---- mcts_pure ------------------------------------------------------------------------------
 
 int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_mode, int32_t* out_move) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (rollout_mode < 0 || rollout_mode > 2) return ap_fail(e, AP_ERR_BAD_ARG, "rollout_mode must be 0, 1 or 2");
   AP_TRY(ap_stage(e, 4 * (size_t)e->geo.G, 0));
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
@@ -599,7 +599,7 @@ int ap_rollout_eval(ap_engine* e, uint64_t seed, int8_t* out_value, int16_t* out
 }
 
 int ap_rollout_eval2(ap_engine* e, uint64_t seed, int32_t impl, int8_t* out_value, int16_t* out_plies) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (impl != 0 && impl != 2) return ap_fail(e, AP_ERR_BAD_ARG, "rollout impl must be 0 (permutation) or 2 (ply by ply)");
   const size_t G = e->geo.G;
   AP_TRY(ap_stage(e, 4 * G, 0));
@@ -615,7 +615,7 @@ int ap_rollout_eval2(ap_engine* e, uint64_t seed, int32_t impl, int8_t* out_valu
 }
 
 int ap_rollout_eval_keys(ap_engine* e, const uint32_t* keys, int8_t* out_value, int16_t* out_plies) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!keys || !out_value || !out_plies) return ap_fail(e, AP_ERR_BAD_ARG, "null argument");
   if (e->geo.W > 15) return ap_fail(e, AP_ERR_BAD_ARG, "the permutation rollout needs width <= 15");
   const size_t G = e->geo.G, kb = G * 256 * sizeof(uint32_t), vb = (G + 15) & ~15ull;
@@ -631,7 +631,7 @@ int ap_rollout_eval_keys(ap_engine* e, const uint32_t* keys, int8_t* out_value, 
 }
 
 int ap_rollout_hash(ap_engine* e, int8_t* out_value) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(ap_stage(e, e->geo.G, 0));
   launch_rollout_hash(e, (int8_t*)e->d_stage);
   AP_LAUNCH_CHECK(e);

@@ -531,7 +531,7 @@ static int conv_alloc(ap_engine* e, NetState* n, ConvLayer& L) {
 
 extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t n_filter, const ap_tensor* tensors,
                            int32_t n_tensors) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!tensors || n_tensors <= 0) return ap_fail(e, AP_ERR_BAD_ARG, "no tensors");
   if (e->geo.W != e->geo.H || e->geo.W > 15)
     return ap_fail(e, AP_ERR_BAD_ARG, "the net path needs a square board of width <= 15");
@@ -774,7 +774,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
 }
 
 extern "C" int ap_net_refresh(ap_engine* e) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
   AP_TRY(net_prep(e));
   AP_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -782,7 +782,7 @@ extern "C" int ap_net_refresh(ap_engine* e) {
 }
 
 extern "C" int ap_net_weights_ptr(ap_engine* e, void** out_dev_ptr, int64_t* out_numel) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
   *out_dev_ptr = e->net->master;
   *out_numel = e->net->master_numel;
@@ -790,7 +790,7 @@ extern "C" int ap_net_weights_ptr(ap_engine* e, void** out_dev_ptr, int64_t* out
 }
 
 extern "C" int ap_net_layout(ap_engine* e, int32_t cap, const char** out_names, int64_t* out_offsets, int64_t* out_numels) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "no net loaded");
   int n = (int)e->net->names.size();
   for (int i = 0; i < n && i < cap; ++i) {
@@ -928,7 +928,7 @@ int net_forward_leaves(ap_engine* e, int precise, bool compact, bool compacted_b
 }
 
 extern "C" int ap_net_forward_leaves(ap_engine* e, int32_t precise, float* out_probs, float* out_values) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   AP_TRY(net_forward_leaves(e, precise));
   const size_t G = e->geo.G, S = e->geo.S;
   if (out_probs) AP_CUDA(e, cudaMemcpyAsync(out_probs, e->d_probs, G * S * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -968,11 +968,11 @@ static int forward_host(ap_engine* e, const float* states, int32_t B, float* out
 }
 
 extern "C" int ap_net_forward(ap_engine* e, const float* states, int32_t B, float* out_probs, float* out_values) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   return forward_host(e, states, B, out_probs, out_values, 0);
 }
 
 extern "C" int ap_net_forward_precise(ap_engine* e, const float* states, int32_t B, float* out_probs, float* out_values) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   return forward_host(e, states, B, out_probs, out_values, 1);
 }

@@ -131,7 +131,7 @@ static void sym_src(int n, int k, int flip, int r, int c, int* sr, int* sc) {
 }
 
 extern "C" int ap_replay_create(ap_engine* e, int64_t maxlen) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   if (maxlen < 1) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_create: maxlen must be >= 1");
   if (e->geo.W != e->geo.H)
     return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_create: the rot90 augmentation needs a square board (train_mxnet.py:122-126)");
@@ -167,7 +167,7 @@ extern "C" int ap_replay_create(ap_engine* e, int64_t maxlen) {
 }
 
 extern "C" int ap_replay_push(ap_engine* e, const uint8_t* state_bits, const float* pi, const float* z, int32_t n) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   ReplayState* r = e->replay;
   if (!r) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_push: no replay ring (ap_replay_create)");
   if (n < 0 || (n && (!state_bits || !pi || !z))) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_push: bad argument");
@@ -189,7 +189,7 @@ extern "C" int ap_replay_push(ap_engine* e, const uint8_t* state_bits, const flo
 }
 
 extern "C" int ap_replay_size(ap_engine* e, int64_t* out_len, int64_t* out_total) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   ReplayState* r = e->replay;
   if (!r) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_size: no replay ring (ap_replay_create)");
   if (out_len) *out_len = r->total < r->maxlen ? r->total : r->maxlen;
@@ -199,7 +199,7 @@ extern "C" int ap_replay_size(ap_engine* e, int64_t* out_len, int64_t* out_total
 
 extern "C" int ap_replay_gather(ap_engine* e, const int64_t* idx, int32_t B, float* out_states, float* out_pi, float* out_z,
                                 int32_t out_on_device) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   ReplayState* r = e->replay;
   if (!r) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_gather: no replay ring (ap_replay_create)");
   if (B <= 0 || !idx || !out_states || !out_pi || !out_z) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_gather: bad argument");
@@ -239,7 +239,7 @@ extern "C" int ap_replay_gather(ap_engine* e, const int64_t* idx, int32_t B, flo
 
 extern "C" int ap_replay_push_sgf(ap_engine* e, const int16_t* moves, int32_t max_len, const int32_t* lengths,
                                   const int8_t* winners, int32_t n_games, uint8_t* out_warning) {
-  if (!e) return AP_ERR_BAD_HANDLE;
+  AP_ENTER(e);
   ReplayState* r = e->replay;
   if (!r) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_push_sgf: no replay ring (ap_replay_create)");
   if (n_games <= 0 || max_len <= 0 || !moves || !lengths || !winners)

@@ -20,8 +20,10 @@ from .selfplay import BatchedSelfPlay
 
 
 def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, c_puct=5, temp=1.0, batch_size=128,
-                        epochs=8, learn_rate=4e-4, buffer_size=2198800, n_in_row=5, seed=0, log=None):
-    """Returns a dict of counters / timings (per rank; wall clock)."""
+                        epochs=8, learn_rate=4e-4, buffer_size=2198800, n_in_row=5, seed=0, log=None, device_pick=False):
+    """Returns a dict of counters / timings (per rank; wall clock).  device_pick: moves sampled on the device with
+    the next ply's search overlapped with the host bookkeeping (``BatchedSelfPlay(device_pick=True)``); the search in
+    flight is joined before the weights change, so it is one ply stale at most."""
     import torch
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -29,7 +31,7 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
     world = dist.get_world_size() if multi else 1
     S = net.board_width * net.board_height
     sp = BatchedSelfPlay(net, n_games, n_playout=n_playout, c_puct=c_puct, temp=temp, n_in_row=n_in_row,
-                         seed=seed + 1000 * rank)
+                         seed=seed + 1000 * rank, device_pick=device_pick)
     ring = ReplayBuffer(net._eng, buffer_size) if rank == 0 else None
     if multi:
         apdist.broadcast_weights(net, src=0)  # identical start
@@ -44,6 +46,7 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
                 out["games"] += 1
                 if states is not None:
                     packed.append(apdist.pack_records(states, pis, zs, S))
+        sp.drain()  # nothing may search while the weights are trained / broadcast
         out["plies"] += plies_per_iter * n_games
         out["playouts"] += plies_per_iter * n_games * n_playout
         mine = np.concatenate(packed, axis=0) if packed else np.zeros((0, apdist.record_width(S)), np.uint8)

@@ -21,6 +21,7 @@ ap.add_argument("--arch", default="simple")
 ap.add_argument("--blocks", type=int, default=10)
 ap.add_argument("--epochs", type=int, default=8)
 ap.add_argument("--batch", type=int, default=128)
+ap.add_argument("--device-pick", action="store_true", help="sample the self-play moves on the device (ap_selfplay_pick)")
 a = ap.parse_args()
 
 import torch  # noqa: E402
@@ -39,7 +40,7 @@ else:
     from alphapig_b200.policy_value_net_mxnet import PolicyValueNet
     net = PolicyValueNet(a.board, a.board, batch_size=a.batch, n_blocks=a.blocks, device=local, seed=0)
 res = selfplay_train_loop(net, a.games, a.iters, plies_per_iter=a.plies, n_playout=a.playouts, batch_size=a.batch,
-                          epochs=a.epochs, log=lambda s: print(s, file=sys.stderr))
+                          epochs=a.epochs, log=lambda s: print(s, file=sys.stderr), device_pick=a.device_pick)
 t = torch.tensor([res["t_selfplay"] + res["t_exchange"] + res["t_train"], res["t_selfplay"], res["t_exchange"], res["t_train"]],
                  dtype=torch.float64, device="cuda")
 cnt = torch.tensor([res["plies"], res["playouts"], res["games"]], dtype=torch.float64, device="cuda")
