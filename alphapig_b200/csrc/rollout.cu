@@ -1,11 +1,13 @@
 // mcts_pure on device: whole searches (n_playout playouts incl. random rollouts) in one launch,
 // one CTA (= one warp) per game.  Replaces reference mcts_pure.MCTS (mcts_pure.py:96-182).
+// Random rollouts are drawn as one random permutation of the empty cells + a bit descent to the first completed line
+// (rollout_eval_perm), the tree keeps children lazy (pure_select_child); DESIGN.md 3.5 has the measurements.
 #include "kernels.h"
 #include "tree.cuh"
 
 // resident CTAs (= games) per SM the pure kernel is compiled for (register budget 65536 / (32 * N)).  Measured on
-// B200, configs[2]: 24 (80 registers, no spills) 267 M playouts/s; the kernel is issue-bound (71 % issue-active
-// under ncu), so more resident warps at the price of spills do not pay.  A variant that kept the root's children
+// B200, configs[2]: 24 (80 registers, no spills) is the best of 32 / 28 / 24 / 20; the kernel is issue-bound
+// (73 % issue-active under ncu), so more resident warps at the price of spills do not pay.  A variant that kept the root's children
 // in shared memory executed 16 % more instructions and was 13 % slower - the children blocks are L2-resident anyway.
 #ifndef AP_PURE_MINBLK
 #define AP_PURE_MINBLK 24

@@ -3,9 +3,11 @@
 ``MCTSPlayer(c_puct, n_playout).get_action(board)`` runs the whole pure-MCTS move search --
 n_playout x (select, uniform-prior expand, uniformly random rollout to the end of the game,
 backup) -- in ONE kernel launch, one CTA per game (csrc/rollout.cu), and returns the most visited
-root action (first maximum, mcts_pure.py:168-169).  The rollout RNG is a device PCG stream seeded
+root action (first maximum, mcts_pure.py:168-169).  The rollouts draw from device Philox streams seeded
 from ``numpy.random`` (the reference draws ``np.random.rand`` per ply, mcts_pure.py:16; its MT19937
-sequence is not reproduced -- the rollout is distributionally equivalent).
+sequence is not reproduced): each rollout is one random permutation of the empty cells and a bit descent to
+the first completed line -- the same distribution of results and game lengths as playing ply by ply, pinned
+exactly with injected draws and statistically against a NumPy reference sample.
 """
 import numpy as np
 
