@@ -130,3 +130,19 @@ def rollout_sample_numpy(board, n_samples, rs, chunk=20000):
         plies.append(np.where(tie, E, t + 1))
         vals.append(np.where(tie, 0, np.where(t % 2 == 0, 1, -1)))
     return np.concatenate(vals), np.concatenate(plies)
+
+
+def philox4x32_10(counter, key, rounds=10):
+    """Philox4x32 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) exactly as
+    ``csrc/rollout.cu:philox4x32_10`` / ``csrc/tree.cu:philox_pick`` code it (multipliers, Weyl key bumps after the
+    round); ``tests/test_cpu_host.py`` checks it against the Random123 known-answer vectors."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = counter
+    k0, k1 = key
+    for _ in range(rounds):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0 = p0 >> 32, p0 & 0xFFFFFFFF
+        hi1, lo1 = p1 >> 32, p1 & 0xFFFFFFFF
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & 0xFFFFFFFF, lo1, (hi0 ^ c3 ^ k1) & 0xFFFFFFFF, lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3

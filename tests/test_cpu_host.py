@@ -296,3 +296,16 @@ def test_vectorised_rollout_sampler_equals_play():
         for i in range(60):
             order = empties[np.argsort(rp.keys[i])]
             assert (int(v[i]), int(p[i])) == rollout_by_play(b, order)
+
+
+def test_philox_known_answers():
+    """The Philox4x32-10 round structure the device rollouts and the self-play move sampling use (restated in
+    oracle/rollout.py with the same constants and key schedule as csrc/rollout.cu) reproduces the Random123
+    known-answer vectors."""
+    from oracle.rollout import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert philox4x32_10(ctr, key) == want
