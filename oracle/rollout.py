@@ -146,3 +146,42 @@ def philox4x32_10(counter, key, rounds=10):
         c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & 0xFFFFFFFF, lo1, (hi0 ^ c3 ^ k1) & 0xFFFFFFFF, lo0
         k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
     return c0, c1, c2, c3
+
+
+def device_move_order(board, seed, g, playout=0):
+    """The move order the device's permutation rollout plays for game ``g`` from ``board`` (a 15-wide-or-narrower
+    position): ``csrc/rollout.cu:perm_draws`` gives board slot (lane, r) the 24 high bits of word r of two
+    Philox4x32-10 blocks (counter (playout, block, g, lane), key = the 64-bit seed); slot (lane, r) is board row
+    lane // 2, column rank_slot((lane % 2) * 8 + r); the empty cells are played in ascending (draw, slot) order."""
+    W = board.width
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    draw = {}
+    for lane in range(32):
+        words = philox4x32_10((playout, 0, g, lane), key) + philox4x32_10((playout, 1, g, lane), key)
+        for r in range(8):
+            q = (lane & 1) * 8 + r
+            col = ((q & 3) << 2) | (q >> 2)
+            draw[(lane >> 1, col)] = (min(words[r] >> 8, 0xFFFFFE), lane * 8 + r)
+    return sorted(board.availables, key=lambda m: draw[(m // W, m % W)])
+
+
+def device_perm_rollout(board, seed, g, playout=0):
+    """Exact host model of ``ap_rollout_eval`` (impl 0) for game ``g``: (value, plies), RNG included."""
+    end, winner = board.game_end()
+    if end:
+        return (0 if winner == -1 else (1 if winner == board.get_current_player() else -1)), 0
+    return rollout_by_play(board, device_move_order(board, seed, g, playout))
+
+
+def outcomes_from_ranks_numpy(full, n_empty, W, H, n):
+    """Vectorised ``rollout_by_play`` for many positions at once.  full: int16 [G][S], -2 / -1 for the stones of the
+    side to move / its opponent, else the ply index (rank) at which the empty cell is played.  Returns (values for the
+    side to move, plies).  Same window rule as ``rollout_sample_numpy``."""
+    import numpy as np
+    wins = line_windows(W, H, n)
+    r = full[:, wins]
+    par = r & 1
+    same = (par == par[:, :, :1]).all(axis=2)
+    t = np.where(same, r.max(axis=2), 30000).min(axis=1)
+    tie = t >= 30000
+    return np.where(tie, 0, np.where(t % 2 == 0, 1, -1)), np.where(tie, n_empty, t + 1)

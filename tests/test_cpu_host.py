@@ -309,3 +309,47 @@ def test_philox_known_answers():
             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
     for ctr, key, want in kat:
         assert philox4x32_10(ctr, key) == want
+
+
+def test_device_rollout_model_reproduces_logged_device_run():
+    """The exact host model of the device rollouts (oracle/rollout.py: Philox draws + slot order) against a LOGGED
+    B200 run: profiles/r1_pure_ab.txt records `ap_rollout_eval(seed=19)` over the 8192 SURVEY 8(d) bench positions as
+    "mean plies 79.4, mean value 0.0439"; the model must print the same (a value mean of 0.0439 over 8192 games pins
+    the sum of the values to exactly 360).  The per-game equality is the GPU test
+    test_rollout_eval_matches_host_model_exactly."""
+    import re
+    import bench
+    from oracle.board import OBoard
+    from oracle.rollout import outcomes_from_ranks_numpy, philox4x32_10
+    line = [ln for ln in open(os.path.join(ROOT, "profiles", "r1_pure_ab.txt")) if ln.startswith("rollout_eval impl 0")][0]
+    want_plies, want_value = re.search(r"mean plies ([\d.]+), mean value ([-\d.]+)", line).groups()
+    W = H = 15
+    G, seed = 8192, 19
+    full = np.zeros((G, W * H), np.int16)
+    n_empty = np.zeros(G, np.int64)
+    for g in range(G):
+        rs = np.random.RandomState(1234 + g)
+        while True:  # bench.synthetic_positions: redraw positions whose random play already ended the game
+            cells, meta = bench.draw_position(rs)
+            b = OBoard(W, H, 5)
+            b.init_board(0)
+            b.states = {int(m): int(cells[m]) for m in np.nonzero(cells)[0]}
+            b.availables = [m for m in range(W * H) if m not in b.states]
+            if not b.game_end()[0]:
+                break
+        key = (seed & 0xFFFFFFFF, seed >> 32)
+        draw = np.zeros(W * H, np.int64)
+        for lane in range(30):  # rows 0..14 = lanes 0..29
+            words = philox4x32_10((0, 0, g, lane), key) + philox4x32_10((0, 1, g, lane), key)
+            for r in range(8):
+                q = (lane & 1) * 8 + r
+                col = ((q & 3) << 2) | (q >> 2)
+                if col < W:
+                    draw[(lane >> 1) * W + col] = (min(words[r] >> 8, 0xFFFFFE) << 8) | (lane * 8 + r)
+        empties = np.array(b.availables)
+        full[g] = np.where(cells == 1, -2, -1)  # side to move is always player 1 in these positions
+        full[g, empties[np.argsort(draw[empties])]] = np.arange(len(empties))
+        n_empty[g] = len(empties)
+    v, p = outcomes_from_ranks_numpy(full, n_empty, W, H, 5)
+    assert "%.1f" % p.mean() == want_plies and "%.4f" % v.mean() == want_value, (p.mean(), v.mean(), line)
+    assert int(v.sum()) == 360

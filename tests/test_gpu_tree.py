@@ -347,3 +347,26 @@ def test_pool_exhaustion_is_reported():
         host_playouts(eng, [root], EVALUATORS["e1"], 5)
     assert ei.value.code == -3
     eng.close()
+
+
+def test_rollout_eval_matches_host_model_exactly():
+    """ap_rollout_eval with the device's OWN random numbers: oracle/rollout.py:device_perm_rollout restates the
+    Philox4x32-10 draws, the slot mapping and the (draw, slot) ordering of csrc/rollout.cu and plays that order move
+    by move on the oracle board (mcts_pure.py:138-157) - value and game length of every game must be identical."""
+    import bench
+    from oracle.rollout import device_perm_rollout
+    from oracle.board import OBoard
+    W = H = 15
+    G = 256
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, n_playout=1, node_capacity=4)
+    cells, meta = bench.synthetic_positions(eng, G)
+    for seed in (19, (7 << 32) + 3):
+        v, p = eng.rollout_eval(seed=seed, impl=0)
+        for g in range(G):
+            b = OBoard(W, H, 5)
+            b.init_board(0)
+            b.states = {int(m): int(cells[g, m]) for m in np.nonzero(cells[g])[0]}
+            b.availables = [m for m in range(W * H) if m not in b.states]
+            b.current_player, b.last_move = int(meta[g, 0]), int(meta[g, 1])
+            assert (int(v[g]), int(p[g])) == device_perm_rollout(b, seed, g), (seed, g)
+    eng.close()
