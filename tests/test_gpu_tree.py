@@ -370,3 +370,33 @@ def test_rollout_eval_matches_host_model_exactly():
             b.current_player, b.last_move = int(meta[g, 0]), int(meta[g, 1])
             assert (int(v[g]), int(p[g])) == device_perm_rollout(b, seed, g), (seed, g)
     eng.close()
+
+
+@pytest.mark.skipif(not os.environ.get("AP_TEST_UNVERIFIED"), reason="written after the round's GPU budget was spent: "
+                    "enable with AP_TEST_UNVERIFIED=1, verify on a B200, then drop the guard (DESIGN 9.3)")
+def test_pure_run_random_rollouts_match_host_model_exactly():
+    """ap_pure_run in rollout_mode 0 (the real mcts_pure configuration): with the device's rollouts predicted
+    exactly on the host (oracle/rollout.py:device_perm_rollout, draws keyed by (seed, game, playout)), the oracle's
+    OPureMCTS must reproduce the device's root visit counts, Q and chosen moves bit for bit."""
+    from oracle.rollout import device_perm_rollout
+    W = H = 15
+    G, n_playout, seed = 6, 300, 11
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, c_puct=5, n_playout=n_playout)
+    roots = [oboard_from(W, H, 5, synth_position(W, H, 5, 1234 + i)) for i in range(G)]
+    ex = [export_oboard(b) for b in roots]
+    eng.boards_import(np.stack([c for c, _ in ex]), np.stack([m for _, m in ex]))
+    moves = eng.pure_run(n_playout, seed=seed, rollout_mode=0)
+    count, acts, visits, q, rootn = eng.search_root(want_q=True)
+    for g in range(G):
+        it = [0]
+
+        def rollout(state, g=g, it=it):
+            v, _ = device_perm_rollout(state, seed, g, playout=it[0])
+            it[0] += 1
+            return v
+
+        o = OPureMCTS(pure_policy_value_fn, 5, n_playout, rollout_fn=rollout)
+        assert o.get_move(roots[g]) == moves[g]
+        assert list(visits[g, :count[g]]) == [nd.N for nd in o.root.children.values()]
+        assert list(q[g, :count[g]]) == [float(nd.Q) for nd in o.root.children.values()]
+    eng.close()
