@@ -43,6 +43,7 @@ SIGNATURES = {
     "ap_version": (C.c_char_p, []),
     "ap_sync": (C.c_int, [_P]),
     "ap_engine_memory": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "ap_engine_node_capacity": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "ap_boards_reset": (C.c_int, [_P, _P, _I, _P]),
     "ap_boards_do_move": (C.c_int, [_P, _P, _P, _I, _P]),
     "ap_boards_status": (C.c_int, [_P, _P, _I, _P, _P]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "ap_search_root": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "ap_search_root_probs": (C.c_int, [_P, C.c_double, _P]),
     "ap_search_advance": (C.c_int, [_P, _P, _I, _P]),
+    "ap_search_set_active": (C.c_int, [_P, _P]),
     "ap_search_stats": (C.c_int, [_P, _P]),
     "ap_selfplay_pick": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32, _P, _P, _P]),
     "ap_pure_run": (C.c_int, [_P, _I, C.c_uint64, _I, _P]),

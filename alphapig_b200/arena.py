@@ -35,7 +35,9 @@ def batched_arena(net, n_games, n_playout=400, c_puct=5, pure_n_playout=1000, n_
         to_move = 1 if first == 0 else 2
         S = W * H
         while live.any():
+            # finished games cost nothing: both search kernels skip them (ap_search_set_active)
             if to_move == 1:
+                az.search_set_active(live)
                 az.search_advance(-1)
                 az.search_run(n_playout)
                 count, acts, visits, _, _ = az.search_root()
@@ -47,6 +49,7 @@ def batched_arena(net, n_games, n_playout=400, c_puct=5, pure_n_playout=1000, n_
             else:
                 cells, meta = az.boards_export()
                 pure.boards_import(cells, meta)
+                pure.search_set_active(live)
                 moves = pure.pure_run(pure_n_playout, seed=int(rs.randint(0, 2 ** 31 - 1)), rollout_mode=0).astype(np.int32)
             lid = np.nonzero(live)[0].astype(np.int32)
             az.boards_do_move(moves[lid], lid)
@@ -56,5 +59,6 @@ def batched_arena(net, n_games, n_playout=400, c_puct=5, pure_n_playout=1000, n_
             live &= ~end
             to_move = 3 - to_move
         winners[ids] = win
+        az.search_set_active(None)
         pure.close()
     return winners

@@ -56,6 +56,8 @@ struct Leaves {
   int32_t* slot;          // [G] net tile of game g, -1 = terminal leaf
   int32_t* game_of_slot;  // [G]
   int32_t* n_eval;        // [1] non-terminal leaves of the last compaction
+  // ap_search_set_active: games with active[g] == 0 are skipped by every search kernel (finished arena games)
+  const uint8_t* active;  // [G]
 };
 
 struct NetState;     // net.cu
@@ -94,6 +96,13 @@ struct ap_engine {
   // reference's mcts_pure never reuses a tree (get_action ends with update_with_move(-1), mcts_pure.py:196-203), so
   // the next tree operation other than reading the root starts from fresh roots
   bool pure_tree = false;
+  // node pools.  cap_auto: the capacity was picked by the library (cfg.node_capacity <= 0) and GROWS on demand - the
+  // reference's trees are unbounded Python objects and a re-rooted subtree keeps accumulating visits over the plies of
+  // a game (root N -> n_playout / (1 - share of the chosen child)), so no fixed bound is safe for self-play with tree
+  // reuse.  An explicit capacity is a hard limit (AP_ERR_POOL_EXHAUSTED when a game runs over it).
+  bool cap_auto = false;
+  uint64_t pool_generation = 0;  // bumped when the pools move (captured graphs hold the old pointers)
+  int32_t* d_max_alloc = nullptr;
   // small batches (interactive play: one game) are launch-latency bound: the n_playout lock-steps of ap_search_run are
   // captured once into a CUDA graph and replayed; rebuilt when n_playout or the prepared weights change
   cudaGraphExec_t run_graph = nullptr;

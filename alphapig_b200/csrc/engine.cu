@@ -80,6 +80,83 @@ static int check_errflags(ap_engine* e) {
   return AP_OK;
 }
 
+static void dev_free(ap_engine* e, void* p, size_t bytes) {
+  if (!p) return;
+  auto it = std::find(e->allocs.begin(), e->allocs.end(), p);
+  if (it != e->allocs.end()) e->allocs.erase(it);
+  cudaFree(p);
+  e->bytes -= bytes;
+}
+static size_t pool_bytes(size_t G, size_t cap) { return G * cap * 32; }
+
+static int alloc_pools(ap_engine* e, int cap, Pools* pl, void** scratch) {
+  const size_t G = e->geo.G, N = G * (size_t)cap;
+  AP_TRY(dev_alloc(e, (void**)&pl->P, N * 8));
+  AP_TRY(dev_alloc(e, (void**)&pl->Q, N * 8));
+  AP_TRY(dev_alloc(e, (void**)&pl->N, N * 4));
+  AP_TRY(dev_alloc(e, (void**)&pl->child_start, N * 4));
+  AP_TRY(dev_alloc(e, (void**)&pl->parent, N * 4));
+  AP_TRY(dev_alloc(e, (void**)&pl->child_count, N * 2));
+  AP_TRY(dev_alloc(e, (void**)&pl->move, N * 2));
+  AP_TRY(dev_alloc(e, (void**)&pl->alloc, G * 4));
+  AP_TRY(dev_alloc(e, scratch, (size_t)e->scratch_slots * scratch_bytes_per_slot(cap)));
+  return AP_OK;
+}
+static void free_pools(ap_engine* e, int cap, Pools* pl, void* scratch) {
+  const size_t G = e->geo.G, N = G * (size_t)cap;
+  dev_free(e, pl->P, N * 8);
+  dev_free(e, pl->Q, N * 8);
+  dev_free(e, pl->N, N * 4);
+  dev_free(e, pl->child_start, N * 4);
+  dev_free(e, pl->parent, N * 4);
+  dev_free(e, pl->child_count, N * 2);
+  dev_free(e, pl->move, N * 2);
+  dev_free(e, pl->alloc, G * 4);
+  dev_free(e, scratch, (size_t)e->scratch_slots * scratch_bytes_per_slot(cap));
+  *pl = Pools{};
+}
+
+// Make room for `need_free` more nodes in every game's pool.  Library-chosen capacities grow (the reference's trees
+// are unbounded); an explicit node_capacity is a hard limit and a game that runs over it reports
+// AP_ERR_POOL_EXHAUSTED from the expanding kernel.  One 4-byte D2H per call.
+static int ensure_pool(ap_engine* e, long long need_free) {
+  if (!e->cap_auto) return AP_OK;
+  int32_t mx = 0;
+  launch_max_alloc(e, e->d_max_alloc);
+  AP_LAUNCH_CHECK(e);
+  AP_TRY(d2h_sync(e, &mx, e->d_max_alloc, 4));
+  const long long need = (long long)mx + need_free;
+  if (need <= e->geo.cap) return AP_OK;
+  long long want = std::max(need, (long long)e->geo.cap * 3 / 2);
+  want = (want + 3) & ~3ll;
+  const size_t G = e->geo.G;
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  auto cost = [&](long long c) { return pool_bytes(G, (size_t)c) + (size_t)e->scratch_slots * scratch_bytes_per_slot((int)c); };
+  const size_t margin = (size_t)1 << 30;
+  if (cost(want) + margin > fr) want = (need + 3) & ~3ll;  // no head-room: take exactly what this search needs
+  if (cost(want) + margin > fr || want > (1ll << 26))
+    return ap_fail(e, AP_ERR_POOL_EXHAUSTED,
+                   "node pools cannot grow to " + std::to_string(want) + " nodes per game (" +
+                       std::to_string(cost(want) >> 20) + " MiB needed, " + std::to_string(fr >> 20) + " MiB free)");
+  Pools np{};
+  void* nscratch = nullptr;
+  const int rc = alloc_pools(e, (int)want, &np, &nscratch);
+  if (rc != AP_OK) {
+    free_pools(e, (int)want, &np, nscratch);
+    return ap_fail(e, AP_ERR_POOL_EXHAUSTED, "node pools cannot grow: " + e->err);
+  }
+  launch_pool_copy(e, e->pools, e->geo.cap, np, (int)want);
+  AP_LAUNCH_CHECK(e);
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  free_pools(e, e->geo.cap, &e->pools, e->scratch);
+  e->pools = np;
+  e->scratch = nscratch;
+  e->geo.cap = (int)want;
+  e->pool_generation++;
+  return AP_OK;
+}
+
 void prof_mark(ap_engine* e) {
   if (!e->profile) return;
   if ((size_t)e->prof_cursor < e->prof_events.size()) cudaEventRecord(e->prof_events[e->prof_cursor++], e->stream);
@@ -114,8 +191,10 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
   g.G = cfg->n_games;
   g.c_puct = cfg->c_puct;
   int cap = cfg->node_capacity;
+  e->cap_auto = cap <= 0;
   if (cap <= 0) {
-    // every playout adds at most S children; a re-rooted subtree can retain about one search's worth
+    // every playout adds at most S children; a re-rooted subtree usually retains about one search's worth - when a
+    // game keeps more (ensure_pool) the pools grow
     long long want = 2ll * std::max(cfg->n_playout_hint, 1) * g.S + g.S + 2;
     cap = (int)std::min<long long>(want, 1 << 20);
   }
@@ -131,19 +210,14 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
     return code;
   };
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(AP_ERR_CUDA);
-  const size_t G = g.G, N = G * (size_t)cap;
+  const size_t G = g.G;
 #define ALLOC(ptr, bytes) \
   if ((rc = dev_alloc(e, (void**)&(ptr), (bytes))) != AP_OK) return fail(rc)
   ALLOC(e->rows, G * AP_ROWS * 4);
   ALLOC(e->meta, G * sizeof(BoardMeta));
-  ALLOC(e->pools.P, N * 8);
-  ALLOC(e->pools.Q, N * 8);
-  ALLOC(e->pools.N, N * 4);
-  ALLOC(e->pools.child_start, N * 4);
-  ALLOC(e->pools.parent, N * 4);
-  ALLOC(e->pools.child_count, N * 2);
-  ALLOC(e->pools.move, N * 2);
-  ALLOC(e->pools.alloc, G * 4);
+  e->scratch_slots = (int)std::min<size_t>(G, 296);
+  if ((rc = alloc_pools(e, g.cap, &e->pools, &e->scratch)) != AP_OK) return fail(rc);
+  ALLOC(e->d_max_alloc, 4);
   ALLOC(e->leaves.rows, G * AP_ROWS * 4);
   ALLOC(e->leaves.meta, G * sizeof(BoardMeta));
   ALLOC(e->leaves.node, G * 4);
@@ -154,13 +228,17 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
   ALLOC(e->leaves.slot, G * 4);
   ALLOC(e->leaves.game_of_slot, G * 4);
   ALLOC(e->leaves.n_eval, 4);
+  {
+    uint8_t* act = nullptr;
+    ALLOC(act, G);
+    cudaMemsetAsync(act, 1, G, e->stream);
+    e->leaves.active = act;
+  }
   ALLOC(e->errflag, G * 4);
   ALLOC(e->stats, 8 * 8);
   ALLOC(e->d_ids, G * 4);
   ALLOC(e->d_probs, G * (size_t)g.S * 4);
   ALLOC(e->d_values, G * 4);
-  e->scratch_slots = (int)std::min<size_t>(G, 296);
-  ALLOC(e->scratch, (size_t)e->scratch_slots * scratch_bytes_per_slot(cap));
 #undef ALLOC
   cudaEventCreate(&e->ev0);
   cudaEventCreate(&e->ev1);
@@ -176,6 +254,12 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
     return fail(AP_ERR_CUDA);
   }
   *out = e;
+  return AP_OK;
+}
+
+int ap_engine_node_capacity(const ap_engine* e, int32_t* out_nodes) {
+  if (!e || !out_nodes) return AP_ERR_BAD_HANDLE;
+  *out_nodes = e->geo.cap;
   return AP_OK;
 }
 
@@ -354,6 +438,7 @@ static int drop_pure_trees(ap_engine* e) {
 int ap_search_select(ap_engine* e, uint8_t* out_terminal, int32_t* out_depth, int16_t* out_path) {
   AP_ENTER(e);
   AP_TRY(drop_pure_trees(e));
+  AP_TRY(ensure_pool(e, e->geo.S));
   launch_select(e);
   AP_LAUNCH_CHECK(e);
   const int G = e->geo.G;
@@ -415,6 +500,7 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
   AP_ENTER(e);
   if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "ap_search_run: no net loaded (ap_net_load)");
   AP_TRY(drop_pure_trees(e));
+  AP_TRY(ensure_pool(e, (long long)n_playout * e->geo.S));
   // phases per lock-step: select, features, one per trunk conv, heads, expand/backup
   const int phases = net_phase_count(e) + 2;
   if (e->profile) {
@@ -449,7 +535,7 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
     return AP_OK;
   };
   const bool use_graph = !e->profile && e->geo.G <= graph_max_games && n_playout >= 4;
-  if (use_graph && (!e->run_graph || e->run_graph_playouts != n_playout || e->run_graph_gen != e->net_generation)) {
+  if (use_graph && (!e->run_graph || e->run_graph_playouts != n_playout || e->run_graph_gen != e->net_generation + (e->pool_generation << 32))) {
     if (e->run_graph) cudaGraphExecDestroy(e->run_graph);
     e->run_graph = nullptr;
     const uint64_t l0 = e->launches;
@@ -468,7 +554,7 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
     e->run_graph_launches = e->launches - l0;
     e->launches = l0;  // counted per replay below
     e->run_graph_playouts = n_playout;
-    e->run_graph_gen = e->net_generation;
+    e->run_graph_gen = e->net_generation + (e->pool_generation << 32);
   }
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   prof_mark(e);
@@ -569,6 +655,19 @@ int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const in
   return ap_sync(e);
 }
 
+int ap_search_set_active(ap_engine* e, const uint8_t* active) {
+  AP_ENTER(e);
+  uint8_t* d = const_cast<uint8_t*>(e->leaves.active);
+  if (!active) {
+    AP_CUDA(e, cudaMemsetAsync(d, 1, e->geo.G, e->stream));
+  } else {
+    std::vector<uint8_t> a(e->geo.G);
+    for (int g = 0; g < e->geo.G; ++g) a[g] = active[g] ? 1 : 0;
+    AP_CUDA(e, cudaMemcpyAsync(d, a.data(), a.size(), cudaMemcpyHostToDevice, e->stream));
+  }
+  return ap_sync(e);
+}
+
 int ap_search_stats(ap_engine* e, uint64_t* out5) {
   AP_ENTER(e);
   unsigned long long h[8];
@@ -584,6 +683,12 @@ int ap_pure_run(ap_engine* e, int32_t n_playout, uint64_t seed, int32_t rollout_
   AP_ENTER(e);
   if (rollout_mode < 0 || rollout_mode > 2) return ap_fail(e, AP_ERR_BAD_ARG, "rollout_mode must be 0, 1 or 2");
   AP_TRY(ap_stage(e, 4 * (size_t)e->geo.G, 0));
+  if (e->cap_auto && 1ll + (long long)n_playout * e->geo.S > e->geo.cap) {
+    // the fused kernel starts every game from a fresh root: drop the trees, then grow the empty pools
+    launch_tree_reset_all(e);
+    AP_LAUNCH_CHECK(e);
+    AP_TRY(ensure_pool(e, (long long)n_playout * e->geo.S));
+  }
   AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   launch_pure_run(e, n_playout, seed, rollout_mode, (int32_t*)e->d_stage);
   AP_LAUNCH_CHECK(e);

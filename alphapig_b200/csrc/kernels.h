@@ -29,6 +29,8 @@ void launch_root(ap_engine* e, const int32_t* d_ids, int n, int32_t* d_count, in
                  double* d_q, int32_t* d_rootn);
 void launch_root_probs(ap_engine* e, double temp, double* d_out);
 size_t scratch_bytes_per_slot(int cap);
+void launch_max_alloc(ap_engine* e, int32_t* d_out);
+void launch_pool_copy(ap_engine* e, const Pools& from, int from_cap, const Pools& to, int to_cap);
 
 // rollout.cu
 void launch_pure_run(ap_engine* e, int n_playout, uint64_t seed, int mode, int32_t* d_move);

@@ -416,7 +416,12 @@ __device__ __forceinline__ int wb_kth_legal(const WBoard& b, int k, int W, int H
 template <int MODE>  // 0 = permutation rollouts (W <= 15), 1 = position hash, 2 = ply-by-ply rollouts
 __global__ void __launch_bounds__(32, AP_PURE_MINBLK)
 k_pure_run(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, int n_playout,
-           unsigned long long seed, int32_t* out_move, int32_t* errflag, unsigned long long* stats) {
+           unsigned long long seed, int32_t* out_move, int32_t* errflag, unsigned long long* stats,
+           const uint8_t* __restrict__ active) {
+  if (!active[blockIdx.x]) {  // skipped game (ap_search_set_active): no search, no move
+    if (threadIdx.x == 0) out_move[blockIdx.x] = -1;
+    return;
+  }
   __shared__ int16_t s_list[AP_MAX_S];
   __shared__ __align__(16) uint8_t s_rank[256];
   __shared__ int s_path[AP_MAX_S + 1];
@@ -632,7 +637,8 @@ __global__ void k_rollout_hash(Geo geo, const uint32_t* rows, const BoardMeta* m
 void launch_pure_run(ap_engine* e, int n_playout, uint64_t seed, int mode, int32_t* d_move) {
   if (mode == 0 && e->geo.W > 15) mode = 2;  // the packed two-colour line check needs a spare column bit
   auto k = (mode == 0) ? k_pure_run<0> : (mode == 1) ? k_pure_run<1> : k_pure_run<2>;
-  k<<<e->geo.G, 32, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, n_playout, seed, d_move, e->errflag, e->stats);
+  k<<<e->geo.G, 32, 0, e->stream>>>(e->geo, e->rows, e->meta, e->pools, n_playout, seed, d_move, e->errflag, e->stats,
+                                  e->leaves.active);
 }
 void launch_rollout_eval(ap_engine* e, uint64_t seed, int impl, const uint32_t* d_keys, int8_t* d_value, int16_t* d_plies) {
   k_rollout_eval<<<(e->geo.G + 3) / 4, 128, 0, e->stream>>>(e->geo, e->rows, e->meta, seed, impl, d_keys, d_value,

@@ -27,6 +27,16 @@ k_select(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict
   int lane = threadIdx.x & 31;
   int g = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
   if (g >= geo.G) return;
+  if (!lv.active[g]) {  // skipped game: no leaf, no net tile, nothing for k_expand_backup to do
+    if (lane == 0) {
+      lv.node[g] = -1;
+      lv.terminal[g] = 1;
+      lv.winner[g] = -1;
+      lv.depth[g] = 0;
+      lv.slot[g] = -1;
+    }
+    return;
+  }
   size_t base = (size_t)g * geo.cap;
   WBoard b = wb_load(rows, meta, g, lane);
   int node = 0, depth = 0;
@@ -89,6 +99,10 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
   if (g >= geo.G) return;
   size_t base = (size_t)g * geo.cap;
   int leaf = lv.node[g];
+  if (leaf < 0) {  // skipped game (ap_search_set_active)
+    if (slot && g == 0 && lane == 0) *lv.n_eval = 0;
+    return;
+  }
   double v;
   float fused_v = 0.f;
   if (!lv.terminal[g]) {
@@ -470,6 +484,39 @@ k_selfplay_pick(Geo geo, Pools pl, double temp, double eps, double alpha, unsign
     }
   }
   if (lane == 0) out_move[g] = pl.move[base + cs + chosen];
+}
+
+// largest number of nodes in use over all games (pool growth check)
+__global__ void k_max_alloc(int G, const int32_t* __restrict__ alloc, int32_t* out) {
+  int m = 0;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) m = max(m, alloc[g]);
+  for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(AP_FULL, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+// move every game's nodes [0, alloc[g]) into pools of a larger per-game stride; node indices are relative to the
+// game's base, so no field changes
+__global__ void k_pool_copy(int G, Pools from, int from_cap, Pools to, int to_cap) {
+  const int g = blockIdx.x;
+  const int n = from.alloc[g];
+  const size_t a = (size_t)g * from_cap, b = (size_t)g * to_cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    to.P[b + i] = from.P[a + i];
+    to.Q[b + i] = from.Q[a + i];
+    to.N[b + i] = from.N[a + i];
+    to.child_start[b + i] = from.child_start[a + i];
+    to.parent[b + i] = from.parent[a + i];
+    to.child_count[b + i] = from.child_count[a + i];
+    to.move[b + i] = from.move[a + i];
+  }
+  if (threadIdx.x == 0) to.alloc[g] = n;
+}
+void launch_max_alloc(ap_engine* e, int32_t* d_out) {
+  cudaMemsetAsync(d_out, 0, 4, e->stream);
+  int blocks = (e->geo.G + 255) / 256;
+  k_max_alloc<<<blocks < 64 ? blocks : 64, 256, 0, e->stream>>>(e->geo.G, e->pools.alloc, d_out);
+}
+void launch_pool_copy(ap_engine* e, const Pools& from, int from_cap, const Pools& to, int to_cap) {
+  k_pool_copy<<<e->geo.G, 256, 0, e->stream>>>(e->geo.G, from, from_cap, to, to_cap);
 }
 
 static inline dim3 sel_grid(int n) { return dim3((n + SEL_WARPS - 1) / SEL_WARPS); }

@@ -61,6 +61,18 @@ def unpack_records(packed, S, width, height):
     return states, pis, zs
 
 
+def split_records(packed, S):
+    """packed rows -> (state bits uint8[n][ceil(9S/8)], pis float32[n][S], zs float32[n]) - the arguments of
+    ``ReplayBuffer.extend_positions`` / ``ap_replay_push``"""
+    n = packed.shape[0]
+    w = record_width(S)
+    sb = (9 * S + 7) // 8
+    off = w - 4 * S - 4
+    pis = np.ascontiguousarray(packed[:, off:off + 4 * S]).view(np.float32).reshape(n, S)
+    zs = np.ascontiguousarray(packed[:, off + 4 * S:]).view(np.float32).reshape(n)
+    return np.ascontiguousarray(packed[:, :sb]), pis, zs
+
+
 def gather_replay(packed, device=None):
     """All-gather variable numbers of packed records from every rank.  Returns uint8[N_total][width]."""
     world = dist.get_world_size()

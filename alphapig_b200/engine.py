@@ -74,6 +74,12 @@ class Engine(object):
         self._check(self.lib.ap_engine_memory(self.h, C.byref(v)))
         return v.value
 
+    def node_capacity(self):
+        """tree nodes per game the pools currently hold (a library-chosen capacity grows on demand)"""
+        v = C.c_int32()
+        self._check(self.lib.ap_engine_node_capacity(self.h, C.byref(v)))
+        return v.value
+
     def launch_count(self):
         v = C.c_uint64()
         self._check(self.lib.ap_launch_count(self.h, C.byref(v)))
@@ -224,6 +230,11 @@ class Engine(object):
         n = self._n(ids)
         mv = np.ascontiguousarray(np.broadcast_to(np.asarray(moves, dtype=np.int32), (n,)))
         self._check(self.lib.ap_search_advance(self.h, _ptr(ids), n, _ptr(mv)))
+
+    def search_set_active(self, active=None):
+        """Searches skip the games whose ``active`` entry is false (None = all games search again)."""
+        a = None if active is None else np.ascontiguousarray(np.asarray(active).astype(np.uint8)).reshape(self.G)
+        self._check(self.lib.ap_search_set_active(self.h, _ptr(a)))
 
     def search_stats(self):
         out = np.zeros(8, np.uint64)

@@ -13,6 +13,7 @@ from __future__ import print_function
 import numpy as np
 
 from .engine import Engine
+from .utils import sgf_dataIter
 
 _SERVICES = {}
 
@@ -130,7 +131,8 @@ class Game(object):
     def __init__(self, board, **kwargs):
         self.board = board
         self._boardSize = board.width * board.height
-        self.sgf_loader = kwargs.get('sgf_loader')  # callable(file_name, sgf_home) -> {'winner', 'seq_num_list'}
+        # callable(file_name, sgf_home) -> {'winner', 'seq_num_list'}; the reference calls utils.sgf_dataIter (game.py:240)
+        self.sgf_loader = kwargs.get('sgf_loader') or sgf_dataIter.get_data_from_files
 
     def graphic(self, board, player1, player2):
         """ASCII rendering, row 0 at the bottom (game.py:180-202)."""
@@ -165,39 +167,32 @@ class Game(object):
         return winner
 
     def start_self_play(self, player, is_shown=0, temp=1e-3, sgf_home=None, file_name=None):
-        """SGF replay for the supervised bootstrap (game.py:233-304): pi is 0.99999 at the recorded
-        move and 1e-6 elsewhere, the winner comes from the record; returns (warning, winner, data)."""
-        if self.sgf_loader is None:
-            raise RuntimeError("Game.start_self_play replays SGF records: pass sgf_loader=callable(file_name, "
-                               "sgf_home) -> {'winner', 'seq_num_list'} (utils/sgf_dataIter.py:45-66 is out of scope)")
-        X_train = self.sgf_loader(file_name, sgf_home)
-        seq = X_train['seq_num_list']
-        data_length = len(seq)
-        self.board.init_board()
-        p1, p2 = self.board.players
-        states, mcts_probs, current_players = [], [], []
-        for num_index, move in enumerate(seq):
-            probs = [0.000001 for _ in range(self._boardSize)]
-            probs[move] = 0.99999
-            states.append(self.board.current_state())
-            mcts_probs.append(np.asarray(probs))
-            current_players.append(self.board.current_player)
+        """SGF replay for the supervised bootstrap (game.py:233-304): every recorded ply becomes a training
+        sample whose pi is 0.99999 at the human move and 1e-6 elsewhere, z comes from the winner in the file
+        name; returns (warning, winner, zip(states, mcts_probs, winners_z)), or (1, None, None) as soon as a
+        recorded move is illegal.  MCTS is never consulted; ``player`` is only reset at the end."""
+        record = self.sgf_loader(file_name, sgf_home)
+        board = self.board
+        board.init_board()
+        samples = []  # (state, pi, player to move) before each recorded move
+        for move in record['seq_num_list']:
+            pi = np.full(self._boardSize, 0.000001)
+            pi[move] = 0.99999
+            samples.append((board.current_state(), pi, board.current_player))
             try:
-                self.board.do_move(move)
+                board.do_move(move)
             except Exception:
                 return 1, None, None
             if is_shown:
-                self.graphic(self.board, p1, p2)
-            if num_index + 1 == data_length:
-                winner = X_train['winner']
-                winners_z = np.zeros(len(current_players))
-                if winner != -1:
-                    winners_z[np.array(current_players) == winner] = 1.0
-                    winners_z[np.array(current_players) != winner] = -1.0
-                player.reset_player()
-                if is_shown:
-                    if winner != -1:
-                        print("Game end. Winner is player:", winner)
-                    else:
-                        print("Game end. Tie")
-                return 0, winner, zip(states, mcts_probs, winners_z)
+                self.graphic(board, *board.players)
+        if not samples:
+            return None  # the reference's loop body never runs on an empty record and falls off the end
+        winner = record['winner']
+        movers = np.array([p for _, _, p in samples])
+        z = np.zeros(len(samples))
+        if winner != -1:
+            z = np.where(movers == winner, 1.0, -1.0)
+        player.reset_player()
+        if is_shown:
+            print("Game end. Winner is player: %s" % winner if winner != -1 else "Game end. Tie")
+        return 0, winner, zip([s for s, _, _ in samples], [p for _, p, _ in samples], z)

@@ -42,13 +42,35 @@ class MCTS(object):
         geom = (board.width, board.height, board.n_in_row)
         if self._eng is not None and self._geom == geom:
             return self._eng
+        if self._eng is not None:
+            self._release()
         if self._net is not None:
-            eng = self._net.search_engine(board.n_in_row, self._c_puct, self._n_playout)
+            if (board.width, board.height) != (self._net.board_width, self._net.board_height):
+                raise ValueError("board is %dx%d but the policy-value net was built for %dx%d"
+                                 % (board.width, board.height, self._net.board_width, self._net.board_height))
+            # every MCTS object owns its tree, as in the reference (mcts_alphaZero.py:93-106): two players on the
+            # same net with equal c_puct / n_playout must not share a device tree
+            eng = self._net.search_engine(board.n_in_row, self._c_puct, self._n_playout, tag=("mcts", id(self)))
         else:
             eng = Engine(width=board.width, height=board.height, n_in_row=board.n_in_row, n_games=1,
                          c_puct=self._c_puct, n_playout=self._n_playout)
         self._eng, self._geom = eng, geom
         return eng
+
+    def _release(self):
+        eng, self._eng = self._eng, None
+        if eng is None:
+            return
+        if self._net is not None:
+            self._net.release_engine(eng)
+        else:
+            eng.close()
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
 
     def _load_root(self, eng, state):
         cells, meta = export_board_state(state)

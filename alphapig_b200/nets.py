@@ -87,6 +87,13 @@ class PolicyValueNetBase(object):
             self._engines[key] = eng
         return eng
 
+    def release_engine(self, eng):
+        """Drop a search engine from the replica cache and free its device memory (an ``MCTS`` going away)."""
+        for key, e in list(self._engines.items()):
+            if e is eng:
+                del self._engines[key]
+        eng.close()
+
     # -- inference (policy_value_net_mxnet_simple.py:178-226) ------------------
     def policy_value(self, state_batch):
         states = np.asarray(state_batch, dtype=np.float32)

@@ -22,11 +22,17 @@ def visit_softmax(visits, counts, temp):
 
 class BatchedSelfPlay(object):
     def __init__(self, net, n_games, n_playout=400, c_puct=5, temp=1.0, n_in_row=5, seed=0,
-                 noise_eps=0.25, dirichlet_alpha=0.3, node_capacity=0, record_states=True, tag=0, device_pick=False):
+                 noise_eps=0.25, dirichlet_alpha=0.3, node_capacity=0, record_states=True, tag=0, device_pick=False,
+                 forced_opening_prob=0.09):
         """device_pick: sample the moves on the device (``ap_selfplay_pick``: pi, Dirichlet noise and the inverse-cdf
         draw per game from Philox streams instead of NumPy's global generator) and run the NEXT ply's search in a
         background thread while this ply's records are assembled on the host - one group of games then keeps the GPU
-        busy (``PipelinedSelfPlay`` needs two half-size groups for that)."""
+        busy (``PipelinedSelfPlay`` needs two half-size groups for that).
+
+        forced_opening_prob: the reference starts 9 % of its self-play games with a forced random two-ply opening drawn
+        from hard-coded 15-wide tables and records both plies with pi = 0.99999 at the move / 1e-6 elsewhere
+        (game_ai.py:76-111); done here per restarting slot on 15-wide boards (the tables index a 15-wide board: the
+        reference itself crashes with them on 8x8).  0 disables it."""
         self.net = net
         self.device_pick = device_pick
         self._seed = int(seed)
@@ -43,9 +49,10 @@ class BatchedSelfPlay(object):
         self.eng = net.search_engine(n_in_row=n_in_row, c_puct=c_puct, n_playout=n_playout, n_games=n_games,
                                      node_capacity=node_capacity, tag=tag)
         self.S = self.eng.S
-        self.eng.boards_reset()
-        self.eng.search_advance(-1)
+        self.opening_prob = float(forced_opening_prob) if self.eng.width == 15 and self.S >= 103 else 0.0
+        self.forced_openings = 0
         self._reset_history()
+        self._restart(np.arange(self.G, dtype=np.int32))
         self.finished_games = 0
         self.plies = 0
         self.host_seconds = 0.0  # time spent outside ap_search_run (sampling, recording, re-rooting)
@@ -55,14 +62,55 @@ class BatchedSelfPlay(object):
         self._ply = 0
         self._rec = {}                                  # ply -> (feats uint8[G][sb], pi float32[G][S], players int8[G])
         self._start = np.zeros(self.G, np.int64)        # first ply of the current game of every slot
+        self._prefix = {}                               # slot -> [(feat, pi, player)] forced-opening records of its game
+
+    # the hard-coded opening tables of game_ai.py:76-77 (15-wide board indices)
+    _BLACK_OPENINGS = np.array([r * 15 + c for r in range(7) for c in range(9)], np.int32)
+    _WHITE_OPENINGS = np.arange(0, 103, dtype=np.int32)
+
+    def _restart(self, ids):
+        """``init_board()`` + fresh root for the slots ``ids`` (a new game each), with the reference's forced random
+        two-ply opening for a ``forced_opening_prob`` share of them (game_ai.py:78-111)."""
+        eng = self.eng
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        if not len(ids):
+            return
+        eng.boards_reset(ids)
+        for g in ids:
+            self._prefix.pop(int(g), None)
+        if self.opening_prob > 0.0:
+            forced = ids[self.rs.random_sample(len(ids)) < self.opening_prob]
+            if len(forced):
+                first = self.rs.choice(self._BLACK_OPENINGS, size=len(forced))
+                second = self.rs.choice(self._WHITE_OPENINGS, size=len(forced))
+                clash = first == second
+                while clash.any():  # the reference redraws both moves until they differ (:79-84)
+                    first[clash] = self.rs.choice(self._BLACK_OPENINGS, size=int(clash.sum()))
+                    second[clash] = self.rs.choice(self._WHITE_OPENINGS, size=int(clash.sum()))
+                    clash = first == second
+                recs = [[] for _ in forced]
+                for mv in (first, second):
+                    if self.record_states:
+                        feats = eng.boards_features_packed(forced)
+                        _, meta = eng.boards_export(forced)
+                        for k in range(len(forced)):
+                            pi = np.full(self.S, 0.000001, np.float32)
+                            pi[mv[k]] = 0.99999
+                            recs[k].append((feats[k], pi, np.int8(meta[k, 0])))
+                    eng.boards_do_move(mv.astype(np.int32), forced)
+                if self.record_states:
+                    for k, g in enumerate(forced):
+                        self._prefix[int(g)] = recs[k]
+                self.forced_openings += len(forced)
+        eng.search_advance(np.full(len(ids), -1, np.int32), ids)
 
     def load_positions(self, cells, meta):
         """Start every slot from a given position (benchmark's synthetic positions)."""
         self.drain()
         self._search_done = False
+        self._reset_history()
         self.eng.boards_import(cells, meta)
         self.eng.search_advance(-1)
-        self._reset_history()
 
     def _finish(self, done, winner):
         """records of the games that just ended (rows of the per-ply history), slots restarted by the caller"""
@@ -70,18 +118,33 @@ class BatchedSelfPlay(object):
         for g in done:
             t_first = int(self._start[g])
             if self.record_states and self._ply >= t_first:
-                plies = range(t_first, self._ply + 1)
-                players = np.array([self._rec[t][2][g] for t in plies])
+                rows = list(self._prefix.get(int(g), ())) + [(self._rec[t][0][g], self._rec[t][1][g], self._rec[t][2][g])
+                                                             for t in range(t_first, self._ply + 1)]
+                players = np.array([r[2] for r in rows])
                 z = np.zeros(len(players))
                 if winner[g] != -1:
                     z[players == winner[g]] = 1.0
                     z[players != winner[g]] = -1.0
-                out.append((int(winner[g]), np.stack([self._rec[t][0][g] for t in plies]),
-                            np.stack([self._rec[t][1][g] for t in plies]).astype(np.float64), z))
+                out.append((int(winner[g]), np.stack([r[0] for r in rows]),
+                            np.stack([r[1] for r in rows]).astype(np.float64), z))
             else:
                 out.append((int(winner[g]), None, None, None))
             self._start[g] = self._ply + 1
         return out
+
+    def _search(self):
+        """One move search for every game.  A library-chosen node capacity grows on demand; if the device cannot hold
+        the grown pools (AP_ERR_POOL_EXHAUSTED before any playout ran) the retained subtrees are dropped for this ply
+        - the searches then start from fresh roots, as after ``reset_player`` - instead of aborting the batch."""
+        from ._lib import AP_ERR_POOL_EXHAUSTED, EngineError
+        try:
+            self.eng.search_run(self.n_playout)
+        except EngineError as err:
+            if err.code != AP_ERR_POOL_EXHAUSTED:
+                raise
+            self.tree_drops = getattr(self, "tree_drops", 0) + 1
+            self.eng.search_advance(-1)
+            self.eng.search_run(self.n_playout)
 
     def _step_device_pick(self):
         import time
@@ -91,7 +154,7 @@ class BatchedSelfPlay(object):
             self._fut.result()          # the search of this ply, started at the end of the previous step
             self._fut = None
         elif not self._search_done:
-            eng.search_run(self.n_playout)
+            self._search()
         self._search_done = False
         t0 = time.perf_counter()
         moves, pi = eng.selfplay_pick(self.temp, self.eps, self.alpha, seed=self._seed, ply=self._ply)
@@ -102,17 +165,15 @@ class BatchedSelfPlay(object):
         eng.boards_do_move(moves)
         end, winner = eng.boards_status()
         done = np.nonzero(end)[0].astype(np.int32)
-        if len(done):
-            eng.boards_reset(done)
-            eng.search_advance(np.full(len(done), -1, np.int32), done)
+        if self.record_states:
+            self._rec[self._ply] = (feats, pi, meta[:, 0].astype(np.int8))
+        out = self._finish(done, winner)
+        self._restart(done)
         # the device is ready for the next ply: search it while the host assembles the records of this one
         if self._pool is None:
             self._pool = ThreadPoolExecutor(1)
-        self._fut = self._pool.submit(eng.search_run, self.n_playout)
-        if self.record_states:
-            self._rec[self._ply] = (feats, pi, meta[:, 0].astype(np.int8))
+        self._fut = self._pool.submit(self._search)
         self.plies += self.G
-        out = self._finish(done, winner)
         self.finished_games += len(done)
         self._ply += 1
         if self.record_states and self._rec:
@@ -136,7 +197,7 @@ class BatchedSelfPlay(object):
         if self.device_pick:
             return self._step_device_pick()
         eng, G, S = self.eng, self.G, self.S
-        eng.search_run(self.n_playout)
+        self._search()
         t0 = time.perf_counter()
         count, acts, visits, _, _ = eng.search_root()
         probs = visit_softmax(visits, count, self.temp)  # child order
@@ -162,25 +223,9 @@ class BatchedSelfPlay(object):
         end, winner = eng.boards_status()
         self.plies += G
         done = np.nonzero(end)[0].astype(np.int32)
-        out = []
-        if len(done):
-            for g in done:
-                t_first = int(self._start[g])
-                if self.record_states and self._ply >= t_first:
-                    plies = range(t_first, self._ply + 1)
-                    players = np.array([self._rec[t][2][g] for t in plies])
-                    z = np.zeros(len(players))
-                    if winner[g] != -1:
-                        z[players == winner[g]] = 1.0
-                        z[players != winner[g]] = -1.0
-                    out.append((int(winner[g]), np.stack([self._rec[t][0][g] for t in plies]),
-                                np.stack([self._rec[t][1][g] for t in plies]).astype(np.float64), z))
-                else:
-                    out.append((int(winner[g]), None, None, None))
-                self._start[g] = self._ply + 1
-            eng.boards_reset(done)
-            eng.search_advance(np.full(len(done), -1, np.int32), done)
-            self.finished_games += len(done)
+        out = self._finish(done, winner)
+        self._restart(done)
+        self.finished_games += len(done)
         self._ply += 1
         # plies older than every live game's start are no longer needed
         if self.record_states and self._rec:

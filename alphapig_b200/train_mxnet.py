@@ -14,9 +14,10 @@ What moved to the GPU behind that face:
   (``alphapig_b200.selfplay.BatchedSelfPlay``) - what ``bench.py`` measures.
 * ``policy_evaluate`` keeps the reference's sequential arena; ``policy_evaluate_batched`` plays all arena
   games concurrently on the device (AlphaZero search via ``ap_search_run``, pure MCTS via ``ap_pure_run``).
-* multi-GPU: every rank runs its own pipeline on its own games; after ``policy_update`` on rank 0 the weights
-  are broadcast (``alphapig_b200.dist.broadcast_weights``) and finished-game records are all-gathered
-  (``gather_replay``) - see ``run``.
+* multi-GPU (``run`` under ``torch.distributed``): every rank plays its own self-play games on its own GPU; the
+  records of each iteration are gathered to rank 0 (``alphapig_b200.dist.gather_replay``) and pushed into ITS
+  ring, rank 0 runs ``policy_update`` and the weights are broadcast (``dist.broadcast_weights``).  The SGF
+  bootstrap phase is data loading, not search: rank 0 does it alone.
 
 Logging config, e-mail and the YAML loader of the reference are out of scope: ``conf`` is a plain dict.
 """
@@ -99,6 +100,7 @@ class TrainPipeline(object):
         self.data_buffer = ReplayBuffer(self.policy_value_net._eng, self.buffer_size)
         self.episode_len = 0
         self._batched = None
+        self._pending = None  # multi-rank run(): packed records of this iteration, gathered to rank 0 afterwards
 
     # -- data ---------------------------------------------------------------------------------
     def _load_training_data(self, data_dir):
@@ -139,6 +141,18 @@ class TrainPipeline(object):
                 self.episode_len = len(r['seq_num_list'])
         _logger.info('game_batch_index: %s, length of data_buffer: %s', training_index, len(self.data_buffer))
 
+    def _store(self, states, pis, zs):
+        """``data_buffer.extend(get_equi_data(play_data))`` for one game's un-augmented positions - into the local
+        ring, or (multi-rank ``run``) into the packed records that go to the trainer rank."""
+        states = np.asarray(states)
+        if states.dtype != np.uint8 or states.ndim != 2:
+            states = np.packbits(states.reshape(states.shape[0], -1).astype(np.uint8), axis=1)
+        if self._pending is None:
+            self.data_buffer.extend_positions(states, pis, zs)
+        else:
+            from . import dist as apdist
+            self._pending.append(apdist.pack_records(states, pis, zs, self.board_width * self.board_height))
+
     def collect_selfplay_data_ai(self, n_games=1, training_index=None):
         """One reference-style self-play game at a time (train_mxnet.py:171-180)."""
         for _ in range(n_games):
@@ -146,7 +160,10 @@ class TrainPipeline(object):
             _logger.info('traing_index: %s,   winner is: %s', training_index, winner)
             play_data = list(play_data)[:]
             self.episode_len = len(play_data)
-            self.data_buffer.extend(play_data)
+            if play_data:
+                self._store(np.stack([np.asarray(st) for st, _, _ in play_data]),
+                            np.stack([np.asarray(pi) for _, pi, _ in play_data]),
+                            np.array([z for _, _, z in play_data], dtype=np.float32))
 
     def collect_selfplay_data_batched(self, n_plies=1, n_games=None, seed=0):
         """``n_games`` concurrent self-play games advance ``n_plies`` plies; finished games go into the ring."""
@@ -159,7 +176,7 @@ class TrainPipeline(object):
         for _ in range(n_plies):
             for winner, states, pis, zs in self._batched.step():
                 if states is not None:
-                    self.data_buffer.extend_positions(states, pis, zs)
+                    self._store(states, pis, zs)
                     self.episode_len = len(zs)
                     finished += 1
         return finished
@@ -213,24 +230,38 @@ class TrainPipeline(object):
         return 1.0 * (win_cnt[1] + 0.5 * win_cnt[-1]) / n_games
 
     def run(self, model_dir='./logs', batched=False):
-        """run the training pipeline (train_mxnet.py:265-283).  Under torch.distributed every rank collects on
-        its own GPU; rank 0 trains and broadcasts the weights after each update."""
+        """run the training pipeline (train_mxnet.py:265-283).  Under torch.distributed every rank collects
+        self-play games on its own GPU, the iteration's records are gathered to rank 0, rank 0 trains and the
+        weights are broadcast after each update."""
         import torch.distributed as dist
         from . import dist as apdist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         rank = dist.get_rank() if multi else 0
+        S = self.board_width * self.board_height
         try:
             for i in range(self.game_batch_num):
                 t0 = time.time()
-                if i < self._sgf_bootstrap_batches and self._length_train_data:
-                    self.collect_selfplay_data(self.play_batch_size, training_index=i)
-                elif batched:
-                    self.collect_selfplay_data_batched(1)
+                sgf_phase = i < self._sgf_bootstrap_batches and self._length_train_data
+                if sgf_phase:
+                    if rank == 0:
+                        self.collect_selfplay_data(self.play_batch_size, training_index=i)
                 else:
-                    self.collect_selfplay_data_ai(self.play_batch_size, training_index=i)
+                    self._pending = [] if multi else None
+                    if batched:
+                        self.collect_selfplay_data_batched(1)
+                    else:
+                        self.collect_selfplay_data_ai(self.play_batch_size, training_index=i)
+                    if multi:
+                        mine = (np.concatenate(self._pending, axis=0) if self._pending
+                                else np.zeros((0, apdist.record_width(S)), np.uint8))
+                        self._pending = None
+                        allrec = apdist.gather_replay(mine)
+                        if rank == 0 and allrec.shape[0]:
+                            bits, pis, zs = apdist.split_records(allrec, S)
+                            self.data_buffer.extend_positions(bits, pis, zs)
                 _logger.info('collection cost time: %d ', time.time() - t0)
                 _logger.info("batch i:%s, episode_len:%s, buffer_len:%s", i + 1, self.episode_len, len(self.data_buffer))
-                if len(self.data_buffer) > self.batch_size and rank == 0:
+                if rank == 0 and len(self.data_buffer) > self.batch_size:
                     self.policy_update()
                 if multi:
                     apdist.broadcast_weights(self.policy_value_net, src=0)

@@ -62,6 +62,12 @@ int ap_sync(ap_engine* e);
 /* bytes of device memory held by the handle */
 int ap_engine_memory(const ap_engine* e, uint64_t* out_bytes);
 
+/* tree nodes per game the pools hold now.  cfg.node_capacity > 0 is a hard limit (AP_ERR_POOL_EXHAUSTED when a game
+ * runs over it); cfg.node_capacity <= 0 lets the library pick 2 * n_playout_hint * S + S + 2 and GROW the pools
+ * whenever a search could run out (a re-rooted subtree keeps its visits, mcts_alphaZero.py:159-167, so no fixed size is
+ * safe for self-play with tree reuse; the reference's trees are unbounded Python objects). */
+int ap_engine_node_capacity(const ap_engine* e, int32_t* out_nodes);
+
 /* ---- boards: replaces game.Board (game.py:21-170) --------------------------- */
 /* Board.init_board(start_player)                                   game.py:35-44 */
 int ap_boards_reset(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* start_player);
@@ -116,6 +122,11 @@ int ap_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64
                      int32_t* out_moves /* [G] */, float* out_pi /* [G][S] */, double* out_noise /* [G][S] or NULL */);
 /* MCTS.update_with_move(move): re-root on the child (subtree kept) or fresh root (-1 / absent)  (:159-167) */
 int ap_search_advance(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves);
+/* Restrict every following search (ap_search_select / _run, ap_pure_run) to the games with active[g] != 0; NULL =
+ * all games (the default).  Skipped games keep their boards and trees and report move -1 from ap_pure_run.  The
+ * reference plays its arena games one after the other (train_mxnet.py:239-263) and simply stops calling get_action
+ * for a finished game; a batch of concurrent games needs this mask for the same effect. */
+int ap_search_set_active(ap_engine* e, const uint8_t* active /* [G] or NULL */);
 /* counters since the last call: playouts, sum of children scanned, children written, path nodes, terminal leaves */
 int ap_search_stats(ap_engine* e, uint64_t* out5);
 

@@ -46,3 +46,19 @@ def e3_quantised(board):
 
 
 EVALUATORS = {"e1": e1_uniform, "e2": e2_hash, "e3": e3_quantised}
+
+
+def e4_peaky(board):
+    """Very peaky priors (Dirichlet with concentration 0.003 per move, i.e. total concentration < 1 over ~200 legal
+    moves: nearly all mass on one move; 0.03 still spreads over ~6 moves and searches only ~3 plies deep) and small
+    values, a pure function of the position: the search follows one line 7-10 plies into the tree at 400 playouts and
+    most of a re-rooted subtree survives every ply (root N grows past 1000) - the regime of a trained net, which flat
+    random-weight priors never reach (stresses the re-root compaction, deep backups and pool growth)."""
+    rs = np.random.RandomState(position_key(board) ^ 0x1b873593)
+    n = len(board.availables)
+    pri = rs.dirichlet(0.003 * np.ones(n)) if n > 1 else np.ones(n)
+    val = float(rs.uniform(-0.3, 0.3))
+    return zip(board.availables, pri), val
+
+
+EVALUATORS["e4"] = e4_peaky

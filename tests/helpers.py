@@ -66,3 +66,26 @@ def host_playouts(eng, roots, policy_fn, n_playout):
             vals[g] = v
             assert bool(term[g]) == leaf.game_end()[0]
         eng.search_expand_backup(counts, acts, pri, vals)
+
+
+def engine_net_evaluator(eng):
+    """``policy_value_fn`` for the oracle MCTS that returns the ENGINE's own fp32 priors / value of a position
+    (``ap_net_forward`` on a second handle, batch 1), widened exactly to fp64 - SURVEY T4's contract for how evaluator
+    output enters the tree.  With it the oracle must rebuild, bit for bit, the tree the all-device search built."""
+    def fn(board):
+        st = np.ascontiguousarray(board.current_state(), dtype=np.float32)[None]
+        p, v = eng.net_forward(st)
+        av = list(board.availables)
+        return zip(av, p[0][av].astype(np.float64)), float(v[0, 0])
+    return fn
+
+
+def assert_root_equals_oracle(eng, g, omcts, what=""):
+    """root children (acts, visits, Q) and the root's own N of game g == the oracle tree's, exactly"""
+    count, acts, visits, q, rootn = eng.search_root(game_ids=[g], want_q=True)
+    n = int(count[0])
+    kids = omcts.root.children
+    assert list(acts[0, :n]) == list(kids.keys()), (what, g, "acts")
+    assert list(visits[0, :n]) == [nd.N for nd in kids.values()], (what, g, "visits")
+    assert list(q[0, :n]) == [float(nd.Q) for nd in kids.values()], (what, g, "Q")
+    assert int(rootn[0]) == omcts.root.N, (what, g, "root N")

@@ -4,7 +4,7 @@ Tolerance (north_star): |d log p| <= 1e-3 and |d v| <= 1e-3 absolute, identical 
 import numpy as np
 import pytest
 
-from helpers import export_oboard, oboard_from, synth_position
+from helpers import assert_root_equals_oracle, engine_net_evaluator, export_oboard, oboard_from, synth_position
 from oracle import net as onet
 
 pytestmark = pytest.mark.gpu
@@ -240,3 +240,96 @@ def test_inception_shim_train_step():
     arg, aux = net.get_policy_param()
     rp, rv = onet.forward(arg, aux, st, "inception", n_blocks=2)
     assert np.abs(np.log(p1) - np.log(rp)).max() <= TOL
+
+
+def _peaky_simple_net(W, seed, scale):
+    """the reference net with its policy FC weights scaled: soft-max outputs become very peaky and position
+    dependent - what a trained net looks like to the tree (Xavier weights give near-uniform priors)"""
+    arg, aux = onet.init_params("simple", W, W, seed=seed)
+    arg = dict(arg)
+    arg["fc_3_1_1_weight"] = arg["fc_3_1_1_weight"] * np.float32(scale)
+    return arg, aux
+
+
+def test_device_search_deep_trees_peaky_net_vs_oracle():
+    """ap_search_run (all-device loop) at 15x15, n_playout 400, 6 plies with tree reuse on a peaky net: mean select
+    depth >= 5, root N grows past 1000, the retained subtrees outgrow the default node capacity (pools grow between
+    plies).  The oracle MCTS, fed the engine's own fp32 priors / values through a second handle, must rebuild every
+    root bit for bit (visits, Q, root N) on every ply."""
+    from oracle.mcts import OMCTS
+    W = 15
+    G, n_playout, plies = 4, 400, 6
+    arg, aux = _peaky_simple_net(W, 0, 70.0)
+    a = _engine(width=W, height=W, n_in_row=5, n_games=G, c_puct=5, n_playout=n_playout)
+    b = _engine(width=W, height=W, n_in_row=5, n_games=1, c_puct=5, n_playout=1, node_capacity=8)
+    for e in (a, b):
+        e.net_load("simple", _merged(arg, aux))
+    cap0 = a.node_capacity()
+    roots = [oboard_from(W, W, 5, synth_position(W, W, 5, 1234 + g)) for g in range(G)]
+    cm = [export_oboard(r) for r in roots]
+    a.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+    ev = engine_net_evaluator(b)
+    oracles = [OMCTS(ev, 5, n_playout) for _ in range(G)]
+    depth_sum = playouts = 0
+    max_root_n = 0
+    for ply in range(plies):
+        a.search_stats()
+        a.search_run(n_playout)
+        st = a.search_stats()
+        depth_sum += st["path_nodes"] - st["playouts"]
+        playouts += st["playouts"]
+        moves = np.zeros(G, np.int32)
+        for g in range(G):
+            o_acts, _ = oracles[g].get_move_probs(roots[g], 1.0)
+            assert_root_equals_oracle(a, g, oracles[g], "ply %d" % ply)
+            max_root_n = max(max_root_n, oracles[g].root.N)
+            vis = [nd.N for nd in oracles[g].root.children.values()]
+            moves[g] = o_acts[int(np.argmax(vis))]
+        a.search_advance(moves)
+        a.boards_do_move(moves)
+        for g in range(G):
+            oracles[g].update_with_move(int(moves[g]))
+            roots[g].do_move(int(moves[g]))
+        if any(r.game_end()[0] for r in roots):
+            break
+    print("peaky net: mean depth %.2f, max root N %d, capacity %d -> %d" % (depth_sum / playouts, max_root_n, cap0,
+                                                                        a.node_capacity()))
+    assert depth_sum / playouts >= 5.0
+    assert max_root_n > 2 * n_playout
+    assert a.node_capacity() > cap0
+    a.close()
+    b.close()
+
+
+def test_single_game_15x15_graph_path_vs_oracle():
+    """ONE 15x15 game, n_playout 400 (what human_play_mxnet.py / evaluate/ChessClient.py run): batches of <= 256 games
+    replay the lock-steps as a CUDA graph.  Two plies with tree reuse, then a reset, against the oracle MCTS fed the
+    engine's own priors / values; the second search replays the graph captured by the first."""
+    from oracle.mcts import OMCTS
+    W = 15
+    n_playout = 400
+    arg, aux = onet.init_params("simple", W, W, seed=9)
+    a = _engine(width=W, height=W, n_in_row=5, n_games=1, c_puct=5, n_playout=n_playout)
+    b = _engine(width=W, height=W, n_in_row=5, n_games=1, c_puct=5, n_playout=1, node_capacity=8)
+    for e in (a, b):
+        e.net_load("simple", _merged(arg, aux))
+    root = oboard_from(W, W, 5, synth_position(W, W, 5, 4242))
+    c, m = export_oboard(root)
+    a.boards_import(c[None], m[None])
+    o = OMCTS(engine_net_evaluator(b), 5, n_playout)
+    launches = []
+    for ply, reuse in enumerate((True, True, False)):
+        l0 = a.launch_count()
+        a.search_run(n_playout)
+        launches.append(a.launch_count() - l0)
+        o_acts, _ = o.get_move_probs(root, 1.0)
+        assert_root_equals_oracle(a, 0, o, "ply %d" % ply)
+        vis = [nd.N for nd in o.root.children.values()]
+        mv = int(o_acts[int(np.argmax(vis))])
+        a.search_advance([mv if reuse else -1])
+        o.update_with_move(mv if reuse else -1)
+        a.boards_do_move([mv])
+        root.do_move(mv)
+    assert launches[0] == launches[1] == launches[2] and launches[0] >= 9 * n_playout
+    a.close()
+    b.close()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from helpers import export_oboard, host_playouts, oboard_from, synth_position
+from helpers import assert_root_equals_oracle, export_oboard, host_playouts, oboard_from, synth_position
 from oracle.evaluators import EVALUATORS, position_key
 from oracle.mcts import OMCTS, OPureMCTS, pure_policy_value_fn, softmax
 
@@ -372,8 +372,6 @@ def test_rollout_eval_matches_host_model_exactly():
     eng.close()
 
 
-@pytest.mark.skipif(not os.environ.get("AP_TEST_UNVERIFIED"), reason="written after the round's GPU budget was spent: "
-                    "enable with AP_TEST_UNVERIFIED=1, verify on a B200, then drop the guard (DESIGN 9.3)")
 def test_pure_run_random_rollouts_match_host_model_exactly():
     """ap_pure_run in rollout_mode 0 (the real mcts_pure configuration): with the device's rollouts predicted
     exactly on the host (oracle/rollout.py:device_perm_rollout, draws keyed by (seed, game, playout)), the oracle's
@@ -399,4 +397,73 @@ def test_pure_run_random_rollouts_match_host_model_exactly():
         assert o.get_move(roots[g]) == moves[g]
         assert list(visits[g, :count[g]]) == [nd.N for nd in o.root.children.values()]
         assert list(q[g, :count[g]]) == [float(nd.Q) for nd in o.root.children.values()]
+    eng.close()
+
+
+def test_deep_trees_peaky_evaluator_with_reuse_and_pool_growth():
+    """15x15, n_playout 400, 6 plies with tree reuse under a very peaky injected evaluator (oracle/evaluators.py:e4_peaky):
+    the search runs ~7-10 plies deep, the re-rooted subtree keeps most of its visits (root N grows past 1000) and the
+    retained nodes outgrow the library-chosen capacity, so the pools must GROW mid-game (the reference's trees are
+    unbounded) - visits, Q and root N stay bit-exact vs the oracle throughout.  Exercises k_advance's BFS compaction on
+    deep subtrees and the multi-level backup."""
+    W = H = 15
+    G, n_playout, plies = 4, 400, 6
+    ev = EVALUATORS["e4"]
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, c_puct=5, n_playout=n_playout)  # capacity: library default
+    cap0 = eng.node_capacity()
+    roots = [oboard_from(W, H, 5, synth_position(W, H, 5, 1234 + g)) for g in range(G)]
+    oracles = [OMCTS(ev, 5, n_playout) for _ in range(G)]
+    ex = [export_oboard(b) for b in roots]
+    eng.boards_import(np.stack([c for c, _ in ex]), np.stack([m for _, m in ex]))
+    depth_sum = playouts = 0
+    max_root_n = 0
+    for ply in range(plies):
+        eng.search_stats()
+        host_playouts(eng, roots, ev, n_playout)
+        st = eng.search_stats()
+        depth_sum += st["path_nodes"] - st["playouts"]
+        playouts += st["playouts"]
+        moves = np.zeros(G, np.int32)
+        for g in range(G):
+            o_acts, _ = oracles[g].get_move_probs(roots[g], 1.0)
+            assert_root_equals_oracle(eng, g, oracles[g], "ply %d" % ply)
+            max_root_n = max(max_root_n, oracles[g].root.N)
+            vis = [nd.N for nd in oracles[g].root.children.values()]
+            moves[g] = o_acts[int(np.argmax(vis))]
+        eng.search_advance(moves)
+        eng.boards_do_move(moves)
+        for g in range(G):
+            oracles[g].update_with_move(int(moves[g]))
+            roots[g].do_move(int(moves[g]))
+            assert not roots[g].game_end()[0]
+    assert depth_sum / playouts >= 5.0, depth_sum / playouts
+    assert max_root_n > 2 * n_playout
+    assert eng.node_capacity() > cap0, "the retained subtrees were expected to outgrow the default capacity"
+    eng.close()
+
+
+def test_active_mask_skips_games():
+    """ap_search_set_active: skipped games keep their trees untouched and cost no playouts; the others are unaffected."""
+    W = H = 8
+    G, n_playout = 8, 40
+    eng = _engine(width=W, height=H, n_in_row=5, n_games=G, c_puct=5, n_playout=n_playout)
+    roots = [oboard_from(W, H, 5, synth_position(W, H, 5, 300 + g, 8)) for g in range(G)]
+    ex = [export_oboard(b) for b in roots]
+    eng.boards_import(np.stack([c for c, _ in ex]), np.stack([m for _, m in ex]))
+    active = np.arange(G) % 3 != 1
+    eng.search_set_active(active)
+    eng.search_stats()
+    host_playouts(eng, roots, EVALUATORS["e2"], n_playout)
+    assert eng.search_stats()["playouts"] == int(active.sum()) * n_playout
+    _, _, _, _, rootn = eng.search_root()
+    assert list(rootn) == [n_playout if a else 0 for a in active]
+    for g in np.nonzero(active)[0]:
+        o = OMCTS(EVALUATORS["e2"], 5, n_playout)
+        o.get_move_probs(roots[g], 1.0)
+        assert_root_equals_oracle(eng, int(g), o)
+    mv = eng.pure_run(50, seed=2, rollout_mode=1)
+    assert (mv[~active] == -1).all() and (mv[active] >= 0).all()
+    eng.search_set_active(None)
+    mv = eng.pure_run(50, seed=2, rollout_mode=1)
+    assert (mv >= 0).all()
     eng.close()
