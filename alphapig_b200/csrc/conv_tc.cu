@@ -230,8 +230,11 @@ __device__ __forceinline__ void epi_chunk(const ConvParams& p, const HeadArg<HEA
 // FC operand.  NR = accumulator rows per thread (2 in the single-CTA kernel, 1 in the pair kernel).
 template <int NR, int NCG>
 __device__ __forceinline__ void head_finish(const ConvParams& p, const HeadArg<true>& hw, float (&hacc)[NR][6], uint32_t s_hx,
-                                            int bar_id, int q, int lane, int cg, int tile, const int (&rows)[NR]) {
-  if (cg != 0) {
+                                            int bar_id, int q, int lane, int cg, int tile, const int (&rows)[NR],
+                                            bool live = true) {
+  // live == false (a pair tile's second board past the end of the batch): no data, but the same two barrier
+  // instructions - every warp of a named barrier always meets its peer at the same bar.sync
+  if (live && cg != 0) {
     const uint32_t slot = s_hx + (uint32_t)(((cg - 1) * 128 + q * 32 + lane) * (NR * 6) * 4);
 #pragma unroll
     for (int r = 0; r < NR; ++r)
@@ -241,7 +244,7 @@ __device__ __forceinline__ void head_finish(const ConvParams& p, const HeadArg<t
   }
   __syncwarp();  // bar.sync is the .aligned form: the warp must arrive converged (the predicated blocks above may have split it)
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NCG) : "memory");
-  if (cg == 0) {
+  if (live && cg == 0) {
     const int S = p.W * p.H;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -513,15 +516,15 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
         static_assert(NCG == 4, "HEAD epilogue: four warps per lane quarter");
         const int hh = cg >> 1, cc = cg & 1;
         const int r = hh * 128 + q * 32 + lane;
+        float hacc[1][6];
+#pragma unroll
+        for (int o = 0; o < 6; ++o) hacc[0][o] = 0.f;
         auto body = [&](const int cb) {
           constexpr int NCHH = COUT / 2 / 16;
           const uint32_t a0 = acc_base + (uint32_t)(hh * COUT + cb);
           ResidRegs<2, SPLIT> rrh[2];
           resid_load<RESID, 2, SPLIT>(p, cb, grow0 + hh * 128, rrh[0]);
           uint32_t v[2][16];
-          float hacc[1][6];
-#pragma unroll
-          for (int o = 0; o < 6; ++o) hacc[0][o] = 0.f;
           tmem_ld16_nowait(a0, v[0]);
 #pragma unroll
           for (int i = 0; i < NCHH; ++i) {
@@ -536,10 +539,12 @@ k_conv3x3_tc(const __grid_constant__ ConvParams p, const __grid_constant__ HeadA
             }
             epi_chunk<COUT, RESID, true, 2, SPLIT>(p, hw, v[i & 1], cb + i * 16, grow0 + hh * 128, true, sb, hacc[0], rrh[i & 1]);
           }
-          const int rows[1] = {r};
-          head_finish<1, 2>(p, hw, hacc, sx + (uint32_t)(hh * 128 * 6 * 4), 1 + q * 2 + hh, q, lane, cc, tile, rows);
         };
+        // the column half is a compile-time constant inside body (head weights as immediate constant-bank operands);
+        // the two warps of a named barrier meet again HERE, at one bar.sync instruction, not inside the two copies
         if (cc == 0) body(0); else body(COUT / 2);
+        const int rows[1] = {r};
+        head_finish<1, 2>(p, hw, hacc, sx + (uint32_t)(hh * 128 * 6 * 4), 1 + q * 2 + hh, q, lane, cc, tile, rows);
       } else {
         uint32_t v[2][32];
         float hacc[6];
@@ -804,13 +809,13 @@ k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ Head
       const bool valid = ((r & 15) < p.W) && ((r >> 4) < p.H);
       const long long grow = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS + r;
       const uint32_t sb = smem_u32(s_bias), sx = smem_u32(s_hx);
+      float hacc[1][6];
+      if (HEAD) {
+#pragma unroll
+        for (int o = 0; o < 6; ++o) hacc[0][o] = 0.f;
+      }
       auto body = [&](const int cb) {
         uint32_t v[2][32];
-        float hacc[1][6];
-        if (HEAD) {
-#pragma unroll
-          for (int o = 0; o < 6; ++o) hacc[0][o] = 0.f;
-        }
         ResidRegs<4, false> rr[2];
         resid_load<RESID, 4, false>(p, cb, grow, rr[0]);
         tmem_ld32(acc + cb, v[0]);
@@ -830,13 +835,12 @@ k_conv3x3_tc2(const __grid_constant__ ConvParams p, const __grid_constant__ Head
           }
           epi_chunk<COUT, RESID, HEAD, 4>(p, hw, v[i & 1], c0, grow, valid, sb, hacc[0], rr[i & 1]);
         }
-        if constexpr (HEAD) {
-          const int rows[1] = {r};
-          head_finish<1, 2>(p, hw, hacc, sx, 1 + q, q, lane, cbase != 0 ? 1 : 0, tile, rows);
-        }
       };
       if constexpr (HEAD) {
         if (cbase == 0) body(0); else body(NH);
+        // one bar.sync instruction for both warps of the named barrier (not one per inlined copy of body)
+        const int rows[1] = {r};
+        head_finish<1, 2>(p, hw, hacc, sx, 1 + q, q, lane, cbase != 0 ? 1 : 0, tile, rows);
       } else {
         body(cbase);
       }
@@ -1128,12 +1132,7 @@ k_conv3x3_tc4(const __grid_constant__ ConvParams p, const __grid_constant__ Head
         if (nh == 1) {
           // both column halves of this board are in hsum: combine the two 64-column warps, finish, write the FC operand
           const int rows[2] = {q * 32 + lane, 128 + q * 32 + lane};
-          if (live) {
-            head_finish<2, 2>(p, hw, hsum, sx, 1 + q, q, lane, ch, board, rows);
-          } else {  // keep the named barriers of head_finish balanced for the peer warp
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-          }
+          head_finish<2, 2>(p, hw, hsum, sx, 1 + q, q, lane, ch, board, rows, live);
         }
       } else {
         body(nh * kNT4 + cw);
