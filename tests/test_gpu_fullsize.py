@@ -11,14 +11,14 @@ from oracle.board import OBoard
 pytestmark = pytest.mark.gpu
 
 
-def _net_engine(G, n_playout):
+def _net_engine(G, n_playout, node_capacity=None):
     from alphapig_b200.engine import Engine
     from alphapig_b200.params import init_params
     arg, aux = init_params("simple", 15, 15, seed=0, synthetic_stats=True)
     merged = dict(arg)
     merged.update(aux)
     eng = Engine(width=15, height=15, n_in_row=5, n_games=G, c_puct=5, n_playout=n_playout,
-                 node_capacity=n_playout * 225 + 2)
+                 node_capacity=n_playout * 225 + 2 if node_capacity is None else node_capacity)
     eng.net_load("simple", merged)
     return eng
 
@@ -75,7 +75,7 @@ def test_c2_full_size_search_matches_oracle_on_sampled_games():
     from helpers import assert_root_equals_oracle, engine_net_evaluator
     from oracle.mcts import OMCTS
     G, n_playout = 4096, 400
-    eng = _net_engine(G, n_playout)
+    eng = _net_engine(G, n_playout, node_capacity=0)  # library default: room for a re-rooted subtree, grows on demand
     probe = _net_engine(1, 1)
     cells, meta = bench.synthetic_positions(eng, G)
     sample = [0, 1, 2, 3, 255, 256, 257, 1000, 1023, 1024, 2047, 2048, 2049, 3000, 3333, 4000, 4093, 4094, 4095,

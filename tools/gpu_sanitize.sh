@@ -9,9 +9,11 @@
 OUT=${1:-gpurun_out}
 mkdir -p $OUT
 rc=0
-for mode in s p; do
-  compute-sanitizer --tool racecheck --print-limit 5 tools/sanitizer_repro/tmem_alloc_pair $mode > $OUT/sanitize_repro_racecheck_$mode.log 2>&1
-  echo "repro racecheck $mode: $(grep -c 'Race reported' $OUT/sanitize_repro_racecheck_$mode.log) race reports, $(grep -E 'tmem base|RACECHECK SUMMARY' $OUT/sanitize_repro_racecheck_$mode.log | tr '\n' ' ')"
+i=0
+for cfg in "s 128 0 2 64 1" "p 128 0 2 64 1" "s 384 2 148 256 3" "p 384 2 148 256 3" "p 384 2 148 512 3"; do
+  i=$((i+1))
+  compute-sanitizer --tool racecheck --print-limit 5 tools/sanitizer_repro/tmem_alloc_pair $cfg > $OUT/sanitize_repro_racecheck_$i.log 2>&1
+  echo "repro racecheck [$cfg]: $(grep -c 'Race reported' $OUT/sanitize_repro_racecheck_$i.log) race reports; $(grep -E 'tmem base|RACECHECK SUMMARY' $OUT/sanitize_repro_racecheck_$i.log | tr '\n' ' ')"
 done
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
   timeout 1500 compute-sanitizer --tool $tool --print-limit 200 python tools/sanitize_small.py > $OUT/sanitize_$tool.log 2>&1

@@ -9,16 +9,17 @@
 // and does not order it by the cluster barrier.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -o tmem_alloc_pair tmem_alloc_pair.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 template <bool PAIR>
-__global__ void __cluster_dims__(2, 1, 1) k_alloc(unsigned* out) {
+__global__ void __cluster_dims__(2, 1, 1) k_alloc(unsigned* out, int alloc_warp, unsigned cols) {
   __shared__ unsigned slot;
-  if (threadIdx.x < 32) {
+  if ((int)(threadIdx.x >> 5) == alloc_warp) {
     if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"((unsigned)__cvta_generic_to_shared(&slot)) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&slot)), "r"(cols) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"((unsigned)__cvta_generic_to_shared(&slot)) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&slot)), "r"(cols) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
@@ -27,19 +28,24 @@ __global__ void __cluster_dims__(2, 1, 1) k_alloc(unsigned* out) {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned base = slot;  // <- the flagged read
-  if (threadIdx.x == 64) out[blockIdx.x] = base;
+  if (threadIdx.x == 0) out[blockIdx.x] = base;
   __syncthreads();
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (threadIdx.x < 32) {
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 64;" ::"r"(base) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(base) : "memory");
+  if ((int)(threadIdx.x >> 5) == alloc_warp) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
   }
 }
-int main(int argc, char** argv) {
-  unsigned* d; cudaMalloc(&d, 64); unsigned h[4] = {9, 9, 9, 9};
+int main(int argc, char** argv) {  // tmem_alloc_pair <p|s> [threads] [alloc warp] [CTAs] [TMEM columns] [launches]
   const bool pair = argc > 1 && argv[1][0] == 'p';
-  if (pair) k_alloc<true><<<2, 128>>>(d); else k_alloc<false><<<2, 128>>>(d);
+  const int threads = argc > 2 ? atoi(argv[2]) : 128, warp = argc > 3 ? atoi(argv[3]) : 0, grid = argc > 4 ? atoi(argv[4]) : 2;
+  const unsigned cols = argc > 5 ? atoi(argv[5]) : 64;
+  const int launches = argc > 6 ? atoi(argv[6]) : 1;
+  unsigned* d; cudaMalloc(&d, 4 * grid); unsigned h[2] = {9, 9};
+  for (int i = 0; i < launches; ++i)
+    if (pair) k_alloc<true><<<grid, threads>>>(d, warp, cols); else k_alloc<false><<<grid, threads>>>(d, warp, cols);
   cudaError_t e = cudaDeviceSynchronize(); cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
-  printf("%s: %s, tmem base per CTA: %u %u\n", pair ? "cta_group::2" : "cta_group::1", cudaGetErrorString(e), h[0], h[1]);
+  printf("%s x%d launches, %d CTAs x %d threads, warp %d allocates %u columns: %s, tmem base of CTA 0/1: %u %u\n",
+         pair ? "cta_group::2" : "cta_group::1", launches, grid, threads, warp, cols, cudaGetErrorString(e), h[0], h[1]);
   return e != cudaSuccess;
 }
