@@ -84,6 +84,13 @@ SIGNATURES = {
     "ap_replay_size": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ap_replay_gather": (C.c_int, [_P, _P, _I, _P, _P, _P, _I]),
     "ap_replay_push_sgf": (C.c_int, [_P, _P, _I, _P, _P, _I, _P]),
+    "ap_replay_push_packed": (C.c_int, [_P, _P, C.c_int64, _I]),
+    "ap_traj_create": (C.c_int, [_P, _I, C.c_int64]),
+    "ap_traj_append_forced": (C.c_int, [_P, _P, _I, _P]),
+    "ap_traj_finish": (C.c_int, [_P, _P, _I, _P]),
+    "ap_traj_discard": (C.c_int, [_P, _P, _I]),
+    "ap_traj_outbox": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "ap_traj_outbox_clear": (C.c_int, [_P]),
 }
 
 _lib = None

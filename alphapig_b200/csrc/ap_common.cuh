@@ -62,6 +62,7 @@ struct Leaves {
 
 struct NetState;     // net.cu
 struct ReplayState;  // replay.cu
+struct TrajState;    // traj.cu
 
 struct ap_engine {
   ap_config cfg;
@@ -90,6 +91,7 @@ struct ap_engine {
   // net
   NetState* net = nullptr;
   ReplayState* replay = nullptr;
+  TrajState* traj = nullptr;
   float* d_probs = nullptr;   // [G][S] fp32
   float* d_values = nullptr;  // [G]
   // ap_pure_run leaves lazily materialised trees (only the root's child block is complete, see rollout.cu); the
@@ -153,6 +155,10 @@ int ap_ids(ap_engine* e, const int32_t* game_ids, int32_t n);  // uploads ids (o
 
 // replay.cu
 void replay_destroy(ap_engine* e);
+// traj.cu
+void traj_destroy(ap_engine* e);
+int traj_append_pick(ap_engine* e, const float* d_pi);
+int traj_record_width(int S);
 // net.cu
 int net_destroy(ap_engine* e);
 int net_forward_leaves(ap_engine* e, int precise, bool compact = false, bool compacted_by_select = false);

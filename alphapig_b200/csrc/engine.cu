@@ -273,6 +273,7 @@ int ap_engine_destroy(ap_engine* e) {
   cudaStreamSynchronize(e->stream);
   net_destroy(e);
   replay_destroy(e);
+  traj_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_stage) cudaFree(e->d_stage);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -639,6 +640,7 @@ int ap_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64
   double* d_n = out_noise ? (double*)((char*)e->d_stage + mb + pb) : nullptr;
   launch_selfplay_pick(e, temp, eps, alpha, seed, ply, d_m, d_p, d_n);
   AP_LAUNCH_CHECK(e);
+  AP_TRY(traj_append_pick(e, d_p));  // device-side trajectories (ap_traj_create): this ply's (state, pi, player)
   AP_CUDA(e, cudaMemcpyAsync(out_moves, d_m, 4 * G, cudaMemcpyDeviceToHost, e->stream));
   if (out_noise) AP_CUDA(e, cudaMemcpyAsync(out_noise, d_n, nb, cudaMemcpyDeviceToHost, e->stream));
   return d2h_sync(e, out_pi, d_p, pb);

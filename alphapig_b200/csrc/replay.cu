@@ -8,8 +8,8 @@
 // Deque bookkeeping: logical sample a (counted since creation) = record a/8 under symmetry a%8, in the
 // reference's order (for i in 1..4: rot90^i, rot90^i + fliplr).  The deque holds the last
 // min(total, maxlen) logical samples; index j of the deque is logical sample total - len + j.
-#include "board.cuh"
 #include "kernels.h"
+#include "state_bits.cuh"
 
 struct ReplayState {
   int64_t maxlen = 0;      // deque maxlen, in augmented samples
@@ -74,24 +74,7 @@ __global__ void k_replay_sgf(Geo geo, const int16_t* __restrict__ moves, int max
     }
     if (emit) {
       const int slot = (int)((rec_base[g] + ply) % cap);
-      for (int i = lane; i < nw; i += 32) wbuf[i] = 0u;
-      __syncwarp();
-      auto setbit = [&](int f) { atomicOr(&wbuf[f >> 5], 1u << ((((f >> 3) & 3) << 3) + 7 - (f & 7))); };
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const uint32_t own = wb_rows_dropped(b, b.cur, d, W, lane);
-        const uint32_t opp = wb_rows_dropped(b, 3 - b.cur, d, W, lane);
-        if (lane < H) {
-          const int r = W - 1 - lane;  // axis-1 flip of current_state (game.py:94)
-          for (int w = 0; w < W; ++w) {
-            if ((own >> w) & 1u) setbit((6 - 2 * d) * S + r * W + w);
-            if ((opp >> w) & 1u) setbit((7 - 2 * d) * S + r * W + w);
-          }
-        }
-      }
-      if (b.nst % 2 == 0)
-        for (int k = lane; k < S; k += 32) setbit(8 * S + k);
-      __syncwarp();
+      wb_pack_state(b, W, H, S, lane, wbuf, nw);
       uint8_t* ob = bits + (size_t)slot * sb;
       const uint8_t* wb8 = reinterpret_cast<const uint8_t*>(wbuf);
       for (int i = lane; i < sb; i += 32) ob[i] = wb8[i];
@@ -185,6 +168,46 @@ extern "C" int ap_replay_push(ap_engine* e, const uint8_t* state_bits, const flo
     i += run;
   }
   AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  return AP_OK;
+}
+
+// packed records ([state bytes padded to 4][S x fp32 pi][fp32 z], the outbox / exchange format of traj.cu and
+// alphapig_b200/dist.py) -> ring slots
+__global__ void k_replay_unpack(const uint8_t* __restrict__ recs, int rw, int off_pi, int S, int sb, int cap, long long slot0,
+                                uint8_t* bits, float* pi, float* z) {
+  const int i = blockIdx.x;
+  const int slot = (int)((slot0 + i) % cap);
+  const uint8_t* r = recs + (size_t)i * rw;
+  for (int k = threadIdx.x; k < sb; k += blockDim.x) bits[(size_t)slot * sb + k] = r[k];
+  const float* rp = reinterpret_cast<const float*>(r + off_pi);
+  for (int k = threadIdx.x; k < S; k += blockDim.x) pi[(size_t)slot * S + k] = rp[k];
+  if (threadIdx.x == 0) z[slot] = rp[S];
+}
+
+extern "C" int ap_replay_push_packed(ap_engine* e, const void* records, int64_t n, int32_t on_device) {
+  AP_ENTER(e);
+  ReplayState* r = e->replay;
+  if (!r) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_push_packed: no replay ring (ap_replay_create)");
+  if (n < 0 || (n && !records)) return ap_fail(e, AP_ERR_BAD_ARG, "ap_replay_push_packed: bad argument");
+  const int S = e->geo.S, rw = traj_record_width(S), off_pi = rw - 4 * S - 4;
+  const uint8_t* src = (const uint8_t*)records;
+  for (int64_t i = 0; i < n;) {
+    int64_t run = n - i;
+    if (run > r->cap - 1) run = r->cap - 1;  // slots of one launch must not alias
+    const uint8_t* d = src + (size_t)i * rw;
+    if (!on_device) {
+      int rc = ap_stage(e, (size_t)run * rw, 0);
+      if (rc != AP_OK) return rc;
+      AP_CUDA(e, cudaMemcpyAsync(e->d_stage, d, (size_t)run * rw, cudaMemcpyHostToDevice, e->stream));
+      d = (const uint8_t*)e->d_stage;
+    }
+    k_replay_unpack<<<(unsigned)run, 128, 0, e->stream>>>(d, rw, off_pi, S, r->sb, r->cap, (long long)(r->total / 8), r->bits,
+                                                         r->pi, r->z);
+    AP_LAUNCH_CHECK(e);
+    AP_CUDA(e, cudaStreamSynchronize(e->stream));
+    r->total += 8ll * run;
+    i += run;
+  }
   return AP_OK;
 }
 

@@ -345,6 +345,46 @@ class Engine(object):
         self._check(self.lib.ap_replay_gather(self.h, _ptr(idx), idx.shape[0], C.c_void_p(states_ptr), C.c_void_p(pi_ptr),
                                               C.c_void_p(z_ptr), 1))
 
+    def replay_push_packed(self, records, n=None, device_ptr=None):
+        """Append packed records ([state bytes padded to 4][S fp32 pi][fp32 z] each): a uint8 ndarray [n][record
+        width] on the host, or ``device_ptr`` + ``n`` for records already on this GPU (outbox / all-gather result)."""
+        if device_ptr is not None:
+            self._check(self.lib.ap_replay_push_packed(self.h, C.c_void_p(int(device_ptr)), int(n), 1))
+            return
+        rec = np.ascontiguousarray(records, dtype=np.uint8)
+        self._check(self.lib.ap_replay_push_packed(self.h, _ptr(rec), rec.shape[0], 0))
+
+    # -- device-side self-play trajectories (game_ai.py:75,113-131) -------------
+    def traj_create(self, max_plies=0, outbox_records=0):
+        """From now on every ``selfplay_pick`` records its ply on the device; ``traj_finish`` moves finished games'
+        records (z filled in) to the outbox."""
+        if outbox_records <= 0:
+            outbox_records = 2 * self.G * 64
+        self._check(self.lib.ap_traj_create(self.h, int(max_plies), int(outbox_records)))
+
+    def traj_append_forced(self, moves, game_ids):
+        ids = _ids(game_ids)
+        mv = np.ascontiguousarray(moves, dtype=np.int32)
+        self._check(self.lib.ap_traj_append_forced(self.h, _ptr(ids), len(ids), _ptr(mv)))
+
+    def traj_finish(self, game_ids, winners):
+        ids = _ids(game_ids)
+        w = np.ascontiguousarray(winners, dtype=np.int8)
+        self._check(self.lib.ap_traj_finish(self.h, _ptr(ids), len(ids), _ptr(w)))
+
+    def traj_discard(self, game_ids=None):
+        ids = _ids(game_ids)
+        self._check(self.lib.ap_traj_discard(self.h, _ptr(ids), self._n(ids)))
+
+    def traj_outbox(self):
+        """-> (device pointer, number of records, bytes per record)"""
+        p, n, w = C.c_void_p(), C.c_int64(), C.c_int32()
+        self._check(self.lib.ap_traj_outbox(self.h, C.byref(p), C.byref(n), C.byref(w)))
+        return p.value, n.value, w.value
+
+    def traj_outbox_clear(self):
+        self._check(self.lib.ap_traj_outbox_clear(self.h))
+
     def _fwd(self, fn, states):
         st = np.ascontiguousarray(states, dtype=np.float32).reshape(-1, 9, self.height, self.width)
         B = st.shape[0]

@@ -222,6 +222,29 @@ int ap_replay_gather(ap_engine* e, const int64_t* idx, int32_t B, float* out_sta
 int ap_replay_push_sgf(ap_engine* e, const int16_t* moves, int32_t max_len, const int32_t* lengths, const int8_t* winners,
                        int32_t n_games, uint8_t* out_warning /* [n_games] or NULL */);
 
+/* the same append from packed records - [ceil(9S/8) state bytes, zero padded to a multiple of 4][S x fp32 pi][fp32 z]
+ * each - on the host (on_device == 0) or on this GPU (on_device != 0: an outbox or an NCCL all-gather result) */
+int ap_replay_push_packed(ap_engine* e, const void* records, int64_t n, int32_t on_device);
+
+/* ---- self-play trajectories on the device: replaces the states / mcts_probs / current_players lists of
+ * Game_AI.start_self_play (game_ai.py:75,113-131) for all G concurrent games --------------------------------------
+ * After ap_traj_create every ap_selfplay_pick also appends the ply's record - Board.current_state() of the board
+ * the move is picked for, the un-noised pi, the player to move - to the game's trajectory in HBM (max_plies <= 0: S
+ * plies per game).  ap_traj_finish moves the records of finished games to the OUTBOX, a flat device array of packed
+ * records in the format above, with z = +1 / -1 for the plies of the winner / loser and 0 for a tie (winners[i] in
+ * {1, 2, -1}, :124-128), in the order of game_ids.  The outbox is what travels: ap_traj_outbox returns its device
+ * pointer and record count (valid until the next ap_traj_finish), e.g. as the send buffer of an NCCL all-gather whose
+ * result the trainer rank hands to ap_replay_push_packed - no host copy of any record. */
+int ap_traj_create(ap_engine* e, int32_t max_plies, int64_t outbox_records);
+/* the forced random two-ply opening of game_ai.py:78-111: record (state, pi = 0.99999 at moves[i] / 1e-6 elsewhere,
+ * player) for game_ids[i] BEFORE the caller plays moves[i] with ap_boards_do_move */
+int ap_traj_append_forced(ap_engine* e, const int32_t* game_ids, int32_t n, const int32_t* moves);
+int ap_traj_finish(ap_engine* e, const int32_t* game_ids, int32_t n, const int8_t* winners);
+/* forget the plies recorded so far for these games (positions loaded from outside) */
+int ap_traj_discard(ap_engine* e, const int32_t* game_ids, int32_t n);
+int ap_traj_outbox(ap_engine* e, void** out_dev_ptr, int64_t* out_records, int32_t* out_record_bytes);
+int ap_traj_outbox_clear(ap_engine* e);
+
 #ifdef __cplusplus
 }
 #endif

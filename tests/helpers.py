@@ -43,9 +43,10 @@ def synth_position(W, H, n, seed, max_pairs=31):
             return mv
 
 
-def host_playouts(eng, roots, policy_fn, n_playout):
+def host_playouts(eng, roots, policy_fn, n_playout, active=None):
     """n_playout lock-steps of the host-evaluator path: select on device, evaluator on host
-    (called with an OBoard of the leaf), expand/backup on device."""
+    (called with an OBoard of the leaf), expand/backup on device.  active: games the engine searches
+    (ap_search_set_active); the others are left alone."""
     G, S = eng.G, eng.S
     for _ in range(n_playout):
         term, depth, path = eng.search_select()
@@ -54,6 +55,8 @@ def host_playouts(eng, roots, policy_fn, n_playout):
         pri = np.zeros((G, S), np.float64)
         vals = np.zeros(G, np.float64)
         for g in range(G):
+            if active is not None and not active[g]:
+                continue
             leaf = roots[g].clone()
             for m in path[g, :depth[g]]:
                 leaf.do_move(int(m))

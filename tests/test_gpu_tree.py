@@ -453,7 +453,7 @@ def test_active_mask_skips_games():
     active = np.arange(G) % 3 != 1
     eng.search_set_active(active)
     eng.search_stats()
-    host_playouts(eng, roots, EVALUATORS["e2"], n_playout)
+    host_playouts(eng, roots, EVALUATORS["e2"], n_playout, active=active)
     assert eng.search_stats()["playouts"] == int(active.sum()) * n_playout
     _, _, _, _, rootn = eng.search_root()
     assert list(rootn) == [n_playout if a else 0 for a in active]
