@@ -90,3 +90,36 @@ def gather_replay(packed, device=None):
     outs = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf)
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(outs, counts)], axis=0)
+
+
+def gather_records_device(recs, dst=None, group=None):
+    """Gather packed records that live on the GPU (a uint8 CUDA tensor [n][width], n differs per rank) straight over
+    NCCL: one tiny all-gather of the counts, then the padded record blocks - to rank ``dst`` only (``dist.gather``,
+    NCCL send/recv underneath: the trainer is the only consumer) or to every rank (dst=None, all-gather).  Returns
+    the list of per-rank tensors trimmed to their counts (empty list on the ranks that receive nothing)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    nccl = dist.get_backend(group) == "nccl"
+    n = torch.tensor([recs.shape[0]], dtype=torch.int64, device=recs.device)
+    clist = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(clist, n, group=group)
+    counts = [int(c.item()) for c in clist]
+    mx = max(counts + [1])
+    width = recs.shape[1]
+    send = recs
+    if recs.shape[0] != mx:
+        send = torch.zeros((mx, width), dtype=torch.uint8, device=recs.device)
+        send[:recs.shape[0]] = recs
+    send = send.contiguous()
+    if dst is None:
+        if nccl:
+            out = torch.empty((world * mx, width), dtype=torch.uint8, device=recs.device)
+            dist.all_gather_into_tensor(out, send, group=group)
+            parts = [out[r * mx:(r + 1) * mx] for r in range(world)]
+        else:
+            parts = [torch.empty_like(send) for _ in range(world)]
+            dist.all_gather(parts, send, group=group)
+        return [p[:c] for p, c in zip(parts, counts)]
+    parts = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, parts, dst=dst, group=group)
+    return [p[:c] for p, c in zip(parts, counts)] if rank == dst else []

@@ -1,14 +1,33 @@
 """Self-play + train loop over all GPUs of one box (BASELINE.json configs[4]).
 
-Every rank (one process per GPU) plays ``n_games`` concurrent self-play games on its own engine - no
-cross-GPU traffic during search.  Once per iteration the two exchanges of SURVEY 8(e) happen:
-finished-game records are all-gathered as fixed-size packed rows (``dist.gather_replay``, NCCL), rank 0
-pushes them into its device replay ring and runs ``epochs`` train steps on minibatches the gather kernel
-writes straight into device tensors, then the flat fp32 weight buffer is broadcast to every rank
-(``dist.broadcast_weights``, one ncclBroadcast) and each rank rebuilds its fp16 operand images locally.
+Every rank (one process per GPU) plays ``n_games`` concurrent self-play games on its own engine - no cross-GPU traffic
+during search.  The two exchanges of SURVEY 8(e) happen once per iteration (= ``plies_per_iter`` plies), both as NCCL
+collectives on device memory:
 
-The single-GPU form of the same loop is the reference's ``TrainPipeline.run`` (train_mxnet.py:265-283:
-collect one game -> policy_update -> repeat).
+* finished-game records: ``BatchedSelfPlay(device_records=True)`` keeps every game's (state bits, pi, z) records in
+  HBM and moves finished games to a device outbox (csrc/traj.cu); the outbox tensor is gathered to the trainer rank
+  as is (``dist.gather_records_device``: NCCL send/recv of device memory) and pushed into its device replay ring
+  (``ap_replay_push_packed``) - no record ever visits the host;
+* weights: after the trainer's ``policy_update`` one broadcast of the flat fp32 master buffer, then each rank rebuilds
+  its fp16 operand images locally at its next ply boundary.
+
+``overlap=True`` (default): nothing waits for the trainer.  The search of the next ply always runs in the self-play
+object's background thread; the collectives are issued from the main thread while it runs; ``policy_update`` runs in
+a trainer thread on rank 0 (its own CUDA stream, the batch engine's handle) while all ranks - rank 0 included - keep
+searching on the previous weights.  Pipeline per iteration i (boundary = the point inside ``step()`` where no search
+is in flight):
+
+    boundary   : drain the outbox (device copy); if a broadcast completed since the last boundary, swap the new
+                 weights into the search engine (operand-image rebuild, < 1 ms)
+    main thread: all-gather records(i)  ->  join trainer(i-1)  ->  broadcast weights(i-1)  ->  start trainer(i)
+
+so the weights a ply searches with are at most two iterations old; the reference (train_mxnet.py:265-283: collect one
+game -> policy_update -> repeat, everything sequential) has no staleness and no overlap.  ``overlap=False`` is the
+synchronous form of the same loop (every engine drained while rank 0 trains), kept for A/B.
+
+The trainer job is the reference's ``TrainPipeline.policy_update`` (train_mxnet.py:194-237): ONE minibatch drawn with
+``random.sample`` semantics from the ring, up to ``epochs`` steps on it, early stop at KL > 4 kl_targ, adaptive
+``lr_multiplier`` (``train_mxnet.kl_and_lr_rule``).
 """
 import time
 
@@ -19,24 +38,168 @@ from .replay import ReplayBuffer
 from .selfplay import BatchedSelfPlay
 
 
+class _Trainer(object):
+    """``policy_update`` on the trainer rank: owns the replay ring (all ring calls come from its thread)."""
+
+    def __init__(self, net, buffer_size, batch_size, epochs, learn_rate, kl_targ):
+        import torch
+        self.net, self.batch_size, self.epochs = net, batch_size, epochs
+        self.learn_rate, self.kl_targ, self.lr_multiplier = learn_rate, kl_targ, 1.0
+        self.ring = ReplayBuffer(net._eng, buffer_size)
+        self.dev = torch.device("cuda", net._device)
+        self.stream = torch.cuda.Stream(self.dev)
+        self.steps = self.records = self.early_stops = 0
+        self.losses, self.kls = [], []
+        self.seconds = 0.0
+
+    def job(self, gathered):
+        """gathered: list of uint8 CUDA tensors of packed records (one per rank)"""
+        import torch
+        from .train_mxnet import kl_and_lr_rule
+        t0 = time.perf_counter()
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            for recs in gathered:
+                if recs.shape[0]:
+                    self.ring.extend_packed(recs.contiguous())
+                    self.records += recs.shape[0]
+            if len(self.ring) > self.batch_size:
+                st, pi, z = self.ring.sample_torch(self.batch_size, self.dev)
+                st_host = st.cpu().numpy()
+                old_probs, _ = self.net.policy_value(st_host)
+                lr = self.learn_rate * self.lr_multiplier
+                for i in range(self.epochs):
+                    loss, _ = self.net.train_step(st, pi, z, lr, sync=False)
+                    self.steps += 1
+                    new_probs, _ = self.net.policy_value(st_host)
+                    kl = np.mean(np.sum(old_probs * (np.log(old_probs + 1e-10) - np.log(new_probs + 1e-10)), axis=1))
+                    if kl > self.kl_targ * 4:
+                        self.early_stops += 1
+                        break
+                kl, self.lr_multiplier = kl_and_lr_rule(old_probs, new_probs, self.kl_targ, self.lr_multiplier)
+                self.losses.append(float(loss[0]))
+                self.kls.append(float(kl))
+            self.stream.synchronize()
+        self.seconds += time.perf_counter() - t0
+
+
 def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, c_puct=5, temp=1.0, batch_size=128,
-                        epochs=8, learn_rate=4e-4, buffer_size=2198800, n_in_row=5, seed=0, log=None, device_pick=False):
-    """Returns a dict of counters / timings (per rank; wall clock).  device_pick: moves sampled on the device with
-    the next ply's search overlapped with the host bookkeeping (``BatchedSelfPlay(device_pick=True)``); the search in
-    flight is joined before the weights change, so it is one ply stale at most."""
+                        epochs=8, learn_rate=4e-4, buffer_size=2198800, n_in_row=5, seed=0, log=None, device_pick=True,
+                        overlap=True, kl_targ=0.02, warmup_iters=0):
+    """Returns a dict of counters / timings (per rank; wall clock).  ``warmup_iters`` iterations run first and are left
+    out of every counter (the timed region then starts at a ply boundary with the pipeline full)."""
     import torch
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     rank = dist.get_rank() if multi else 0
     world = dist.get_world_size() if multi else 1
+    if not overlap:
+        return _synchronous_loop(net, n_games, n_iters, plies_per_iter, n_playout, c_puct, temp, batch_size, epochs,
+                                 learn_rate, buffer_size, n_in_row, seed, log, device_pick, multi, rank, world)
+    from concurrent.futures import ThreadPoolExecutor
+    dev = torch.device("cuda", net._device)
+    sp = BatchedSelfPlay(net, n_games, n_playout=n_playout, c_puct=c_puct, temp=temp, n_in_row=n_in_row,
+                         seed=seed + 1000 * rank, device_pick=True, device_records=True)
+    trainer = _Trainer(net, buffer_size, batch_size, epochs, learn_rate, kl_targ) if rank == 0 else None
+    pool = ThreadPoolExecutor(1) if rank == 0 else None
+    if multi:
+        apdist.broadcast_weights(net, src=0)  # identical start
+    from .nets import _DevView
+    flat, _ = net._views()
+    staged = flat.clone()  # the weights every rank agreed on last (the trainer keeps writing `flat` in place)
+    wptr, wnum = sp.eng.net_weights()
+    search_w = torch.as_tensor(_DevView(wptr, wnum), device=dev)  # the search engine's own fp32 master copy
+    state = {"take": False, "outbox": None, "new_weights": False, "swaps": 0}
+
+    def boundary(sp_):
+        if state["new_weights"]:
+            # no search in flight: staged fp32 weights -> the search engine's replica, operand images rebuilt there
+            search_w.copy_(staged)
+            torch.cuda.current_stream(dev).synchronize()
+            sp_.eng.net_refresh()
+            state["new_weights"] = False
+            state["swaps"] += 1
+        if state["take"]:
+            state["outbox"] = sp_.take_outbox()
+            state["take"] = False
+    sp.boundary_hook = boundary
+
+    out = dict(plies=0, playouts=0, games=0, records=0, bytes_gathered=0, bytes_broadcast=0, t_total=0.0,
+               t_collectives=0.0, t_wait_trainer=0.0, iters=0)
+    fut = None
+    # The timed region starts and ends right behind the launch of a ply's search (no device synchronisation: that would
+    # let the search in flight finish off the clock), so it covers n_iters * plies_per_iter whole periods per rank.
+    t_start = time.perf_counter()
+    t_end = t_start
+    for it in range(warmup_iters + n_iters):
+        timed = it >= warmup_iters
+        for p in range(plies_per_iter):
+            if p == plies_per_iter - 1:
+                state["take"] = True
+            done = sp.step()
+            if timed:
+                out["games"] += len(done)
+        recs = state["outbox"]
+        state["outbox"] = None
+        # ---- exchanges, issued while the next ply's search runs in sp's background thread --------------------------
+        t0 = time.perf_counter()
+        gathered = apdist.gather_records_device(recs, dst=0) if multi else [recs]
+        t1 = time.perf_counter()
+        if rank == 0 and fut is not None:
+            fut.result()  # policy_update of the previous iteration (normally long finished)
+            fut = None
+        t2 = time.perf_counter()
+        if multi:
+            dist.broadcast(flat, src=0)
+        staged.copy_(flat)  # the trainer is idle here: a consistent snapshot, swapped in at the next boundary
+        torch.cuda.current_stream(dev).synchronize()  # (not the device: the next ply's search is in flight)
+        state["new_weights"] = True
+        t3 = time.perf_counter()
+        if rank == 0:
+            fut = pool.submit(trainer.job, gathered)
+        if timed:
+            out["iters"] += 1
+            out["plies"] += plies_per_iter * n_games
+            out["playouts"] += plies_per_iter * n_games * n_playout
+            out["records"] += int(recs.shape[0])
+            out["bytes_gathered"] += sum(int(g.shape[0]) for g in gathered) * int(recs.shape[1])
+            out["bytes_broadcast"] += flat.numel() * 4 if multi else 0
+            out["t_collectives"] += (t1 - t0) + (t3 - t2)
+            out["t_wait_trainer"] += t2 - t1
+        if it == warmup_iters - 1:
+            t_start = time.perf_counter()
+        t_end = time.perf_counter()
+        if log and rank == 0:
+            log("iter %d: %d games finished so far, ring %d, collectives %.1f ms, waited %.1f ms for the trainer"
+                % (it, out["games"], trainer.records, 1e3 * ((t1 - t0) + (t3 - t2)), 1e3 * (t2 - t1)))
+    out["t_total"] = t_end - t_start
+    sp.drain()
+    torch.cuda.synchronize(dev)
+    if multi:
+        dist.barrier()
+    if fut is not None:
+        fut.result()
+    if trainer is not None:
+        out.update(train_steps=trainer.steps, ring_records=trainer.records, losses=trainer.losses, kls=trainer.kls,
+                   lr_multiplier=trainer.lr_multiplier, early_stops=trainer.early_stops, t_trainer=trainer.seconds)
+    out.update(world=world, weight_swaps=state["swaps"], forced_openings=sp.forced_openings, overlap=True)
+    sp.boundary_hook = None
+    return out
+
+
+def _synchronous_loop(net, n_games, n_iters, plies_per_iter, n_playout, c_puct, temp, batch_size, epochs, learn_rate,
+                      buffer_size, n_in_row, seed, log, device_pick, multi, rank, world):
+    """Everything in sequence per iteration: self-play plies (host-staged records), all-gather, train on rank 0 with every
+    engine idle, broadcast.  A throughput harness for A/B against the overlapped loop: it draws a fresh minibatch for each
+    of the ``epochs`` steps at a fixed learning rate, NOT the reference's ``policy_update`` schedule."""
+    import torch
     S = net.board_width * net.board_height
     sp = BatchedSelfPlay(net, n_games, n_playout=n_playout, c_puct=c_puct, temp=temp, n_in_row=n_in_row,
                          seed=seed + 1000 * rank, device_pick=device_pick)
     ring = ReplayBuffer(net._eng, buffer_size) if rank == 0 else None
     if multi:
-        apdist.broadcast_weights(net, src=0)  # identical start
+        apdist.broadcast_weights(net, src=0)
     out = dict(plies=0, playouts=0, games=0, train_steps=0, records=0, t_selfplay=0.0, t_exchange=0.0, t_train=0.0,
-               losses=[])
+               losses=[], overlap=False)
     dev = "cuda:%d" % net._device
     for it in range(n_iters):
         t0 = time.perf_counter()
@@ -55,12 +218,7 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
         t2 = time.perf_counter()
         if rank == 0:
             if allrec.shape[0]:
-                sb = (9 * S + 7) // 8
-                w = apdist.record_width(S)
-                off = w - 4 * S - 4
-                pis = np.ascontiguousarray(allrec[:, off:off + 4 * S]).view(np.float32).reshape(-1, S)
-                zs = np.ascontiguousarray(allrec[:, off + 4 * S:]).view(np.float32).reshape(-1)
-                ring.extend_positions(np.ascontiguousarray(allrec[:, :sb]), pis, zs)
+                ring.extend_packed(allrec)
                 out["records"] += allrec.shape[0]
             if len(ring) > batch_size:
                 for _ in range(epochs):
@@ -79,4 +237,5 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
             log("iter %d: %d games finished, ring %d, %.2fs self-play %.3fs exchange %.2fs train+broadcast"
                 % (it, out["games"], len(ring), t1 - t0, t2 - t1, t3 - t2))
     out["world"] = world
+    out["t_total"] = out["t_selfplay"] + out["t_exchange"] + out["t_train"]
     return out

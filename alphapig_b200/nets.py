@@ -25,8 +25,8 @@ def _to_numpy(x):
 class _DevView(object):
     """__cuda_array_interface__ wrapper so torch can alias engine-owned device memory."""
 
-    def __init__(self, ptr, numel):
-        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr, numel, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class PolicyValueNetBase(object):
@@ -86,6 +86,16 @@ class PolicyValueNetBase(object):
             eng = self._make_engine(n_games, n_in_row, c_puct, n_playout, node_capacity=node_capacity)
             self._engines[key] = eng
         return eng
+
+    def close(self):
+        """Free every engine of this net (device memory returns at once instead of at garbage collection)."""
+        for eng in list(self._engines.values()):
+            eng.close()
+        self._engines.clear()
+        self._torch = None
+        if getattr(self, "_eng", None) is not None:
+            self._eng.close()
+            self._eng = None
 
     def release_engine(self, eng):
         """Drop a search engine from the replica cache and free its device memory (an ``MCTS`` going away)."""
@@ -153,7 +163,10 @@ class PolicyValueNetBase(object):
             eng.net_refresh()
 
     # -- training (policy_value_net_mxnet_simple.py:228-244) -------------------
-    def train_step(self, state_batch, mcts_probs, winner_batch, learning_rate):
+    def train_step(self, state_batch, mcts_probs, winner_batch, learning_rate, sync=True):
+        """One Adam step on (states, pis, zs); returns (loss (1,), entropy (1,)) as the reference does.
+        sync=False leaves the search-engine replicas on the OLD weights (a search may be running on them): the caller
+        pushes the new ones with ``sync_replicas()`` when no search is in flight (alphapig_b200/loop.py)."""
         import torch
         from . import train as T
         flat, views = self._views()
@@ -174,5 +187,8 @@ class PolicyValueNetBase(object):
         aux = OrderedDict((k, views[k]) for k in self._aux_names)
         loss, entropy = T.train_step(arg, aux, self._opt, x, pi, z, float(learning_rate), self.arch,
                                      self._n_blocks if self.arch != "simple" else 0, wd=self.l2_const)
-        self.sync_replicas()
+        if sync:
+            self.sync_replicas()
+        else:
+            self._eng.net_refresh()  # the batch engine (policy_value / policy_value_fn) follows at once
         return loss.reshape(1).cpu().numpy(), entropy.reshape(1).cpu().numpy()

@@ -40,6 +40,18 @@ class ReplayBuffer(object):
                               np.stack([np.asarray(p) for _, p, _ in play_data]),
                               np.array([z for _, _, z in play_data], dtype=np.float32))
 
+    def extend_packed(self, records):
+        """Append positions given as packed records (``alphapig_b200.dist.pack_records`` / the self-play outbox):
+        a uint8 ndarray [n][record width] or a CUDA uint8 tensor of that shape on the ring's GPU (no host copy)."""
+        if hasattr(records, "data_ptr"):
+            if records.shape[0]:
+                assert records.is_cuda and records.is_contiguous() and records.dtype.itemsize == 1
+                import torch
+                torch.cuda.current_stream(records.device).synchronize()
+                self.eng.replay_push_packed(None, n=records.shape[0], device_ptr=records.data_ptr())
+        elif len(records):
+            self.eng.replay_push_packed(records)
+
     def sample_indices(self, batch_size):
         """The positions ``random.sample(data_buffer, batch_size)`` would pick (same ``random`` state,
         same population size => same indices)."""

@@ -23,7 +23,7 @@ def visit_softmax(visits, counts, temp):
 class BatchedSelfPlay(object):
     def __init__(self, net, n_games, n_playout=400, c_puct=5, temp=1.0, n_in_row=5, seed=0,
                  noise_eps=0.25, dirichlet_alpha=0.3, node_capacity=0, record_states=True, tag=0, device_pick=False,
-                 forced_opening_prob=0.09):
+                 forced_opening_prob=0.09, device_records=False):
         """device_pick: sample the moves on the device (``ap_selfplay_pick``: pi, Dirichlet noise and the inverse-cdf
         draw per game from Philox streams instead of NumPy's global generator) and run the NEXT ply's search in a
         background thread while this ply's records are assembled on the host - one group of games then keeps the GPU
@@ -32,7 +32,14 @@ class BatchedSelfPlay(object):
         forced_opening_prob: the reference starts 9 % of its self-play games with a forced random two-ply opening drawn
         from hard-coded 15-wide tables and records both plies with pi = 0.99999 at the move / 1e-6 elsewhere
         (game_ai.py:76-111); done here per restarting slot on 15-wide boards (the tables index a 15-wide board: the
-        reference itself crashes with them on 8x8).  0 disables it."""
+        reference itself crashes with them on 8x8).  0 disables it.
+
+        device_records (needs device_pick): the (state, pi, z) records never visit the host - every pick appends its
+        ply to the game's trajectory in HBM (``ap_traj_create``), finished games move to the device OUTBOX with z
+        filled in, and ``take_outbox()`` hands the packed records over as a device tensor (for ``ReplayBuffer.
+        extend_packed`` / an NCCL all-gather).  ``step()`` then returns ``(winner, None, None, None)`` per finished game.
+        ``boundary_hook(self)``, if set, runs once per ply at the point where no search is in flight (after the moves
+        were played, before the next search starts): the place to drain the outbox or swap in new weights."""
         self.net = net
         self.device_pick = device_pick
         self._seed = int(seed)
@@ -49,6 +56,13 @@ class BatchedSelfPlay(object):
         self.eng = net.search_engine(n_in_row=n_in_row, c_puct=c_puct, n_playout=n_playout, n_games=n_games,
                                      node_capacity=node_capacity, tag=tag)
         self.S = self.eng.S
+        self.device_records = bool(device_records)
+        self.boundary_hook = None
+        if self.device_records:
+            if not device_pick:
+                raise ValueError("device_records needs device_pick=True (the pick kernel writes the records)")
+            self.record_states = False
+            self.eng.traj_create()
         self.opening_prob = float(forced_opening_prob) if self.eng.width == 15 and self.S >= 103 else 0.0
         self.forced_openings = 0
         self._reset_history()
@@ -97,6 +111,8 @@ class BatchedSelfPlay(object):
                             pi = np.full(self.S, 0.000001, np.float32)
                             pi[mv[k]] = 0.99999
                             recs[k].append((feats[k], pi, np.int8(meta[k, 0])))
+                    if self.device_records:
+                        eng.traj_append_forced(mv, forced)
                     eng.boards_do_move(mv.astype(np.int32), forced)
                 if self.record_states:
                     for k, g in enumerate(forced):
@@ -109,6 +125,8 @@ class BatchedSelfPlay(object):
         self.drain()
         self._search_done = False
         self._reset_history()
+        if self.device_records:
+            self.eng.traj_discard()
         self.eng.boards_import(cells, meta)
         self.eng.search_advance(-1)
 
@@ -168,7 +186,11 @@ class BatchedSelfPlay(object):
         if self.record_states:
             self._rec[self._ply] = (feats, pi, meta[:, 0].astype(np.int8))
         out = self._finish(done, winner)
+        if self.device_records and len(done):
+            eng.traj_finish(done, winner[done])
         self._restart(done)
+        if self.boundary_hook is not None:
+            self.boundary_hook(self)
         # the device is ready for the next ply: search it while the host assembles the records of this one
         if self._pool is None:
             self._pool = ThreadPoolExecutor(1)
@@ -181,6 +203,21 @@ class BatchedSelfPlay(object):
             for t in [t for t in self._rec if t < oldest]:
                 del self._rec[t]
         self.host_seconds += time.perf_counter() - t0
+        return out
+
+    def take_outbox(self):
+        """device_records: the finished games' packed records as a uint8 CUDA tensor [n][record width] (a copy; the
+        outbox is emptied).  Only when no search is in flight: inside ``boundary_hook`` or after ``drain()``."""
+        import torch
+        from .nets import _DevView
+        ptr, n, rw = self.eng.traj_outbox()
+        dev = torch.device("cuda", self.net._device)
+        if n == 0:
+            return torch.empty((0, rw), dtype=torch.uint8, device=dev)
+        view = torch.as_tensor(_DevView(ptr, n * rw, "|u1"), device=dev).view(n, rw)
+        out = view.clone()
+        torch.cuda.current_stream(dev).synchronize()
+        self.eng.traj_outbox_clear()
         return out
 
     def drain(self):

@@ -1,11 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the self-play hot path (BASELINE.json metric: MCTS playouts/s, 15x15, 400 playouts).
+"""Benchmark of the self-play hot path (BASELINE.json metric: MCTS playouts/s and self-play moves/s, 15x15, 400 playouts).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One step = one full MCTS move search (n_playout lock-steps of select -> features -> net ->
-expand/backup) for every one of the G concurrent games of a rank, from the synthetic positions of
-SURVEY 8(d), on a fresh tree.  Prints ONE JSON line (see the prompt's contract / DESIGN.md).
+Headline (the JSON line's `value`): one step = one full MCTS move search (n_playout lock-steps of select ->
+features -> net -> expand/backup) for every one of the G = 4096 concurrent games of a rank, from the synthetic positions
+of SURVEY 8(d), on a fresh tree (BASELINE configs[1]).  The same line carries, under their own keys, driver-timed
+sub-measurements of the other configurations (each with its own `roofline`):
+
+    selfplay        real self-play plies (BatchedSelfPlay, device-side move sampling, records kept, tree reuse);
+                    the line's `moves_per_s` is THIS played figure (all ranks), `moves_per_s_search_only` = value / 400
+    loop            configs[4]: the self-play + train loop with the record gather and the weight broadcast (NCCL)
+                    INSIDE the timed region, training overlapped with search
+    pure            configs[2]: mcts_pure, 8192 games x 1000 playouts                       (N = 1 only)
+    resnet10        the 10-block residual net the reference trains, same move-search workload  (N = 1 only)
+    inception       configs[3]: the builder-defined Inception-ResNet variant                   (N = 1 only)
+    single_game_ms  configs[0]'s GPU side: ONE game through MCTSPlayer.get_action, 8x8 and 15x15 (N = 1 only)
+
+`--legs none` prints the headline alone; `--workload pure|selfplay|loop` and `--net resnet|inception` print one leg as
+its own line.  Prints ONE JSON line (see the prompt's contract / DESIGN.md 6).
 """
 import argparse
 import json
@@ -131,20 +144,39 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------
+def oracle_board_from_position(cells, meta):
+    """(cells, meta) of the C-ABI board format -> oracle board (CPU legs only)"""
+    from oracle.board import OBoard
+    b = OBoard(W, H, N_IN_ROW)
+    b.init_board(0)
+    b.states = {int(m): int(cells[m]) for m in np.nonzero(cells)[0]}
+    b.availables = [m for m in range(W * H) if m not in b.states]
+    b.current_player, b.last_move = int(meta[0]), int(meta[1])
+    recent = [int(h) for h in meta[3:7] if h >= 0]  # most recent first; only the last four plies are ordered
+    b.history = [(m, p) for m, p in b.states.items() if m not in recent] + [(m, b.states[m]) for m in reversed(recent)]
+    return b
+
+
+def synthetic_position_cpu(index):
+    """The SAME position game `index` of the GPU arm starts from (draw_position with RandomState(1234 + index),
+    redrawn while the random play already ended the game), as an oracle board."""
+    rs = np.random.RandomState(1234 + index)
+    while True:
+        b = oracle_board_from_position(*draw_position(rs))
+        if not b.game_end()[0]:
+            return b
+
+
 def _cpu_worker(args):
-    """One process: oracle MCTS + oracle net (PyTorch-CPU fp32, 1 thread), n_moves move searches."""
+    """One process: oracle MCTS + oracle net (PyTorch-CPU fp32, 1 thread), n_moves move searches from the synthetic
+    position of game `seed` (0 - 60 stones, the GPU arm's own positions)."""
     seed, n_moves, n_playout, params = args
     import torch
     torch.set_num_threads(1)
-    from oracle.board import OBoard
     from oracle.mcts import OMCTSPlayer
     from oracle.net import ONet
     net = ONet(W, H, arch=ARCH, params=params)
-    rs = np.random.RandomState(seed)
-    b = OBoard(W, H, N_IN_ROW)
-    b.init_board(0)
-    for m in rs.permutation(W * H)[:2 * rs.randint(0, 8)]:
-        b.do_move(int(m))
+    b = synthetic_position_cpu(seed)
     player = OMCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=n_playout, is_selfplay=1)
     np.random.seed(seed)
     t0 = time.perf_counter()
@@ -168,8 +200,7 @@ def cpu_baseline_single(params, n_moves=2):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     net = ONet(W, H, arch=ARCH, params=params)
-    b = OBoard(W, H, N_IN_ROW)
-    b.init_board(0)
+    b = synthetic_position_cpu(0)
     player = OMCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=N_PLAYOUT, is_selfplay=1)
     np.random.seed(0)
     t0 = time.perf_counter()
@@ -177,8 +208,9 @@ def cpu_baseline_single(params, n_moves=2):
         b.do_move(int(player.get_action(b, temp=1.0)))
     dt = time.perf_counter() - t0
     return {"value": n_moves * N_PLAYOUT / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "oracle port (Python MCTS + PyTorch-CPU fp32 stand-in for MXNet, batch 1): 1 game, %d moves x %d "
-                      "playouts on 15x15, %.1f s" % (n_moves, N_PLAYOUT, dt)}
+            "sample": "oracle port (Python MCTS + PyTorch-CPU fp32 stand-in for MXNet, batch 1): 1 game (synthetic position 0 "
+                      "of the GPU arm), %d moves x %d playouts on 15x15, all %d host threads to the net, %.1f s"
+                      % (n_moves, N_PLAYOUT, threads, dt)}
 
 
 def run_reference(args):
@@ -197,19 +229,20 @@ def run_reference(args):
     with ctx.Pool(procs) as pool:
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(1000 * step + p, 1, N_PLAYOUT, params) for p in range(procs)])
+            res = pool.map(_cpu_worker, [((step * procs + p) % G_PER_GPU, 1, N_PLAYOUT, params) for p in range(procs)])
             dt = time.perf_counter() - t0
             if step >= args.warmup:
                 per_step.append((sum(r[0] for r in res), dt))
     playouts = sum(p for p, _ in per_step)
     secs = sum(t for _, t in per_step)
     value = playouts / secs
-    sample = ("%d processes x 1 game x 1 move x %d playouts per step (host-saturated, 1 torch thread each)"
-              % (procs, N_PLAYOUT))
+    sample = ("%d processes (= host cores) x 1 game x 1 move x %d playouts per step, each from one of the GPU arm's synthetic "
+              "positions (0 - 60 stones), host-saturated, 1 torch thread each" % (procs, N_PLAYOUT))
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(1, len(per_step)),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(G_PER_GPU), "l2": "n/a (CPU)"},
+           "config": {"workload": workload_name(G_PER_GPU), "games_per_gpu": G_PER_GPU, "n_playout": N_PLAYOUT,
+                      "net": NETS[ARCH][0], "l2": "n/a (CPU)", "host_cores": procs},
            "moves_per_s": value / N_PLAYOUT,
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,20 +253,64 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+class Ctx(object):
+    """process-wide state of one bench run: rank / world / device and the NCCL group (one process per GPU)"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            self.peak_src = "measured"
+        except Exception:
+            self.peaks, self.peak_src = {}, "fallback (B200_PROFILING.md)"
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op="max"):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
 def ncu_conv_traffic(G):
     """dram bytes (read + write) per conv launch, averaged over the trunk launches of the committed ncu launch
     list of this workload (profiles/, `ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum` on
     tools/profile_step.py --games 4096).  None when the list is missing or the batch differs."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_launches_v7_final.csv")
-    if G != 4096 or not os.path.exists(path):
+    for name in ("r2_launches_final.csv", "r1_launches_v7_final.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            break
+    else:
+        return None, None
+    if G != 4096:
         return None, None
     per = {}
     with open(path) as f:
         rows = [r for r in csv.reader(f) if len(r) > 5]
     h = {k: i for i, k in enumerate(rows[0])}
     for r in rows[1:]:
-        if "k_conv3x3_tc" in r[h["Kernel Name"]] and r[h["Metric Name"]].startswith("dram__bytes"):
+        if "k_conv" in r[h["Kernel Name"]] and r[h["Metric Name"]].startswith("dram__bytes"):
             per.setdefault(r[h["ID"]], 0.0)
             per[r[h["ID"]]] += float(r[h["Metric Value"]])
     if not per:
@@ -241,155 +318,130 @@ def ncu_conv_traffic(G):
     return sum(per.values()) / len(per), os.path.relpath(path, ROOT)
 
 
-def run_gpu(args):
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
+def az_leg(ctx, args, arch, steps, warmup, G, e2e=True, cpu=False):
+    """BASELINE configs[1] shape with net `arch`: `steps` move searches of G games x N_PLAYOUT playouts per rank.
+    Returns the JSON line's dict on rank 0 (None elsewhere)."""
     import importlib
+    torch = ctx.torch
     from alphapig_b200.params import flop_per_leaf, init_params
     from alphapig_b200 import dist as apdist
-
-    G = args.games
-    arch = args.net
     n_blocks = NETS[arch][2]
     PolicyValueNet = importlib.import_module("alphapig_b200." + NETS[arch][0]).PolicyValueNet
     arg, aux = init_params(arch, W, H, n_blocks=n_blocks, seed=0, synthetic_stats=True)
     kw = {} if arch == "simple" else {"n_blocks": n_blocks}
-    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=local, **kw)
+    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=ctx.local, **kw)
     cap = N_PLAYOUT * W * H + 2
     eng = net.search_engine(n_in_row=N_IN_ROW, c_puct=C_PUCT, n_playout=N_PLAYOUT, n_games=G, node_capacity=cap)
-    if world > 1:
-        # the one collective of the path: post-train weight broadcast from the trainer rank (NCCL over NVLink)
+    if ctx.world > 1:
+        # the collective of THIS leg sits outside its timed region (the search itself has no cross-GPU traffic); the
+        # `loop` leg times the exchanges
         apdist.broadcast_weights(net, src=0)
-    cells, meta = synthetic_positions(eng, G, seed0=1234 + rank * G)
+    cells, meta = synthetic_positions(eng, G, seed0=1234 + ctx.rank * G)
     pin_cells = torch.from_numpy(cells).pin_memory().numpy()
     pin_meta = torch.from_numpy(meta).pin_memory().numpy()
     eng.boards_import(pin_cells, pin_meta)
     eng.search_profile(True)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def resident_step():
         eng.search_advance(-1)
         eng.search_run(N_PLAYOUT)
         return eng.search_timing()[0]
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         resident_step()
     eng.search_stats()
-    clocks = ClockSampler(local)
-    sync_all()
+    clocks = ClockSampler(ctx.local)
+    ctx.sync_all()
     clocks.start()
     l0 = eng.launch_count()
     dev_ms, phase_ms = 0.0, None
-    for _ in range(args.steps):
+    for _ in range(steps):
         dev_ms += resident_step()
         ph = eng.search_profile(True)
         phase_ms = ph if phase_ms is None else phase_ms + ph
-    sync_all()
+    ctx.sync_all()
     launches = eng.launch_count() - l0
     clk = clocks.stop()
     stats = eng.search_stats()
 
     # end to end through the public API with host buffers: H2D positions, search, D2H visit counts
-    e2e_s = 0.0
-    sync_all()
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        eng.boards_import(pin_cells, pin_meta)
-        eng.search_advance(-1)
-        eng.search_run(N_PLAYOUT)
-        count, acts, visits, _, rootn = eng.search_root()
-        if i >= args.warmup:
-            e2e_s += time.perf_counter() - t0
-    assert int(rootn.min()) == N_PLAYOUT and int(visits.sum()) == G * (N_PLAYOUT - 1)
-    sync_all()
-    h2d = pin_cells.nbytes + pin_meta.nbytes + 4 * G * 3
-    d2h = count.nbytes + acts.nbytes + visits.nbytes + rootn.nbytes
-
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_max = float(t[0]), float(t[1])
-    total_playouts = world * G * N_PLAYOUT * args.steps
+    e2e_s = h2d = d2h = 0.0
+    if e2e:
+        ctx.sync_all()
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            eng.boards_import(pin_cells, pin_meta)
+            eng.search_advance(-1)
+            eng.search_run(N_PLAYOUT)
+            count, acts, visits, _, rootn = eng.search_root()
+            if i >= warmup:
+                e2e_s += time.perf_counter() - t0
+        assert int(rootn.min()) == N_PLAYOUT and int(visits.sum()) == G * (N_PLAYOUT - 1)
+        ctx.sync_all()
+        h2d = pin_cells.nbytes + pin_meta.nbytes + 4 * G * 3
+        d2h = count.nbytes + acts.nbytes + visits.nbytes + rootn.nbytes
+    dev_ms_max, e2e_max = ctx.reduce([dev_ms, e2e_s])
+    total_playouts = ctx.world * G * N_PLAYOUT * steps
     value = total_playouts / (dev_ms_max / 1000.0)
-    e2e_value = total_playouts / e2e_max
-
-    if rank == 0:
-        peaks = {}
-        pk_src = "fallback"
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            pk_src = "measured (sustained)"
-        except Exception:
-            pass
-        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        n_conv = len(phase_ms) - 4
-        conv_ms = float(phase_ms[2:2 + n_conv].sum())
-        cfin = 256 if arch == "simple" else 128
-        head_flop = 2 * (cfin * 6 * W * H + 4 * (W * H) ** 2 + 2 * W * H)
-        conv_flop_leaf = flop_per_leaf(arch, W, H, n_blocks=n_blocks) - head_flop  # trunk convs only
-        lockstep = args.steps * N_PLAYOUT
-        conv_launches = lockstep * n_conv
-        # terminal leaves never reach the net (compacted out on the device): only evaluated leaves count as work
-        evaluated = stats["playouts"] - stats["terminal_leaves"]
-        achieved = conv_flop_leaf * evaluated / (conv_ms / 1000.0) / 1e12
-        traffic, traffic_src = ncu_conv_traffic(G) if arch == "simple" else (None, None)
-        roof = {"bound": "tensor", "kernel": "k_conv3x3_tc (%d launches per lock-step, all trunk layers)" % n_conv,
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_source": pk_src, "traffic": traffic, "traffic_source": traffic_src,
-                "avg_launch_ms": conv_ms / conv_launches,
-                "algorithmic_flop_per_launch_avg": conv_flop_leaf * evaluated / conv_launches,
-                "evaluated_leaves": int(evaluated), "terminal_leaves_skipped": int(stats["terminal_leaves"]),
-                "phase_ms_per_lockstep": {"select": float(phase_ms[0]) / lockstep, "features": float(phase_ms[1]) / lockstep,
-                                          "trunk_convs": [float(x) / lockstep for x in phase_ms[2:2 + n_conv]],
-                                          "heads": float(phase_ms[2 + n_conv]) / lockstep,
-                                          "expand_backup": float(phase_ms[3 + n_conv]) / lockstep}}
-        # tree kernels against the HBM roofline (they are latency bound; reported for honesty)
-        tree_bytes = 20 * stats["children_scanned"] + 20 * stats["children_written"] + 24 * stats["path_nodes"] + \
-            128 * stats["playouts"]
-        tree_ms = float(phase_ms[0] + phase_ms[3 + n_conv])
-        roof["tree_kernels"] = {"bound": "hbm", "achieved_gbs": tree_bytes / (tree_ms / 1000.0) / 1e9,
-                                "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)),
-                                "frac": tree_bytes / (tree_ms / 1000.0) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
-                                "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
-                                "terminal_leaf_frac": stats["terminal_leaves"] / max(1, stats["playouts"])}
-        cpu = None
-        if world == 1 and not args.no_cpu and arch == "simple":
-            cpu = cpu_baseline_single((arg, aux), n_moves=2)
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-               "config": {"workload": workload_name(G, arch), "games_per_gpu": G, "n_playout": N_PLAYOUT,
-                          "net": NETS[arch][0], "flop_per_leaf": flop_per_leaf(arch, W, H, n_blocks=n_blocks),
-                          "arithmetic": ("fp16 operands, fp32 TMEM accumulate (net); fp64 (tree)" if arch != "resnet" else
-                                         "hi + lo fp16 activations x error-diffusion-rounded fp16 weights, two products per K "
-                                         "step, fp32 TMEM accumulate (net, precision=%s); fp64 (tree)" % eng.net_precision),
-                          "l2": "working set (node pools + activation planes, >10 GB) is larger than L2; no flush needed",
-                          "timing": "CUDA events on the engine stream around each ap_search_run, summed over steps, max over ranks"},
-               "moves_per_s": value / N_PLAYOUT,
-               "clocks": clk,
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "timing": "wall clock around boards_import + search_advance + search_run + search_root"},
-               "gpu_launches": int(launches),
-               "roofline": roof}
-        if cpu is not None:
-            out["cpu_baseline"] = cpu
-        print(json.dumps(out))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    precision = eng.net_precision
+    net.close()
+    if ctx.rank != 0:
+        return None
+    peak_tf = float(ctx.peaks.get("bf16_tflops_sustained", 1400.0))
+    n_conv = len(phase_ms) - 4
+    conv_ms = float(phase_ms[2:2 + n_conv].sum())
+    cfin = 256 if arch == "simple" else 128
+    head_flop = 2 * (cfin * 6 * W * H + 4 * (W * H) ** 2 + 2 * W * H)
+    conv_flop_leaf = flop_per_leaf(arch, W, H, n_blocks=n_blocks) - head_flop  # trunk convs only
+    lockstep = steps * N_PLAYOUT
+    conv_launches = lockstep * n_conv
+    # terminal leaves never reach the net (compacted out on the device): only evaluated leaves count as work
+    evaluated = stats["playouts"] - stats["terminal_leaves"]
+    achieved = conv_flop_leaf * evaluated / (conv_ms / 1000.0) / 1e12
+    traffic, traffic_src = ncu_conv_traffic(G) if arch == "simple" else (None, None)
+    roof = {"bound": "tensor", "kernel": "conv trunk kernels (%d launches per lock-step)" % n_conv,
+            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+            "peak_source": ctx.peak_src + " (bf16 sustained: the kernels run inside a seconds-long power-capped step)",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "avg_launch_ms": conv_ms / conv_launches,
+            "algorithmic_flop_per_launch_avg": conv_flop_leaf * evaluated / conv_launches,
+            "evaluated_leaves": int(evaluated), "terminal_leaves_skipped": int(stats["terminal_leaves"]),
+            "phase_ms_per_lockstep": {"select": float(phase_ms[0]) / lockstep, "features": float(phase_ms[1]) / lockstep,
+                                      "trunk_convs": [float(x) / lockstep for x in phase_ms[2:2 + n_conv]],
+                                      "heads": float(phase_ms[2 + n_conv]) / lockstep,
+                                      "expand_backup": float(phase_ms[3 + n_conv]) / lockstep}}
+    # tree kernels against the HBM roofline (they are latency bound; reported for honesty, SURVEY 8(d))
+    tree_bytes = 20 * stats["children_scanned"] + 20 * stats["children_written"] + 24 * stats["path_nodes"] + \
+        128 * stats["playouts"]
+    tree_ms = float(phase_ms[0] + phase_ms[3 + n_conv])
+    hbm = float(ctx.peaks.get("hbm_gbs", 6650.0))
+    roof["tree_kernels"] = {"bound": "hbm", "achieved_gbs": tree_bytes / (tree_ms / 1000.0) / 1e9, "peak_gbs": hbm,
+                            "frac": tree_bytes / (tree_ms / 1000.0) / 1e9 / hbm,
+                            "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
+                            "mean_select_depth": stats["path_nodes"] / max(1, stats["playouts"]) - 1.0,
+                            "terminal_leaf_frac": stats["terminal_leaves"] / max(1, stats["playouts"])}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": steps,
+           "warmup": warmup, "ms_per_step": dev_ms_max / steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+           "config": {"workload": workload_name(G, arch), "games_per_gpu": G, "n_playout": N_PLAYOUT,
+                      "net": NETS[arch][0], "flop_per_leaf": flop_per_leaf(arch, W, H, n_blocks=n_blocks),
+                      "arithmetic": ("fp16 operands, fp32 TMEM accumulate (net); fp64 (tree)" if arch != "resnet" else
+                                     "hi + lo fp16 activations x error-diffusion-rounded fp16 weights, two products per K "
+                                     "step, fp32 TMEM accumulate (net, precision=%s); fp64 (tree)" % precision),
+                      "l2": "working set (node pools + activation planes, >10 GB) is larger than L2; no flush needed",
+                      "timing": "CUDA events on the engine stream around each ap_search_run, summed over steps, max over ranks",
+                      "host_cores": os.cpu_count()},
+           "moves_per_s": value / N_PLAYOUT,
+           "clocks": clk,
+           "gpu_launches": int(launches),
+           "roofline": roof}
+    if e2e:
+        out["e2e"] = {"value": total_playouts / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(d2h),
+                      "timing": "wall clock around boards_import + search_advance + search_run + search_root"}
+    if cpu:
+        out["cpu_baseline"] = cpu_baseline_single((arg, aux), n_moves=2)
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -432,153 +484,257 @@ def ncu_pure_launch(G):
             m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"), os.path.relpath(path, ROOT))
 
 
-def run_gpu_pure(args):
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def pure_leg(ctx, args, steps, warmup, G, cpu=False):
+    torch = ctx.torch
     from alphapig_b200.engine import Engine
-    G = args.games if args.games != G_PER_GPU else PURE_GAMES
     eng = Engine(width=W, height=H, n_in_row=N_IN_ROW, n_games=G, c_puct=5, n_playout=PURE_PLAYOUT,
-                 node_capacity=PURE_PLAYOUT * W * H + 2, device=local)
-    cells, meta = synthetic_positions(eng, G, seed0=1234 + rank * G)
+                 node_capacity=PURE_PLAYOUT * W * H + 2, device=ctx.local)
+    cells, meta = synthetic_positions(eng, G, seed0=1234 + ctx.rank * G)
     pin_cells = torch.from_numpy(cells).pin_memory().numpy()
     pin_meta = torch.from_numpy(meta).pin_memory().numpy()
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
+    for i in range(warmup):
         eng.pure_run(PURE_PLAYOUT, seed=i, rollout_mode=args.rollout_mode)
     eng.search_stats()
-    clocks = ClockSampler(local)
-    sync_all()
+    clocks = ClockSampler(ctx.local)
+    ctx.sync_all()
     clocks.start()
     l0 = eng.launch_count()
     dev_ms = 0.0
-    for i in range(args.steps):
+    for i in range(steps):
         eng.pure_run(PURE_PLAYOUT, seed=100 + i, rollout_mode=args.rollout_mode)
         dev_ms += eng.search_timing()[0]
-    sync_all()
+    ctx.sync_all()
     launches = eng.launch_count() - l0
     clk = clocks.stop()
     stats = eng.search_stats()
     e2e_s = 0.0
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
         eng.boards_import(pin_cells, pin_meta)
         mv = eng.pure_run(PURE_PLAYOUT, seed=200 + i, rollout_mode=args.rollout_mode)
-        if i >= args.warmup:
+        if i >= warmup:
             e2e_s += time.perf_counter() - t0
-    sync_all()
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total = world * G * PURE_PLAYOUT * args.steps
-    value = total / (float(t[0]) / 1000.0)
-    if rank == 0:
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            src = "measured (burst)"
-        except Exception:
-            peaks, src = {}, "fallback"
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        tree_bytes = 20 * stats["children_scanned"] + 20 * stats["children_written"] + 24 * stats["path_nodes"] + \
-            64 * stats["playouts"]
-        ach = tree_bytes / (dev_ms / 1000.0) / 1e9
-        traffic, issue_pct, traffic_src = ncu_pure_launch(G)
-        out = {"metric": "mcts_pure_playouts_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "f64 tree / u32 bitboards", "data": "synthetic",
-               "config": {"workload": "15x15 mcts_pure batched random-rollout player, %d playouts/move, %d games per GPU"
-                                      % (PURE_PLAYOUT, G),
-                          "l2": "node pools (%d games x %d nodes x 32 B) are larger than L2; no flush needed"
-                                % (G, PURE_PLAYOUT * W * H + 2),
-                          "timing": "CUDA events on the engine stream around the fused k_pure_run launch"},
-               "moves_per_s": value / PURE_PLAYOUT,
-               "rollout_plies_per_s": stats["rollout_plies"] / (dev_ms / 1000.0),
-               "rollout": ("permutation (one sorted random-key permutation of the empty cells + 8-step bit descent to "
-                           "the first line; plies = length of the random game it decides)" if args.rollout_mode == 0
-                           else "ply by ply"),
-               "clocks": clk,
-               "e2e": {"value": total / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": int(pin_cells.nbytes + pin_meta.nbytes),
-                       "d2h_bytes_per_step": int(mv.nbytes), "timing": "wall clock around boards_import + pure_run"},
-               "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": "k_pure_run (one launch = one move search for every game)",
-                            "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src,
-                            "traffic": traffic, "traffic_source": traffic_src,
-                            "issue_active_pct_ncu": issue_pct, "avg_launch_ms": dev_ms / args.steps,
-                            "algorithmic_bytes_per_launch": tree_bytes / args.steps,
-                            "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
-                            "note": "issue bound (73 % issue-active under ncu): register-resident rollouts and warp-level select.  "
-                                    "achieved = SURVEY 8(d)'s algorithmic bytes (what the reference's tree touches: every "
-                                    "child of every scanned / expanded node) over the launch time; the kernel itself keeps "
-                                    "children lazy and re-reads hot blocks from L2, so its DRAM traffic is ~2 % of that"}}
-        if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_pure_baseline()
-        print(json.dumps(out))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.sync_all()
+    dev_max, e2e_max = ctx.reduce([dev_ms, e2e_s])
+    total = ctx.world * G * PURE_PLAYOUT * steps
+    value = total / (dev_max / 1000.0)
+    eng.close()
+    if ctx.rank != 0:
+        return None
+    hbm = float(ctx.peaks.get("hbm_gbs", 6650.0))
+    tree_bytes = 20 * stats["children_scanned"] + 20 * stats["children_written"] + 24 * stats["path_nodes"] + \
+        64 * stats["playouts"]
+    ach = tree_bytes / (dev_ms / 1000.0) / 1e9
+    traffic, issue_pct, traffic_src = ncu_pure_launch(G)
+    out = {"metric": "mcts_pure_playouts_per_s", "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": steps,
+           "warmup": warmup, "ms_per_step": dev_max / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64 tree / u32 bitboards", "data": "synthetic",
+           "config": {"workload": "15x15 mcts_pure batched random-rollout player, %d playouts/move, %d games per GPU"
+                                  % (PURE_PLAYOUT, G),
+                      "l2": "node pools (%d games x %d nodes x 32 B) are larger than L2; no flush needed"
+                            % (G, PURE_PLAYOUT * W * H + 2),
+                      "timing": "CUDA events on the engine stream around the fused k_pure_run launch"},
+           "moves_per_s": value / PURE_PLAYOUT,
+           "rollout_plies_per_s": stats["rollout_plies"] / (dev_ms / 1000.0),
+           "rollout": ("permutation (one sorted random-key permutation of the empty cells + 8-step bit descent to "
+                       "the first line; plies = length of the random game it decides)" if args.rollout_mode == 0
+                       else "ply by ply"),
+           "clocks": clk,
+           "e2e": {"value": total / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(pin_cells.nbytes + pin_meta.nbytes),
+                   "d2h_bytes_per_step": int(mv.nbytes), "timing": "wall clock around boards_import + pure_run"},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": "k_pure_run (one launch = one move search for every game)",
+                        "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                        "peak_source": ctx.peak_src + " (hbm copy bandwidth)",
+                        "traffic": traffic, "traffic_source": traffic_src,
+                        "issue_active_pct_ncu": issue_pct, "avg_launch_ms": dev_ms / steps,
+                        "algorithmic_bytes_per_launch": tree_bytes / steps,
+                        "bytes_per_playout": tree_bytes / max(1, stats["playouts"]),
+                        "note": "issue bound (73 % issue-active under ncu): register-resident rollouts and warp-level select.  "
+                                "achieved = SURVEY 8(d)'s algorithmic bytes (what the reference's tree touches: every "
+                                "child of every scanned / expanded node) over the launch time; the kernel itself keeps "
+                                "children lazy and re-reads hot blocks from L2, so its DRAM traffic is ~2 % of that"}}
+    if cpu:
+        out["cpu_baseline"] = cpu_pure_baseline()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
-# real self-play plies (BatchedSelfPlay.step: search + host-side sampling, recording, re-rooting); `--workload selfplay`
+# real self-play plies (BatchedSelfPlay.step: search + move sampling, recording, re-rooting); `--workload selfplay`
 # ------------------------------------------------------------------------------------------
-def run_gpu_selfplay(args):
-    import torch
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
+def selfplay_leg(ctx, args, steps, warmup, G):
+    torch = ctx.torch
     from alphapig_b200.params import init_params
     from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
     from alphapig_b200.selfplay import BatchedSelfPlay, PipelinedSelfPlay
-    G = args.games
     arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
-    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=local)
-    kw = dict(n_playout=N_PLAYOUT, c_puct=C_PUCT, temp=1.0, n_in_row=N_IN_ROW, seed=0, node_capacity=2 * N_PLAYOUT * W * H + 2)
+    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=ctx.local)
+    kw = dict(n_playout=N_PLAYOUT, c_puct=C_PUCT, temp=1.0, n_in_row=N_IN_ROW, seed=ctx.rank)
+    groups = 1 if args.device_pick else args.groups
     if args.device_pick:
-        args.groups = 1
         kw["device_pick"] = True
-    sp = PipelinedSelfPlay(net, G, n_groups=args.groups, **kw) if args.groups > 1 else BatchedSelfPlay(net, G, **kw)
-    parts = sp.groups if args.groups > 1 else [sp]
+        kw["device_records"] = bool(args.device_records)
+    sp = PipelinedSelfPlay(net, G, n_groups=groups, **kw) if groups > 1 else BatchedSelfPlay(net, G, **kw)
+    parts = sp.groups if groups > 1 else [sp]
     cm, k = [], 0
     for part in parts:
-        cm.append(synthetic_positions(part.eng, part.G, seed0=1234 + k))
+        cm.append(synthetic_positions(part.eng, part.G, seed0=1234 + ctx.rank * G + k))
         k += part.G
-    cells = np.concatenate([c for c, _ in cm])
-    meta = np.concatenate([m for _, m in cm])
-    sp.load_positions(cells, meta)
-    calls = args.groups if args.groups > 1 else 1   # one pipelined step() advances one group
-    for _ in range(args.warmup * calls):
+    sp.load_positions(np.concatenate([c for c, _ in cm]), np.concatenate([m for _, m in cm]))
+    calls = groups if groups > 1 else 1   # one pipelined step() advances one group
+    for _ in range(warmup * calls):
         sp.step()
-    torch.cuda.synchronize()
+    ctx.sync_all()
+    # The pipelined forms keep the NEXT ply's search in flight when step() returns.  One more untimed step after the
+    # barrier puts every rank right behind such a launch; the timed region then is exactly `steps` periods of
+    # [join search t, pick / record / re-root t, launch search t + 1] and ends right behind a launch again.
+    for _ in range(calls):
+        sp.step()
+    for part in parts:
+        if not args.device_pick:
+            part.eng.search_stats()
+    clocks = ClockSampler(ctx.local)
+    clocks.start()
     host0 = sp.host_seconds
     t0 = time.perf_counter()
     games = moves = 0
-    for _ in range(args.steps * calls):
+    for _ in range(steps * calls):
         games += len(sp.step())
-        moves += sp.last_moves if args.groups > 1 else G
+        moves += sp.last_moves if groups > 1 else G
     dt = time.perf_counter() - t0
-    if args.groups > 1 or args.device_pick:
-        sp.drain()
-    print(json.dumps({"metric": "selfplay_moves_per_s", "value": moves / dt, "unit": "moves/s", "n_gpus": 1,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
-                      "higher_is_better": True, "data": "synthetic start positions, then real self-play with tree reuse",
-                      "playouts_per_s": moves * N_PLAYOUT / dt,
-                      "host_ms_per_step": 1000 * (sp.host_seconds - host0) / args.steps, "groups": args.groups,
-                      "move_sampling": "device (ap_selfplay_pick), next search overlapped with the host bookkeeping"
-                                       if args.device_pick else "host (numpy)",
-                      "games_finished": games,
-                      "config": {"workload": "BatchedSelfPlay.step: %d games, n_playout=%d, temp=1.0, Dirichlet noise, records kept"
-                                             % (G, N_PLAYOUT)}}))
+    clk = clocks.stop()
+    sp.drain()
+    dt_max, = ctx.reduce([dt])
+    moves_all, games_all = ctx.reduce([moves, games], op="sum")
+    host_ms = 1000 * (sp.host_seconds - host0) / steps
+    forced = sum(getattr(part, "forced_openings", 0) for part in parts)
+    cap = [part.eng.node_capacity() for part in parts]
+    net.close()
+    if ctx.rank != 0:
+        return None
+    return {"metric": "selfplay_moves_per_s", "value": moves_all / dt_max, "unit": "moves/s", "n_gpus": ctx.world,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1000 * dt_max / steps,
+            "higher_is_better": True, "data": "synthetic start positions, then real self-play with tree reuse",
+            "playouts_per_s": moves_all * N_PLAYOUT / dt_max,
+            "host_ms_per_step": host_ms, "groups": groups,
+            "move_sampling": ("device (ap_selfplay_pick), next search overlapped with the host bookkeeping"
+                              if args.device_pick else "host (numpy)"),
+            "records": ("device trajectories + outbox (ap_traj_*)" if args.device_pick and args.device_records
+                        else "host (features + pi copied per ply)"),
+            "games_finished": int(games_all), "forced_openings": int(forced),
+            "node_capacity": cap, "clocks": clk,
+            "timing": "wall clock over `steps` whole periods of every game's ply (search + sampling + re-root + records; the "
+                      "region starts and ends right behind the launch of the next ply's search), max over ranks",
+            "config": {"workload": "BatchedSelfPlay.step: %d games per GPU, n_playout=%d, temp=1.0, Dirichlet noise, records kept, "
+                                   "tree reuse" % (G, N_PLAYOUT)}}
+
+
+# ------------------------------------------------------------------------------------------
+# configs[4]: self-play + train loop, collectives inside the timed region; `--workload loop`
+# ------------------------------------------------------------------------------------------
+def loop_leg(ctx, args, iters, warmup_iters, G, plies=2):
+    from alphapig_b200.loop import selfplay_train_loop
+    from alphapig_b200.params import init_params
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
+    net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=ctx.local)
+    clocks = ClockSampler(ctx.local)
+    clocks.start()
+    res = selfplay_train_loop(net, G, iters, plies_per_iter=plies, n_playout=N_PLAYOUT, c_puct=C_PUCT, temp=1.0,
+                              batch_size=128, epochs=8, seed=7, warmup_iters=warmup_iters, overlap=not args.no_overlap)
+    clk = clocks.stop()
+    t_max, coll_max, wait_max = ctx.reduce([res["t_total"], res.get("t_collectives", 0.0), res.get("t_wait_trainer", 0.0)])
+    playouts, plies_all, games, recs = ctx.reduce([res["playouts"], res["plies"], res["games"], res["records"]], op="sum")
+    net.close()
+    if ctx.rank != 0:
+        return None
+    return {"metric": "loop_playouts_per_s", "value": playouts / t_max, "unit": UNIT, "n_gpus": ctx.world,
+            "moves_per_s": plies_all / t_max, "iters": iters, "warmup_iters": warmup_iters, "plies_per_iter": plies,
+            "seconds": t_max, "higher_is_better": True,
+            "games_finished": int(games), "records_to_trainer": int(recs),
+            "train_steps": res.get("train_steps"), "trainer_seconds": res.get("t_trainer"),
+            "last_losses": (res.get("losses") or [])[-3:], "last_kls": (res.get("kls") or [])[-3:],
+            "lr_multiplier": res.get("lr_multiplier"), "weight_swaps": res.get("weight_swaps"),
+            "collectives": {"in_timed_region": True,
+                            "what": "per iteration: counts all-gather + record gather to the trainer rank (device memory) "
+                                    "and one broadcast of the flat fp32 weights, NCCL" if ctx.world > 1 else "none (1 GPU)",
+                            "seconds_main_thread_max": coll_max, "wait_for_trainer_seconds_max": wait_max,
+                            "bytes_gathered": res.get("bytes_gathered"), "bytes_broadcast": res.get("bytes_broadcast")},
+            "overlap": bool(res.get("overlap")), "clocks": clk,
+            "timing": "wall clock from the ply boundary after the warm-up iterations to the end of the last iteration's "
+                      "last search (barrier + synchronize both sides), max over ranks",
+            "config": {"workload": "self-play + train loop (configs[4]): %d games per GPU, n_playout=%d, simple net, %d plies per "
+                                   "iteration, policy_update (batch 128, <= 8 epochs, KL rule) on rank 0 overlapped with search"
+                                   % (G, N_PLAYOUT, plies)}}
+
+
+# ------------------------------------------------------------------------------------------
+# configs[0]'s GPU side: ONE game through the reference-named shims (what human_play / ChessClient pay per move)
+# ------------------------------------------------------------------------------------------
+def single_game_leg(ctx, n_moves=6):
+    from alphapig_b200.game import Board
+    from alphapig_b200.mcts_alphaZero import MCTSPlayer
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    out = {"n_playout": N_PLAYOUT, "what": "MCTSPlayer.get_action(board, temp=1.0) wall clock per move, one game, "
+                                            "is_selfplay=1 (tree reuse); first two moves are warm-up"}
+    for Wb in (8, 15):
+        net = PolicyValueNet(Wb, Wb, batch_size=128, seed=0)
+        player = MCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=N_PLAYOUT, is_selfplay=1)
+        b = Board(width=Wb, height=Wb, n_in_row=N_IN_ROW)
+        b.init_board(0)
+        np.random.seed(0)
+        ts = []
+        for _ in range(n_moves + 2):
+            t0 = time.perf_counter()
+            mv = player.get_action(b, temp=1.0)
+            ts.append(time.perf_counter() - t0)
+            b.do_move(mv)
+        ts = np.array(ts[2:])
+        out["%dx%d" % (Wb, Wb)] = {"ms_per_move": 1e3 * float(ts.mean()), "min_ms": 1e3 * float(ts.min()),
+                                  "playouts_per_s": N_PLAYOUT / float(ts.mean())}
+        del player
+        net.close()
+    return out
+
+
+def run_gpu(args):
+    ctx = Ctx()
+    G = args.games
+    if args.workload == "pure":
+        out = pure_leg(ctx, args, args.steps, args.warmup, G if G != G_PER_GPU else PURE_GAMES,
+                       cpu=ctx.world == 1 and not args.no_cpu)
+    elif args.workload == "selfplay":
+        out = selfplay_leg(ctx, args, args.steps, args.warmup, G)
+    elif args.workload == "loop":
+        out = loop_leg(ctx, args, args.steps, 1, G)
+    else:
+        headline = args.net == "simple"
+        out = az_leg(ctx, args, args.net, args.steps, args.warmup, G, e2e=True,
+                     cpu=ctx.world == 1 and not args.no_cpu and headline)
+        if headline and args.legs != "none":
+            legs = {}
+            args.device_pick, args.device_records = True, True
+            legs["selfplay"] = selfplay_leg(ctx, args, 3, 1, G)
+            legs["loop"] = loop_leg(ctx, args, 2, 1, G)
+            if ctx.world == 1:
+                legs["pure"] = pure_leg(ctx, args, 5, 3, PURE_GAMES, cpu=False)
+                legs["resnet10"] = az_leg(ctx, args, "resnet", 2, 1, G, e2e=False)
+                legs["inception"] = az_leg(ctx, args, "inception", 3, 2, G, e2e=False)
+                legs["single_game_ms"] = single_game_leg(ctx)
+            if ctx.rank == 0:
+                out["moves_per_s_search_only"] = out["moves_per_s"]
+                out["moves_per_s"] = legs["selfplay"]["value"]
+                out["moves_per_s_note"] = ("played self-play moves per second (the `selfplay` leg: every ply decided by a full "
+                                           "400-playout search, sampled, recorded and re-rooted); moves_per_s_search_only = "
+                                           "value / n_playout")
+                for k, v in legs.items():
+                    if k in ("resnet10", "inception") and v is not None:
+                        v = {kk: v[kk] for kk in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config",
+                                                   "clocks", "gpu_launches", "roofline")}
+                    out[k] = v
+    if ctx.rank == 0:
+        print(json.dumps(out))
+    ctx.close()
 
 
 def main():
@@ -589,23 +745,26 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--games", type=int, default=G_PER_GPU, help="concurrent games per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--legs", default="all", choices=["all", "none"],
+                    help="default az run: all = append the selfplay / loop / pure / resnet10 / inception / single-game "
+                         "sub-measurements to the line; none = headline only")
     ap.add_argument("--groups", type=int, default=2, help="selfplay workload: pipelined game groups (1 = none)")
     ap.add_argument("--device-pick", action="store_true",
                     help="selfplay workload: one group, moves sampled on the device, next search overlapped with the host phase")
+    ap.add_argument("--device-records", action="store_true",
+                    help="selfplay workload with --device-pick: records stay on the device (trajectories + outbox)")
+    ap.add_argument("--no-overlap", action="store_true", help="loop workload: the synchronous loop (A/B)")
     ap.add_argument("--rollout-mode", type=int, default=0, choices=[0, 2],
                     help="pure workload: 0 = permutation rollouts (default), 2 = ply-by-ply rollouts (A/B)")
     ap.add_argument("--net", default="simple", choices=sorted(NETS),
                     help="az workload: simple = BASELINE configs[1] (default, the headline); resnet = the 10-block net the "
                          "reference trains; inception = configs[3] (builder-defined variant)")
-    ap.add_argument("--workload", default="az", choices=["az", "pure", "selfplay"],
-                    help="az = BASELINE configs[1] (default, the headline metric); pure = configs[2] (mcts_pure, 1000 playouts)")
+    ap.add_argument("--workload", default="az", choices=["az", "pure", "selfplay", "loop"],
+                    help="az = BASELINE configs[1] (default, the headline metric); pure = configs[2] (mcts_pure, 1000 playouts); "
+                         "selfplay = real self-play plies; loop = configs[4] (self-play + train, collectives timed)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "pure":
-        run_gpu_pure(args)
-    elif args.workload == "selfplay":
-        run_gpu_selfplay(args)
     else:
         run_gpu(args)
 

@@ -203,6 +203,20 @@ assert allp.shape == (8, D.record_width(S))
 _, _, z = D.unpack_records(allp, S, 6, 6)
 assert list(z) == [0.0] * 3 + [1.0] * 5
 assert np.array_equal(allp[3 * rank: 3 * rank + n] if rank == 0 else allp[3:], packed)
+# (1b) the device-tensor form (CPU tensors under gloo): to every rank, and to the trainer rank only
+t = torch.from_numpy(packed)
+parts = D.gather_records_device(t)
+assert [p.shape[0] for p in parts] == [3, 5] and torch.equal(parts[rank], t)
+assert np.array_equal(torch.cat(parts).numpy(), allp)
+parts0 = D.gather_records_device(t, dst=0)
+if rank == 0:
+    assert np.array_equal(torch.cat(parts0).numpy(), allp)
+else:
+    assert parts0 == []
+bits2, pis2, z2 = D.split_records(allp, S)
+st_u, pi_u, z_u = D.unpack_records(allp, S, 6, 6)
+assert np.array_equal(np.unpackbits(bits2, axis=1)[:, :9 * S].reshape(-1, 9, 6, 6).astype(np.float32), st_u)
+assert np.array_equal(pis2, pi_u) and np.array_equal(z2, z_u)
 # (2) weight broadcast through the same code path the GPU build uses (flat buffer + sync hook)
 class FakeNet:
     def __init__(self):

@@ -88,3 +88,107 @@ def test_train_pipeline_small(tmp_path):
     p1, v1 = net.policy_value(x)
     p2, v2 = net2.policy_value(x)
     assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+
+
+def _play_and_collect(device_records, W, n_in_row, G, n_playout, seed, max_plies, opening_prob):
+    """finished-game records of BatchedSelfPlay(device_pick=True), host-assembled or from the device outbox, as one
+    (bits, pi, z) triple in emission order"""
+    from alphapig_b200 import dist as apdist
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    from alphapig_b200.selfplay import BatchedSelfPlay
+    S = W * W
+    net = PolicyValueNet(W, W, batch_size=32, seed=0, n_in_row=n_in_row)
+    sp = BatchedSelfPlay(net, n_games=G, n_playout=n_playout, n_in_row=n_in_row, seed=seed, device_pick=True,
+                         device_records=device_records, forced_opening_prob=opening_prob)
+    bits, pis, zs, winners, boxes = [], [], [], [], []
+    if device_records:
+        sp.boundary_hook = lambda s: boxes.append(s.take_outbox())
+    for _ in range(max_plies):
+        for winner, st, pi, z in sp.step():
+            winners.append(winner)
+            if not device_records:
+                bits.append(st)
+                pis.append(pi.astype(np.float32))
+                zs.append(z.astype(np.float32))
+    sp.drain()
+    forced = sp.forced_openings
+    if device_records:
+        rec = np.concatenate([b.cpu().numpy() for b in boxes], axis=0)
+        assert rec.shape[1] == apdist.record_width(S)
+        b_, p_, z_ = apdist.split_records(rec, S)
+        out = (b_, p_, z_)
+    else:
+        out = (np.concatenate(bits), np.concatenate(pis), np.concatenate(zs))
+    net.close()
+    return out, winners, forced
+
+
+@pytest.mark.parametrize("W,n_in_row,G,n_playout,plies,opening", [(6, 4, 48, 20, 30, 0.0), (15, 5, 12, 12, 150, 1.0)])
+def test_device_trajectories_equal_host_assembled_records(W, n_in_row, G, n_playout, plies, opening):
+    """Device-side trajectories + outbox (csrc/traj.cu: every pick appends its ply's packed record in HBM, finished games
+    move to the outbox with z filled in) against the host-assembled records of the same self-play run (same Philox
+    seeds => same moves): bit-identical state planes, pi and z, in the same order - including, on 15x15, the forced
+    random two-ply opening records of game_ai.py:78-111 (probability forced to 1 here)."""
+    host, w_host, f_host = _play_and_collect(False, W, n_in_row, G, n_playout, 5, plies, opening)
+    devc, w_dev, f_dev = _play_and_collect(True, W, n_in_row, G, n_playout, 5, plies, opening)
+    assert w_host == w_dev and len(w_host) >= (20 if W == 6 else 3) and f_host == f_dev
+    if opening:
+        assert f_host >= G
+    assert host[0].shape == devc[0].shape and host[0].shape[0] > 0
+    assert np.array_equal(host[0], devc[0]), "state bits"
+    assert np.array_equal(host[1], devc[1]), "pi"
+    assert np.array_equal(host[2], devc[2]), "z"
+    if opening:  # the first two records of a game are the forced plies: pi = 0.99999 at the move, 1e-6 elsewhere
+        pi0 = devc[1][0]
+        assert np.isclose(pi0.max(), 0.99999) and np.isclose(np.sort(pi0)[-2], 1e-6)
+
+
+def test_ring_push_packed_equals_push():
+    """ap_replay_push_packed (host pointer and device pointer) fills the ring exactly as ap_replay_push does."""
+    import torch
+    from alphapig_b200 import dist as apdist
+    from alphapig_b200.engine import Engine
+    W = 8
+    S = W * W
+    rs = np.random.RandomState(3)
+    n = 37
+    bits = np.packbits((rs.rand(n, 9 * S) > 0.6).astype(np.uint8), axis=1)
+    pis = rs.dirichlet(np.ones(S), size=n).astype(np.float32)
+    zs = rs.choice([-1.0, 0.0, 1.0], size=n).astype(np.float32)
+    packed = apdist.pack_records(bits, pis, zs, S)
+    engs = [Engine(width=W, height=W, n_games=1) for _ in range(3)]
+    for e in engs:
+        e.replay_create(8 * 20)  # smaller than n records: the ring wraps
+    engs[0].replay_push(bits, pis, zs)
+    engs[1].replay_push_packed(packed)
+    t = torch.from_numpy(packed).cuda()
+    engs[2].replay_push_packed(None, n=n, device_ptr=t.data_ptr())
+    ref = engs[0].replay_gather(np.arange(8 * 20))
+    for e in engs[1:]:
+        assert e.replay_size() == engs[0].replay_size()
+        got = e.replay_gather(np.arange(8 * 20))
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+    for e in engs:
+        e.close()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_selfplay_train_loop_single_gpu(overlap):
+    """configs[4] on one GPU, small board: games finish, their records reach the ring (device outbox -> packed push in the
+    overlapped loop), policy_update runs (in the trainer thread, overlapped with search), new weights are swapped into
+    the search engine at ply boundaries and the searches keep working on them."""
+    from alphapig_b200.loop import selfplay_train_loop
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    W = 6
+    net = PolicyValueNet(W, W, batch_size=32, seed=0, n_in_row=4)
+    w0 = net.get_policy_param()[0]["conv1_weight"].copy()
+    res = selfplay_train_loop(net, 64, 4, plies_per_iter=8, n_playout=16, batch_size=32, epochs=3, buffer_size=20000,
+                              n_in_row=4, seed=1, overlap=overlap, warmup_iters=1 if overlap else 0)
+    assert res["overlap"] == overlap and res["games"] > 20 and res["records"] >= 7 * res["games"] * (0 if overlap else 1)
+    assert res["train_steps"] >= 3 and np.isfinite(res["losses"]).all()
+    assert res["playouts"] == 4 * 8 * 64 * 16 and res["t_total"] > 0
+    if overlap:
+        assert res["weight_swaps"] >= 3 and res["ring_records"] >= res["records"] > 0
+        assert res["lr_multiplier"] in (1.0, 1.5, 2.25, 3.375, 1 / 1.5, 1 / 2.25, 1 / 3.375, 5.0625, 1 / 5.0625)
+    assert not np.array_equal(w0, net.get_policy_param()[0]["conv1_weight"])
+    net.close()

@@ -21,7 +21,9 @@ ap.add_argument("--arch", default="simple")
 ap.add_argument("--blocks", type=int, default=10)
 ap.add_argument("--epochs", type=int, default=8)
 ap.add_argument("--batch", type=int, default=128)
-ap.add_argument("--device-pick", action="store_true", help="sample the self-play moves on the device (ap_selfplay_pick)")
+ap.add_argument("--device-pick", action="store_true", help="synchronous loop: sample the self-play moves on the device")
+ap.add_argument("--no-overlap", action="store_true", help="the synchronous loop (host-staged records, engines drained while training)")
+ap.add_argument("--warmup-iters", type=int, default=1)
 a = ap.parse_args()
 
 import torch  # noqa: E402
@@ -40,20 +42,19 @@ else:
     from alphapig_b200.policy_value_net_mxnet import PolicyValueNet
     net = PolicyValueNet(a.board, a.board, batch_size=a.batch, n_blocks=a.blocks, device=local, seed=0)
 res = selfplay_train_loop(net, a.games, a.iters, plies_per_iter=a.plies, n_playout=a.playouts, batch_size=a.batch,
-                          epochs=a.epochs, log=lambda s: print(s, file=sys.stderr), device_pick=a.device_pick)
-t = torch.tensor([res["t_selfplay"] + res["t_exchange"] + res["t_train"], res["t_selfplay"], res["t_exchange"], res["t_train"]],
-                 dtype=torch.float64, device="cuda")
+                          epochs=a.epochs, log=lambda s: print(s, file=sys.stderr), device_pick=a.device_pick,
+                          overlap=not a.no_overlap, warmup_iters=a.warmup_iters)
+t = torch.tensor([res["t_total"]], dtype=torch.float64, device="cuda")
 cnt = torch.tensor([res["plies"], res["playouts"], res["games"]], dtype=torch.float64, device="cuda")
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
 if int(os.environ.get("RANK", "0")) == 0:
+    keep = {k: v for k, v in res.items() if k not in ("losses", "kls")}
     print(json.dumps({"workload": "self-play + train loop, %s net, %d games/GPU, n_playout %d" % (a.arch, a.games, a.playouts),
                       "n_gpus": world, "moves_per_s": float(cnt[0] / t[0]), "playouts_per_s": float(cnt[1] / t[0]),
-                      "games_finished": int(cnt[2]), "train_steps": res["train_steps"], "records": res["records"],
-                      "seconds": {"total": float(t[0]), "selfplay": float(t[1]), "exchange": float(t[2]),
-                                  "train_and_broadcast": float(t[3])},
-                      "last_losses": res["losses"][-3:]}))
+                      "games_finished": int(cnt[2]), "seconds_total_max": float(t[0]), "rank0": keep,
+                      "last_losses": res.get("losses", [])[-3:]}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
