@@ -58,6 +58,7 @@ SIGNATURES = {
     "ap_search_expand_backup": (C.c_int, [_P, _P, _P, _P, _P]),
     "ap_search_expand_backup_dense": (C.c_int, [_P, _P, _P]),
     "ap_search_run": (C.c_int, [_P, _I]),
+    "ap_search_run_vl": (C.c_int, [_P, _I, _I]),
     "ap_search_root": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "ap_search_root_probs": (C.c_int, [_P, C.c_double, _P]),
     "ap_search_advance": (C.c_int, [_P, _P, _I, _P]),

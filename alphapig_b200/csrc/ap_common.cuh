@@ -107,6 +107,16 @@ struct ap_engine {
   int32_t* d_max_alloc = nullptr;
   // small batches (interactive play: one game) are launch-latency bound: the n_playout lock-steps of ap_search_run are
   // captured once into a CUDA graph and replayed; rebuilt when n_playout or the prepared weights change
+  // opt-in multi-leaf mode (ap_search_run_vl): leaf records for G * vl_kstride leaves, per-node in-flight visit counts
+  Leaves leaves_vl{};
+  int vl_kstride = 0;
+  int32_t* vn = nullptr;  // [G][cap] virtual visits (all zero between lock-steps)
+  int vn_cap = 0;
+  int32_t* vl_remain = nullptr;  // [G]
+  int32_t* vl_issued = nullptr;  // [G]
+  cudaGraphExec_t vl_graph = nullptr;
+  int vl_graph_playouts = 0, vl_graph_k = 0;
+  uint64_t vl_graph_gen = 0, vl_graph_launches = 0;
   cudaGraphExec_t run_graph = nullptr;
   int run_graph_playouts = 0;
   uint64_t run_graph_gen = 0, run_graph_launches = 0;
@@ -166,6 +176,8 @@ int net_emit_features_launch(ap_engine* e, bool compact = false);
 int net_check_err(ap_engine* e);
 int net_phase_count(ap_engine* e);
 bool net_can_compact(ap_engine* e);
+int net_board_capacity(ap_engine* e);
+int net_run_compacted(ap_engine* e, int nb_max, const int32_t* nb_dev);
 void net_feature_planes(ap_engine* e, __half** feat, long long* mpad);
 void net_fc_finish_args(ap_engine* e, const float** partial, const float** bias, long long* rows, int* np, int* ksplit);
 void prof_mark(ap_engine* e);

@@ -268,6 +268,10 @@ int ap_engine_destroy(ap_engine* e) {
     cudaGraphExecDestroy(e->run_graph);
     e->run_graph = nullptr;
   }
+  if (e && e->vl_graph) {
+    cudaGraphExecDestroy(e->vl_graph);
+    e->vl_graph = nullptr;
+  }
   AP_ENTER(e);
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
@@ -577,6 +581,113 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
         e->prof_ms[ph] += ms;
       }
   }
+  AP_TRY(net_check_err(e));
+  return check_errflags(e);
+}
+
+// ---- opt-in multi-leaf search with virtual loss (kernels and semantics: tree.cu, k_select_vl) -------------------
+static int vl_prepare(ap_engine* e, int k) {
+  const size_t G = e->geo.G, S = e->geo.S;
+  if (e->vl_kstride < k) {
+    // leaf records for G * kstride leaves (the old ones, if any, stay in e->allocs until the handle dies)
+    const int ks = std::max(k, std::min(64, net_board_capacity(e) / (int)G));
+    const size_t L = G * (size_t)ks;
+    Leaves& lv = e->leaves_vl;
+    if (e->vl_graph) {
+      cudaGraphExecDestroy(e->vl_graph);
+      e->vl_graph = nullptr;
+    }
+#define VALLOC(ptr, bytes) AP_TRY(dev_alloc(e, (void**)&(ptr), (bytes)))
+    VALLOC(lv.rows, L * AP_ROWS * 4);
+    VALLOC(lv.meta, L * sizeof(BoardMeta));
+    VALLOC(lv.node, L * 4);
+    VALLOC(lv.terminal, L);
+    VALLOC(lv.winner, L);
+    VALLOC(lv.depth, L * 4);
+    VALLOC(lv.path, L * S * 2);
+    VALLOC(lv.slot, L * 4);
+    VALLOC(lv.game_of_slot, L * 4);
+    VALLOC(lv.n_eval, 4);
+    if (!e->vl_remain) {
+      VALLOC(e->vl_remain, G * 4);
+      VALLOC(e->vl_issued, G * 4);
+    }
+#undef VALLOC
+    lv.active = e->leaves.active;
+    e->vl_kstride = ks;
+  }
+  if (!e->vn || e->vn_cap != e->geo.cap) {  // follows the pools when they grow; all zero between lock-steps
+    if (e->vn) dev_free(e, e->vn, G * (size_t)e->vn_cap * 4);
+    e->vn = nullptr;
+    AP_TRY(dev_alloc(e, (void**)&e->vn, G * (size_t)e->geo.cap * 4));
+    e->vn_cap = e->geo.cap;
+  }
+  return AP_OK;
+}
+
+int ap_search_run_vl(ap_engine* e, int32_t n_playout, int32_t k) {
+  AP_ENTER(e);
+  if (!e->net) return ap_fail(e, AP_ERR_NO_NET, "ap_search_run_vl: no net loaded (ap_net_load)");
+  if (n_playout < 1 || k < 1) return ap_fail(e, AP_ERR_BAD_ARG, "ap_search_run_vl: n_playout >= 1, k >= 1");
+  if (!net_can_compact(e)) return ap_fail(e, AP_ERR_BAD_ARG, "ap_search_run_vl: this net has no compacted-batch path");
+  if ((long long)k * e->geo.G > net_board_capacity(e) || k > 64)
+    return ap_fail(e, AP_ERR_BAD_ARG, "ap_search_run_vl: n_games * k exceeds the net batch (" +
+                                          std::to_string(net_board_capacity(e)) + " boards) or k > 64");
+  AP_TRY(drop_pure_trees(e));
+  AP_TRY(ensure_pool(e, (long long)n_playout * e->geo.S));
+  AP_TRY(vl_prepare(e, k));
+  const int G = e->geo.G;
+  std::vector<int32_t> rem(G, n_playout);
+  AP_TRY(h2d(e, e->vl_remain, rem.data(), sizeof(int32_t) * G));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  // a fresh root takes one lock-step for its first playout, then ceil((n - 1) / k); a reused tree ceil(n / k) <= that
+  const int steps = 1 + (n_playout - 1 + k - 1) / k;
+  auto enqueue = [&]() -> int {
+    AP_CUDA(e, cudaMemsetAsync(e->leaves_vl.n_eval, 0, 4, e->stream));
+    for (int it = 0; it < steps; ++it) {
+      launch_select_vl(e, e->leaves_vl, e->vn, k, e->vl_kstride, e->vl_remain, e->vl_issued);
+      AP_LAUNCH_CHECK(e);
+      AP_TRY(net_run_compacted(e, G * k, e->leaves_vl.n_eval));
+      launch_expand_backup_vl(e, e->leaves_vl, e->vn, e->vl_kstride, e->vl_issued);
+      AP_LAUNCH_CHECK(e);
+    }
+    return AP_OK;
+  };
+  static const int graph_max_games = getenv("AP_GRAPH_MAX_GAMES") ? atoi(getenv("AP_GRAPH_MAX_GAMES")) : 256;
+  const bool use_graph = !e->profile && G <= graph_max_games && steps >= 4;
+  const uint64_t gen = e->net_generation + (e->pool_generation << 32);
+  if (use_graph && (!e->vl_graph || e->vl_graph_playouts != n_playout || e->vl_graph_k != k || e->vl_graph_gen != gen)) {
+    if (e->vl_graph) cudaGraphExecDestroy(e->vl_graph);
+    e->vl_graph = nullptr;
+    const uint64_t l0 = e->launches;
+    cudaGraph_t g = nullptr;
+    AP_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    if (rc != AP_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    AP_CUDA(e, ce);
+    const cudaError_t ci = cudaGraphInstantiate(&e->vl_graph, g, 0);
+    cudaGraphDestroy(g);
+    AP_CUDA(e, ci);
+    e->vl_graph_launches = e->launches - l0;
+    e->launches = l0;
+    e->vl_graph_playouts = n_playout;
+    e->vl_graph_k = k;
+    e->vl_graph_gen = gen;
+  }
+  AP_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  if (use_graph) {
+    AP_CUDA(e, cudaGraphLaunch(e->vl_graph, e->stream));
+    e->launches += e->vl_graph_launches;
+  } else {
+    AP_TRY(enqueue());
+  }
+  AP_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  AP_CUDA(e, cudaStreamSynchronize(e->stream));
+  cudaEventElapsedTime(&e->last_total_ms, e->ev0, e->ev1);
   AP_TRY(net_check_err(e));
   return check_errflags(e);
 }

@@ -22,6 +22,8 @@ void launch_expand_backup(ap_engine* e, const int32_t* d_counts, const int16_t* 
                           const double* d_val64, const float* d_pri32, const float* d_val32,
                           const int32_t* d_slot = nullptr, bool fuse_fc_finish = false);
 void launch_compact_leaves(ap_engine* e);
+void launch_select_vl(ap_engine* e, const Leaves& lv, int32_t* vn, int k, int kstride, int32_t* remain, int32_t* issued);
+void launch_expand_backup_vl(ap_engine* e, const Leaves& lv, int32_t* vn, int kstride, const int32_t* issued);
 void launch_selfplay_pick(ap_engine* e, double temp, double eps, double alpha, uint64_t seed, uint32_t ply, int32_t* d_move,
                           float* d_pi, double* d_noise);
 void launch_advance(ap_engine* e, int n, const int32_t* d_moves);

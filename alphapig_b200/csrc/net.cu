@@ -847,6 +847,15 @@ static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values, const
   return fc_tc_launch(e, n, nb, d_probs, d_values, nb_dev, skip_finish);
 }
 
+int net_board_capacity(ap_engine* e) { return e->net ? e->net->bcap : 0; }
+// the tensor-core path on a compacted batch whose feature planes are already written (at most nb_max boards, the
+// count read on the device); the split-K FC partial logits are left for the consumer (net_fc_finish_args)
+int net_run_compacted(ap_engine* e, int nb_max, const int32_t* nb_dev) {
+  NetState* n = e->net;
+  if (!n || n->head_mode != 2 || n->fc_ksplit <= 1) return ap_fail(e, AP_ERR_BAD_ARG, "needs the fused-head split-K path");
+  return run_fast(e, nb_max, nullptr, nullptr, nb_dev, true);
+}
+
 // fp32 path on dense NCHW states (device) for nb <= bcap_ref boards
 static int run_ref(ap_engine* e, const float* d_states, int nb, float* d_probs, float* d_values) {
   NetState* n = e->net;

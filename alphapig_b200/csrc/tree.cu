@@ -149,6 +149,197 @@ k_expand_backup(Geo geo, Pools pl, Leaves lv, const int32_t* __restrict__ counts
 }
 
 // ---------------------------------------------------------------------------------------------
+// Opt-in multi-leaf mode (ap_search_run_vl): up to k playouts of a game in flight per lock-step, kept apart by
+// VIRTUAL LOSS.  The reference runs its playouts strictly one after the other (mcts_alphaZero.py:147-149), so a single
+// interactive game (human_play_mxnet.py, evaluate/ChessClient.py) is latency bound on a GPU: 400 lock-steps of ~9
+// dependent kernels.  Here a game's warp selects up to k leaves back to back; every node on a selected path carries a
+// virtual visit (vn) until its backup, and a child with vn > 0 in-flight visits is scored as if each of them had
+// already returned a loss:  N' = N + vn,  Q' = (N Q - vn) / N',  u = c P sqrt(Np + vn_parent) / (1 + N').
+// vn == 0 leaves the reference's arithmetic untouched, so k = 1 builds the parity-mode tree bit for bit.  All k
+// leaves are evaluated as ONE net batch, then expanded / backed up in selection order.  Visit counts differ from the
+// sequential search for k > 1 (that is what virtual loss does); every playout still passes through exactly one root
+// child, so the root's children still sum to n_playout - 1 for a fresh tree.
+// A game whose root is still a leaf issues ONE playout in that lock-step (k traversals would all stop at the root).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tree_select_child_vl(const Pools& pl, const int32_t* __restrict__ vn, size_t base, int cs,
+                                                    int cc, int np_eff, double c_puct, int lane) {
+  constexpr int PER = AP_MAX_S / 32;
+  double p[PER], q[PER];
+  int n[PER], v[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lane + 32 * j;
+    const size_t c = base + cs + i;
+    p[j] = 0.0, q[j] = 0.0, n[j] = 0, v[j] = 0;
+    if (i < cc) {
+      p[j] = pl.P[c];
+      q[j] = pl.Q[c];
+      n[j] = pl.N[c];
+      v[j] = vn[c];
+    }
+  }
+  const double sq = __dsqrt_rn((double)np_eff);
+  double bv = -CUDART_INF;
+  int bi = INT_MAX;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lane + 32 * j;
+    if (i < cc) {
+      double qq = q[j];
+      int nn = n[j];
+      if (v[j] > 0) {  // in-flight visits count as losses
+        nn = n[j] + v[j];
+        qq = __ddiv_rn(__dsub_rn(__dmul_rn((double)n[j], q[j]), (double)v[j]), (double)nn);
+      }
+      const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, p[j]), sq), (double)(1 + nn));
+      const double val = __dadd_rn(qq, u);
+      if (val > bv || bi == INT_MAX) {
+        bv = val;
+        bi = i;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    double ov = __shfl_xor_sync(AP_FULL, bv, d);
+    int oi = __shfl_xor_sync(AP_FULL, bi, d);
+    bool take = (oi != INT_MAX) && (bi == INT_MAX || (oi < bi ? !(bv > ov) : (ov > bv)));
+    if (take) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  return bi;
+}
+
+// one warp per game; leaf record j = g * kstride + i.  remain[g] = playouts this game still owes in this search.
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+k_select_vl(Geo geo, const uint32_t* __restrict__ rows, const BoardMeta* __restrict__ meta, Pools pl, int32_t* vn,
+            Leaves lv, int k, int kstride, int32_t* remain, int32_t* issued, unsigned long long* stats, __half* feat,
+            long long mpad) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+  if (g >= geo.G) return;
+  const size_t base = (size_t)g * geo.cap;
+  int want = min(k, remain[g]);
+  if (!lv.active[g]) want = 0;
+  if (want > 1 && pl.child_start[base] < 0) want = 1;  // fresh root: k traversals would all end at the root
+  const WBoard root = wb_load(rows, meta, g, lane);
+  for (int i = 0; i < want; ++i) {
+    const int j = g * kstride + i;
+    WBoard b = root;
+    int node = 0, depth = 0;
+    unsigned long long scanned = 0;
+    while (true) {
+      const int cs = pl.child_start[base + node];
+      const int cc = pl.child_count[base + node];
+      const int np = pl.N[base + node];
+      const int mv = pl.move[base + node];
+      const int vp = vn[base + node];  // in-flight visits through this node BEFORE this traversal
+      if (depth > 0) {
+        if (lane == 0) lv.path[(size_t)j * geo.S + depth - 1] = (int16_t)mv;
+        wb_do_move(b, mv, geo.W, lane);
+      }
+      __syncwarp();
+      if (lane == 0) vn[base + node] = vp + 1;
+      __syncwarp();
+      if (cs < 0) break;
+      node = cs + tree_select_child_vl(pl, vn, base, cs, cc, np + vp, geo.c_puct, lane);
+      ++depth;
+      scanned += cc;
+    }
+    int winner;
+    const bool end = wb_game_end(b, geo.n_in_row, geo.S, winner);
+    wb_store(b, lv.rows, lv.meta, j, lane, 0);
+    int sl = -1;
+    if (lane == 0) {
+      lv.node[j] = node;
+      lv.terminal[j] = end ? 1 : 0;
+      lv.winner[j] = (int8_t)winner;
+      lv.depth[j] = depth;
+      atomicAdd(&stats[0], 1ull);
+      atomicAdd(&stats[1], scanned);
+      atomicAdd(&stats[3], (unsigned long long)(depth + 1));
+      if (end) atomicAdd(&stats[4], 1ull);
+      if (!end) {
+        sl = atomicAdd(lv.n_eval, 1);
+        lv.game_of_slot[sl] = j;
+      }
+      lv.slot[j] = sl;
+    }
+    sl = __shfl_sync(AP_FULL, sl, 0);
+    if (sl >= 0) emit_features_warp(b, geo.W, geo.H, sl, feat, mpad, lane);
+    __syncwarp();
+  }
+  if (lane == 0) {
+    issued[g] = want;
+    remain[g] -= want;
+  }
+}
+
+// the issued[g] leaves of game g in selection order: expand (unless terminal or already expanded by an earlier leaf of
+// this lock-step), back the value up, take the virtual visits off the path
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+k_expand_backup_vl(Geo geo, Pools pl, int32_t* vn, Leaves lv, int kstride, const int32_t* __restrict__ issued,
+                   int32_t* errflag, unsigned long long* stats, FcFinish fin) {
+  __shared__ int16_t s_list[SEL_WARPS][AP_MAX_S];
+  __shared__ float s_prob[SEL_WARPS][AP_MAX_S];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int g = blockIdx.x * SEL_WARPS + w;
+  if (g >= geo.G) return;
+  const size_t base = (size_t)g * geo.cap;
+  const int n = issued[g];
+  for (int i = 0; i < n; ++i) {
+    const int j = g * kstride + i;
+    const int leaf = lv.node[j];
+    double v;
+    if (!lv.terminal[j]) {
+      const int src = lv.slot[j];
+      float pr[8];
+      const float fv = fc_finish_warp(fin, src, geo.S, lane, pr);
+      v = (double)fv;
+      if (pl.child_start[base + leaf] < 0) {  // not yet expanded by a duplicate leaf of this lock-step
+        WBoard b = wb_load(lv.rows, lv.meta, j, lane);
+        const int A = wb_legal_list(b, geo.W, geo.H, lane, s_list[w]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_prob[w][lane + 32 * q] = pr[q];
+        __syncwarp();
+        const bool ok = tree_expand(pl, base, g, geo.cap, leaf, A, s_list[w],
+                                    [&](int kk, int mv) { return (double)s_prob[w][mv]; }, lane);
+        if (!ok && lane == 0) errflag[g] = AP_ERR_POOL_EXHAUSTED;
+        if (ok && lane == 0) atomicAdd(&stats[2], (unsigned long long)A);
+      }
+    } else {
+      const int winner = lv.winner[j];
+      const int cur = lv.meta[j].cur;
+      v = (winner == -1) ? 0.0 : ((winner == cur) ? 1.0 : -1.0);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      tree_backup(pl, base, leaf, -v);
+      for (int nd = leaf; nd >= 0; nd = pl.parent[base + nd]) vn[base + nd] -= 1;
+    }
+    __syncwarp();
+  }
+  if (g == 0 && lane == 0) *lv.n_eval = 0;
+}
+
+void launch_select_vl(ap_engine* e, const Leaves& lv, int32_t* vn, int k, int kstride, int32_t* remain, int32_t* issued) {
+  __half* feat = nullptr;
+  long long mpad = 0;
+  net_feature_planes(e, &feat, &mpad);
+  k_select_vl<<<(e->geo.G + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, e->stream>>>(
+      e->geo, e->rows, e->meta, e->pools, vn, lv, k, kstride, remain, issued, e->stats, feat, mpad);
+}
+void launch_expand_backup_vl(ap_engine* e, const Leaves& lv, int32_t* vn, int kstride, const int32_t* issued) {
+  FcFinish fin{nullptr, nullptr, 0, 0, 0};
+  net_fc_finish_args(e, &fin.partial, &fin.bias, &fin.rows, &fin.np, &fin.ksplit);
+  k_expand_backup_vl<<<(e->geo.G + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, e->stream>>>(
+      e->geo, e->pools, vn, lv, kstride, issued, e->errflag, e->stats, fin);
+}
+
+// ---------------------------------------------------------------------------------------------
 // MCTS.update_with_move (mcts_alphaZero.py:159-167): re-root on a child keeping its subtree,
 // compacted breadth-first (children blocks stay contiguous and ordered) through a per-CTA
 // scratch slot, or a fresh TreeNode(None, 1.0).

@@ -186,6 +186,11 @@ class Engine(object):
     def search_run(self, n_playout):
         self._check(self.lib.ap_search_run(self.h, int(n_playout)))
 
+    def search_run_vl(self, n_playout, k):
+        """Opt-in multi-leaf search: up to k playouts per game in flight per lock-step (virtual loss); k = 1 is
+        ``search_run``'s tree bit for bit."""
+        self._check(self.lib.ap_search_run_vl(self.h, int(n_playout), int(k)))
+
     def search_timing(self):
         a, b = C.c_float(), C.c_float()
         self._check(self.lib.ap_search_timing(self.h, C.byref(a), C.byref(b)))

@@ -692,6 +692,17 @@ def single_game_leg(ctx, n_moves=6):
         ts = np.array(ts[2:])
         out["%dx%d" % (Wb, Wb)] = {"ms_per_move": 1e3 * float(ts.mean()), "min_ms": 1e3 * float(ts.min()),
                                   "playouts_per_s": N_PLAYOUT / float(ts.mean())}
+        # opt-in multi-leaf mode (virtual loss, 8 playouts in flight per lock-step): NOT the reference's sequential search
+        player = MCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=N_PLAYOUT, is_selfplay=1, leaves_per_step=8)
+        b.init_board(0)
+        ts = []
+        for _ in range(n_moves + 2):
+            t0 = time.perf_counter()
+            mv = player.get_action(b, temp=1.0)
+            ts.append(time.perf_counter() - t0)
+            b.do_move(mv)
+        ts = np.array(ts[2:])
+        out["%dx%d" % (Wb, Wb)]["virtual_loss_k8_ms_per_move"] = 1e3 * float(ts.mean())
         del player
         net.close()
     return out

@@ -108,6 +108,14 @@ int ap_search_expand_backup_dense(ap_engine* e, const float* priors /* [G][S] */
 /* MCTS.get_move_probs (:141-157) with the device net as policy_value_fn:
  * n_playout x (select -> features -> net -> expand/backup), no host round trip. */
 int ap_search_run(ap_engine* e, int32_t n_playout);
+/* OPT-IN multi-leaf search for small batches (interactive play: human_play_mxnet.py, evaluate/ChessClient.py run ONE
+ * game, which is launch-latency bound in the strictly sequential form above): up to k playouts of every game are in
+ * flight per lock-step, kept apart by virtual loss (every in-flight visit of a child counts as a loss until its
+ * backup), and evaluated as one net batch.  n_games * k must fit the net batch (256 boards for small engines).
+ * k = 1 builds the same tree as ap_search_run bit for bit; k > 1 changes visit counts (NOT the reference's search:
+ * mcts_alphaZero.py:147-149 runs the playouts one after the other) while every game still gets exactly n_playout
+ * playouts. */
+int ap_search_run_vl(ap_engine* e, int32_t n_playout, int32_t k);
 /* Root children in insertion order: acts, visit counts, Q; root's own N.   (:152-154) */
 int ap_search_root(ap_engine* e, const int32_t* game_ids, int32_t n, int32_t* out_count, int16_t* out_acts /* [n][S] */,
                    int32_t* out_visits /* [n][S] */, double* out_q /* [n][S] or NULL */, int32_t* out_root_n /* [n] or NULL */);

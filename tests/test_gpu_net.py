@@ -333,3 +333,75 @@ def test_single_game_15x15_graph_path_vs_oracle():
     assert launches[0] == launches[1] == launches[2] and launches[0] >= 9 * n_playout
     a.close()
     b.close()
+
+
+def test_virtual_loss_mode_k1_is_parity_mode_and_k8_keeps_the_playout_budget():
+    """ap_search_run_vl (opt-in multi-leaf search, virtual loss): k = 1 must build ap_search_run's tree bit for bit
+    (two plies, tree reuse); k = 8 gives every game exactly n_playout playouts (root N), root children summing to
+    n_playout - 1 on a fresh tree, legal ascending children - in ~1/6 of the lock-steps."""
+    W = 15
+    G, n_playout = 3, 200
+    arg, aux = onet.init_params("simple", W, W, seed=5)
+    roots = [oboard_from(W, W, 5, synth_position(W, W, 5, 600 + g)) for g in range(G)]
+    cm = [export_oboard(b) for b in roots]
+    engs = [_engine(width=W, height=W, n_in_row=5, n_games=G, n_playout=n_playout) for _ in range(3)]
+    for e in engs:
+        e.net_load("simple", _merged(arg, aux))
+        e.boards_import(np.stack([c for c, _ in cm]), np.stack([m for _, m in cm]))
+    a, b, c = engs
+    for ply in range(2):
+        a.search_run(n_playout)
+        b.search_run_vl(n_playout, 1)
+        ra, rb = a.search_root(want_q=True), b.search_root(want_q=True)
+        assert all(np.array_equal(x, y) for x, y in zip(ra, rb)), "k = 1, ply %d" % ply
+        count, acts, visits = ra[0], ra[1], ra[2]
+        mv = np.array([acts[g, int(np.argmax(visits[g, :count[g]]))] for g in range(G)], np.int32)
+        for e in (a, b):
+            e.search_advance(mv)
+            e.boards_do_move(mv)
+    # k = 8 on fresh trees
+    c.search_stats()
+    l0 = c.launch_count()
+    c.search_run_vl(n_playout, 8)
+    launches = c.launch_count() - l0
+    st = c.search_stats()
+    count, acts, visits, q, rootn = c.search_root(want_q=True)
+    legal = c.boards_legal()
+    assert st["playouts"] == G * n_playout and (rootn == n_playout).all()
+    for g in range(G):
+        n = int(count[g])
+        assert n == int(legal[g].sum()) and list(acts[g, :n]) == list(np.nonzero(legal[g])[0])
+        assert int(visits[g, :n].sum()) == n_playout - 1
+        assert (np.abs(q[g, :n]) <= 1.0).all()
+    assert launches <= 9 * (1 + (n_playout - 1 + 7) // 8) + 4  # 26 lock-steps instead of 200
+    # reuse + a second multi-leaf search: root N accumulates as in the sequential search
+    mv = np.array([acts[g, int(np.argmax(visits[g, :count[g]]))] for g in range(G)], np.int32)
+    kept = np.array([visits[g, int(np.argmax(visits[g, :count[g]]))] for g in range(G)])
+    c.search_advance(mv)
+    c.boards_do_move(mv)
+    c.search_run_vl(n_playout, 8)
+    _, _, _, _, rootn2 = c.search_root()
+    assert (rootn2 == kept + n_playout).all()
+    for e in engs:
+        e.close()
+
+
+def test_virtual_loss_shim_and_limits():
+    from alphapig_b200._lib import EngineError
+    from alphapig_b200.game import Board
+    from alphapig_b200.mcts_alphaZero import MCTSPlayer
+    from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
+    W = 8
+    net = PolicyValueNet(W, W, batch_size=16, seed=0)
+    player = MCTSPlayer(net.policy_value_fn, c_puct=5, n_playout=100, is_selfplay=1, leaves_per_step=8)
+    b = Board(width=W, height=W, n_in_row=5)
+    b.init_board()
+    np.random.seed(1)
+    for _ in range(4):
+        mv, pi = player.get_action(b, temp=1.0, return_prob=1)
+        assert mv in b.availables and abs(pi.sum() - 1.0) < 1e-9 and (pi[list(b.states)] == 0).all()
+        b.do_move(mv)
+    eng = net.search_engine(n_games=200, n_playout=10, tag="vl-limit")
+    with pytest.raises(EngineError):
+        eng.search_run_vl(10, 4)  # 200 games x 4 leaves do not fit the 256-board batch of a small engine
+    net.close()
