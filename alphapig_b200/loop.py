@@ -84,9 +84,12 @@ class _Trainer(object):
 
 def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, c_puct=5, temp=1.0, batch_size=128,
                         epochs=8, learn_rate=4e-4, buffer_size=2198800, n_in_row=5, seed=0, log=None, device_pick=True,
-                        overlap=True, kl_targ=0.02, warmup_iters=0):
+                        overlap=True, kl_targ=0.02, warmup_iters=0, start_positions=None, prefill=None):
     """Returns a dict of counters / timings (per rank; wall clock).  ``warmup_iters`` iterations run first and are left
-    out of every counter (the timed region then starts at a ply boundary with the pipeline full)."""
+    out of every counter (the timed region then starts at a ply boundary with the pipeline full).
+    start_positions: (cells, meta) every slot's first game starts from (default: empty boards).
+    prefill: callable(ring) run once on the trainer rank before the first iteration - the reference fills its buffer
+    from SGF records for the first 4000 batches before any self-play game is trained on (train_mxnet.py:270-273)."""
     import torch
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -99,7 +102,11 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
     dev = torch.device("cuda", net._device)
     sp = BatchedSelfPlay(net, n_games, n_playout=n_playout, c_puct=c_puct, temp=temp, n_in_row=n_in_row,
                          seed=seed + 1000 * rank, device_pick=True, device_records=True)
+    if start_positions is not None:
+        sp.load_positions(*start_positions)
     trainer = _Trainer(net, buffer_size, batch_size, epochs, learn_rate, kl_targ) if rank == 0 else None
+    if trainer is not None and prefill is not None:
+        prefill(trainer.ring)
     pool = ThreadPoolExecutor(1) if rank == 0 else None
     if multi:
         apdist.broadcast_weights(net, src=0)  # identical start

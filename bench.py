@@ -638,10 +638,23 @@ def loop_leg(ctx, args, iters, warmup_iters, G, plies=2):
     from alphapig_b200.policy_value_net_mxnet_simple import PolicyValueNet
     arg, aux = init_params(ARCH, W, H, seed=0, synthetic_stats=True)
     net = PolicyValueNet(W, H, batch_size=128, model_params=(arg, aux), device=ctx.local)
+    # every slot starts from a synthetic mid-game position (games then end within the few timed plies and their records
+    # travel); the trainer's ring starts with an SGF-style bootstrap (train_mxnet.py:270-273: the reference trains on
+    # replayed human games before self-play), so policy_update runs in every timed iteration
+    probe = net.search_engine(n_in_row=N_IN_ROW, c_puct=C_PUCT, n_playout=1, n_games=G, node_capacity=8, tag="positions")
+    cells, meta = synthetic_positions(probe, G, seed0=1234 + ctx.rank * G)
+    net.release_engine(probe)
+
+    def prefill(ring):
+        rs = np.random.RandomState(99)
+        seqs = [[int(m) for m in rs.permutation(W * H)[:40 + (g % 30)]] for g in range(64)]
+        ring.eng.replay_push_sgf(seqs, [1 + (g % 2) for g in range(64)])
+
     clocks = ClockSampler(ctx.local)
     clocks.start()
     res = selfplay_train_loop(net, G, iters, plies_per_iter=plies, n_playout=N_PLAYOUT, c_puct=C_PUCT, temp=1.0,
-                              batch_size=128, epochs=8, seed=7, warmup_iters=warmup_iters, overlap=not args.no_overlap)
+                              batch_size=128, epochs=8, seed=7, warmup_iters=warmup_iters, overlap=not args.no_overlap,
+                              start_positions=(cells, meta), prefill=prefill)
     clk = clocks.stop()
     t_max, coll_max, wait_max = ctx.reduce([res["t_total"], res.get("t_collectives", 0.0), res.get("t_wait_trainer", 0.0)])
     playouts, plies_all, games, recs = ctx.reduce([res["playouts"], res["plies"], res["games"], res["records"]], op="sum")
@@ -692,8 +705,9 @@ def single_game_leg(ctx, n_moves=6):
         ts = np.array(ts[2:])
         out["%dx%d" % (Wb, Wb)] = {"ms_per_move": 1e3 * float(ts.mean()), "min_ms": 1e3 * float(ts.min()),
                                   "playouts_per_s": N_PLAYOUT / float(ts.mean())}
-        # opt-in multi-leaf mode (virtual loss, 8 playouts in flight per lock-step): NOT the reference's sequential search
-        player = MCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=N_PLAYOUT, is_selfplay=1, leaves_per_step=8)
+        # opt-in multi-leaf mode (virtual loss, K playouts in flight per lock-step): NOT the reference's sequential search
+        K = 16
+        player = MCTSPlayer(net.policy_value_fn, c_puct=C_PUCT, n_playout=N_PLAYOUT, is_selfplay=1, leaves_per_step=K)
         b.init_board(0)
         ts = []
         for _ in range(n_moves + 2):
@@ -702,7 +716,7 @@ def single_game_leg(ctx, n_moves=6):
             ts.append(time.perf_counter() - t0)
             b.do_move(mv)
         ts = np.array(ts[2:])
-        out["%dx%d" % (Wb, Wb)]["virtual_loss_k8_ms_per_move"] = 1e3 * float(ts.mean())
+        out["%dx%d" % (Wb, Wb)]["virtual_loss_k%d_ms_per_move" % K] = 1e3 * float(ts.mean())
         del player
         net.close()
     return out
