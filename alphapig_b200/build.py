@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libalphapig_b200.so")
-SOURCES = ["engine.cu", "boards.cu", "tree.cu", "rollout.cu", "net.cu", "conv_tc.cu", "heads_tc.cu", "replay.cu", "traj.cu"]
+SOURCES = ["engine.cu", "boards.cu", "tree.cu", "rollout.cu", "net.cu", "conv_tc.cu", "front_tc.cu", "heads_tc.cu", "replay.cu", "traj.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
               "-fmad=true"]

@@ -558,6 +558,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if (const char* m = getenv("AP_CONV4")) n->conv4 = m[0] - '0';
   if (const char* m = getenv("AP_CONV4_128")) n->conv4_128 = m[0] - '0';
   if (const char* m = getenv("AP_HEAD_PAIR")) n->head_pair = m[0] != '0';
+  if (const char* m = getenv("AP_FRONT_FUSED")) n->front_fused = m[0] != '0';
   if (const char* m = getenv("AP_HEAD_MODE")) n->head_mode = (m[0] == '0') ? 0 : (m[0] == '1') ? 1 : 2;
   long long total = 0;
   for (int i = 0; i < n_tensors; ++i) {
@@ -747,6 +748,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
     return bad(rc);
   if ((rc = nalloc(e, n, (void**)&n->d_err, 4)) != AP_OK) return bad(rc);
   if ((rc = conv_tc_configure(e)) != AP_OK) return bad(rc);
+  if ((rc = front_tc_configure(e)) != AP_OK) return bad(rc);
   if (cudaFuncSetAttribute(k_head_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
     return bad(ap_fail(e, AP_ERR_CUDA, "cudaFuncSetAttribute(k_head_fc)"));
   if ((rc = nalloc(e, n, (void**)&n->hbuf, (size_t)n->bcap * 6 * S * 4)) != AP_OK) return bad(rc);
@@ -826,7 +828,15 @@ static int run_fast(ap_engine* e, int nb, float* d_probs, float* d_values, const
   NetState* n = e->net;
   const size_t last = n->trunk.size() - 1;
   if (nb_dev && n->head_mode != 2) return ap_fail(e, AP_ERR_BAD_ARG, "compacted batches need the fused head path");
-  for (size_t i = 0; i < n->trunk.size(); ++i) {
+  size_t first = 0;
+  if (n->front_fused && front_tc_supported(n)) {
+    // conv1 + conv2 in one kernel: conv1's output goes TMEM -> shared memory -> conv2's MMAs, never to HBM
+    AP_TRY(front_tc_launch(e, n, nb, nb_dev));
+    prof_mark(e);  // phase "conv1" (empty: the fused kernel is accounted to conv2)
+    prof_mark(e);
+    first = 2;
+  }
+  for (size_t i = first; i < n->trunk.size(); ++i) {
     // head_mode 2: the last trunk layer also computes the two 1x1 head convs and never stores its own output
     AP_TRY(conv_tc_launch(e, n, n->trunk[i], nb, nb_dev, n->head_mode == 2 && i == last));
     prof_mark(e);

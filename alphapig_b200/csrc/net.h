@@ -101,6 +101,8 @@ struct NetState {
                       // fused-head layer (AP_CONV4 for A/B timing)
   int conv4_128 = 0;  // 128-channel layers on that kernel too: 1 = cin 64 (conv3), 2 = all (AP_CONV4_128, A/B timing)
   NetHeadW head_w;
+  int front_fused = 1;  // conv1 + conv2 of the 6-conv net as one kernel (front_tc.cu); AP_FRONT_FUSED=0 runs the two layers
+                        // separately (A/B timing and the bit-equality test)
   int head_pair = 1;  // run the fused-head layer on the CTA-pair kernel (measured faster: its double-buffered TMEM hides
                       // the longer epilogue); AP_HEAD_PAIR=0 selects the single-CTA kernel for A/B timing
   int* d_err = nullptr;
@@ -116,6 +118,10 @@ int conv_tc_kc(const ConvLayer& L, int split);
 bool conv_tc_supported(int cin_pad, int cout);
 int conv_tc_smem_bytes(const ConvLayer& L, int* out_nb);
 int conv_tc_configure(ap_engine* e);
+// front_tc.cu
+bool front_tc_supported(const NetState* n);
+int front_tc_configure(ap_engine* e);
+int front_tc_launch(ap_engine* e, NetState* n, int n_boards, const int* n_boards_dev);
 // heads_tc.cu
 void fc_tc_dims(int S, int* kp, int* np);
 int fc_tc_configure(ap_engine* e, NetState* n);

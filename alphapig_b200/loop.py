@@ -19,9 +19,11 @@ is in flight):
 
     boundary   : drain the outbox (device copy); if a broadcast completed since the last boundary, swap the new
                  weights into the search engine (operand-image rebuild, < 1 ms)
-    main thread: all-gather records(i)  ->  join trainer(i-1)  ->  broadcast weights(i-1)  ->  start trainer(i)
+    main thread: gather records(i) to the trainer rank  ->  if the previous policy_update has finished (rank 0 says so
+                 in a 4-byte broadcast): broadcast its weights and start the next policy_update on everything gathered
+                 since; otherwise the records queue up and nobody waits
 
-so the weights a ply searches with are at most two iterations old; the reference (train_mxnet.py:265-283: collect one
+so the weights a ply searches with are a few iterations old at most (the trainer shares rank 0's GPU with its search); the reference (train_mxnet.py:265-283: collect one
 game -> policy_update -> repeat, everything sequential) has no staleness and no overlap.  ``overlap=False`` is the
 synchronous form of the same loop (every engine drained while rank 0 trains), kept for A/B.
 
@@ -130,9 +132,11 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
             state["take"] = False
     sp.boundary_hook = boundary
 
-    out = dict(plies=0, playouts=0, games=0, records=0, bytes_gathered=0, bytes_broadcast=0, t_total=0.0,
-               t_collectives=0.0, t_wait_trainer=0.0, iters=0)
+    out = dict(plies=0, playouts=0, games=0, records=0, bytes_gathered=0, bytes_broadcast=0, broadcasts=0, t_total=0.0,
+               t_collectives=0.0, iters=0)
     fut = None
+    pending = []
+    ready = torch.zeros(1, dtype=torch.int32, device=dev)
     # The timed region starts and ends right behind the launch of a ply's search (no device synchronisation: that would
     # let the search in flight finish off the clock), so it covers n_iters * plies_per_iter whole periods per rank.
     t_start = time.perf_counter()
@@ -150,34 +154,43 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
         # ---- exchanges, issued while the next ply's search runs in sp's background thread --------------------------
         t0 = time.perf_counter()
         gathered = apdist.gather_records_device(recs, dst=0) if multi else [recs]
-        t1 = time.perf_counter()
-        if rank == 0 and fut is not None:
-            fut.result()  # policy_update of the previous iteration (normally long finished)
-            fut = None
-        t2 = time.perf_counter()
-        if multi:
-            dist.broadcast(flat, src=0)
-        staged.copy_(flat)  # the trainer is idle here: a consistent snapshot, swapped in at the next boundary
-        torch.cuda.current_stream(dev).synchronize()  # (not the device: the next ply's search is in flight)
-        state["new_weights"] = True
-        t3 = time.perf_counter()
         if rank == 0:
-            fut = pool.submit(trainer.job, gathered)
+            pending.extend(g for g in gathered if g.shape[0])
+        # The trainer shares its GPU with rank 0's search and is slowed down by it; nobody waits for it.  Rank 0 tells
+        # the others whether a finished policy_update is there to be broadcast; if not, the records just queue up.
+        ready[0] = 1 if (rank != 0 or fut is None or fut.done()) else 0
+        if multi:
+            dist.broadcast(ready, src=0)
+        t1 = time.perf_counter()
+        if int(ready.item()):
+            if rank == 0 and fut is not None:
+                fut.result()
+                fut = None
+            if multi:
+                dist.broadcast(flat, src=0)
+            staged.copy_(flat)  # the trainer is idle here: a consistent snapshot, swapped in at the next boundary
+            torch.cuda.current_stream(dev).synchronize()  # (not the device: the next ply's search is in flight)
+            state["new_weights"] = True
+            if timed:
+                out["broadcasts"] += 1
+                out["bytes_broadcast"] += flat.numel() * 4 if multi else 0
+            if rank == 0:
+                fut = pool.submit(trainer.job, pending)
+                pending = []
+        t3 = time.perf_counter()
         if timed:
             out["iters"] += 1
             out["plies"] += plies_per_iter * n_games
             out["playouts"] += plies_per_iter * n_games * n_playout
             out["records"] += int(recs.shape[0])
             out["bytes_gathered"] += sum(int(g.shape[0]) for g in gathered) * int(recs.shape[1])
-            out["bytes_broadcast"] += flat.numel() * 4 if multi else 0
-            out["t_collectives"] += (t1 - t0) + (t3 - t2)
-            out["t_wait_trainer"] += t2 - t1
+            out["t_collectives"] += t3 - t0
         if it == warmup_iters - 1:
             t_start = time.perf_counter()
         t_end = time.perf_counter()
         if log and rank == 0:
-            log("iter %d: %d games finished so far, ring %d, collectives %.1f ms, waited %.1f ms for the trainer"
-                % (it, out["games"], trainer.records, 1e3 * ((t1 - t0) + (t3 - t2)), 1e3 * (t2 - t1)))
+            log("iter %d: %d games finished so far, ring %d, exchanges %.1f ms on the main thread"
+                % (it, out["games"], trainer.records, 1e3 * (t3 - t0)))
     out["t_total"] = t_end - t_start
     sp.drain()
     torch.cuda.synchronize(dev)
@@ -185,6 +198,8 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
         dist.barrier()
     if fut is not None:
         fut.result()
+    if rank == 0 and pending:
+        trainer.job(pending)  # records gathered after the last policy_update started (off the clock)
     if trainer is not None:
         out.update(train_steps=trainer.steps, ring_records=trainer.records, losses=trainer.losses, kls=trainer.kls,
                    lr_multiplier=trainer.lr_multiplier, early_stops=trainer.early_stops, t_trainer=trainer.seconds)

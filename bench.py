@@ -656,7 +656,7 @@ def loop_leg(ctx, args, iters, warmup_iters, G, plies=2):
                               batch_size=128, epochs=8, seed=7, warmup_iters=warmup_iters, overlap=not args.no_overlap,
                               start_positions=(cells, meta), prefill=prefill)
     clk = clocks.stop()
-    t_max, coll_max, wait_max = ctx.reduce([res["t_total"], res.get("t_collectives", 0.0), res.get("t_wait_trainer", 0.0)])
+    t_max, coll_max = ctx.reduce([res["t_total"], res.get("t_collectives", 0.0)])
     playouts, plies_all, games, recs = ctx.reduce([res["playouts"], res["plies"], res["games"], res["records"]], op="sum")
     net.close()
     if ctx.rank != 0:
@@ -669,9 +669,10 @@ def loop_leg(ctx, args, iters, warmup_iters, G, plies=2):
             "last_losses": (res.get("losses") or [])[-3:], "last_kls": (res.get("kls") or [])[-3:],
             "lr_multiplier": res.get("lr_multiplier"), "weight_swaps": res.get("weight_swaps"),
             "collectives": {"in_timed_region": True,
-                            "what": "per iteration: counts all-gather + record gather to the trainer rank (device memory) "
-                                    "and one broadcast of the flat fp32 weights, NCCL" if ctx.world > 1 else "none (1 GPU)",
-                            "seconds_main_thread_max": coll_max, "wait_for_trainer_seconds_max": wait_max,
+                            "what": "per iteration: counts all-gather + record gather to the trainer rank (device memory), a "
+                                    "4-byte ready flag and - when a policy_update has finished - one broadcast of the flat fp32 "
+                                    "weights, NCCL" if ctx.world > 1 else "none (1 GPU)",
+                            "seconds_main_thread_max": coll_max, "weight_broadcasts": res.get("broadcasts"),
                             "bytes_gathered": res.get("bytes_gathered"), "bytes_broadcast": res.get("bytes_broadcast")},
             "overlap": bool(res.get("overlap")), "clocks": clk,
             "timing": "wall clock from the ply boundary after the warm-up iterations to the end of the last iteration's "

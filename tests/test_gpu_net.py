@@ -405,3 +405,26 @@ def test_virtual_loss_shim_and_limits():
     with pytest.raises(EngineError):
         eng.search_run_vl(10, 4)  # 200 games x 4 leaves do not fit the 256-board batch of a small engine
     net.close()
+
+
+@pytest.mark.parametrize("W,nst", [(15, 611), (8, 131), (15, 3)])
+def test_fused_front_kernel_is_bit_identical_to_separate_layers(monkeypatch, W, nst):
+    """front_tc.cu (conv1 + conv2 of the 6-conv net in one kernel, conv1's output handed to conv2 through shared
+    memory) against the two separate conv launches (AP_FRONT_FUSED=0): identical probabilities and values, bit for bit,
+    on batches of several tiles per CTA, one tile per CTA and fewer tiles than CTAs - and both within 1e-3 of the
+    oracle."""
+    arg, aux = onet.init_params("simple", W, W, seed=11)
+    boards, st = _states(W, nst, 9000, 31 if W == 15 else 10)
+    outs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("AP_FRONT_FUSED", fused)
+        eng = _engine(width=W, height=W, n_in_row=5, n_games=4)
+        eng.net_load("simple", _merged(arg, aux))
+        outs.append(eng.net_forward(st))
+        # second pass on the same handle: the kernel's barriers / TMEM are set up from scratch every launch
+        p2, v2 = eng.net_forward(st[::-1].copy())
+        assert np.array_equal(p2[::-1], outs[-1][0]) and np.array_equal(v2[::-1], outs[-1][1])
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    ref_p, ref_v = onet.forward(arg, aux, st, "simple")
+    assert np.abs(np.log(outs[1][0]) - np.log(ref_p)).max() <= TOL and np.abs(outs[1][1] - ref_v).max() <= TOL

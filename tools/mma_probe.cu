@@ -1,7 +1,7 @@
 // Micro-benchmark (development tool, not product): raw tcgen05.mma issue/execute rate on sm_100a for
 // the operand layouts conv_tc.cu uses (K-major, no swizzle, 8x16B core matrices).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/mma_probe tools/mma_probe.cu
-// Prints cycles per MMA for N in {64,128,256}, A start aligned / misaligned by one 16-byte row,
+// Prints cycles per MMA for N in {32,64,128,256}, A start aligned / misaligned by one 16-byte row,
 // descriptors hoisted vs recomputed per instruction, and with a concurrent TMA stream into smem.
 #include <cstdio>
 #include <cuda_fp16.h>
@@ -119,7 +119,7 @@ int main() {
   for (int tma = 0; tma < 2; ++tma)
     for (int rec = 0; rec < 2; ++rec)
       for (int aoff = 0; aoff < 2; ++aoff)
-        for (int n = 64; n <= 256; n *= 2) {
+        for (int n = 32; n <= 256; n *= 2) {
           ProbeParams p{n, aoff, rec, 2048, tma, 0, d_src, d_out, d_err};
           cudaEvent_t e0, e1;
           cudaEventCreate(&e0);
