@@ -204,3 +204,22 @@ def test_resnet_symbol_matches_reference_graph():
         if name.endswith("_weight") and len(shp) == 4:
             k = 1 if name.startswith("conv3_") else 3
             assert shp[2:] == (k, k), name
+
+
+def test_mxnet_pin():
+    """Arithmetic pin of the nets at the MXNet boundary - runs once tests/golden/mxnet_pin.npz exists (written by
+    tools/mxnet_pin.py on a machine with MXNet; MXNet is not installable here, so until then the oracle's net arithmetic
+    stays "parity unpinned" and this test is skipped, not faked)."""
+    import pytest
+    path = os.path.join(GOLDEN, "mxnet_pin.npz")
+    if not os.path.exists(path):
+        pytest.skip("no MXNet-written fixture (python tools/mxnet_pin.py --reference <AlphaPig checkout>)")
+    from alphapig_b200.params import init_params
+    from oracle import net as onet
+    z = np.load(path)
+    st = z["states"]
+    for tag, arch, nb in (("simple", "simple", 0), ("res3", "resnet", 3)):
+        arg, aux = init_params(arch, 15, 15, n_blocks=nb, seed=0, synthetic_stats=True)
+        p, v = onet.forward(arg, aux, st, arch, n_blocks=nb)
+        assert np.abs(np.log(p) - np.log(z[tag + "_probs"])).max() < 2e-5, tag
+        assert np.abs(v - z[tag + "_values"]).max() < 2e-5, tag
