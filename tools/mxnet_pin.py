@@ -41,7 +41,8 @@ def main():
     import policy_value_net_mxnet as ref_res  # noqa: E402  (the reference's files, unmodified)
     import policy_value_net_mxnet_simple as ref_simple  # noqa: E402
     from alphapig_b200.params import init_params  # noqa: E402
-    from tests.helpers import oboard_from, synth_position  # noqa: E402
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oboard_from, synth_position  # noqa: E402
 
     W = 15
     boards = [oboard_from(W, W, 5, synth_position(W, W, 5, 1234 + g)) for g in range(a.boards)]
