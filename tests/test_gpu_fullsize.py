@@ -90,8 +90,9 @@ def test_c2_full_size_search_matches_oracle_on_sampled_games():
     eng.search_advance(-1)
     l0 = eng.launch_count()
     eng.search_run(n_playout)
-    # the fused 9-launch lock-step, launched directly (+ the pool-capacity check)
-    assert 9 * n_playout <= eng.launch_count() - l0 <= 9 * n_playout + 2
+    # the fused lock-step, launched directly: select, conv1+conv2, conv3, conv4, conv5, conv_final+heads, FC,
+    # expand/backup = 8 launches (9 with AP_FRONT_FUSED=0), + the pool-capacity check
+    assert 8 * n_playout <= eng.launch_count() - l0 <= 9 * n_playout + 2
     count, acts, visits, _, _ = eng.search_root()
     moves = np.zeros(G, np.int32)
     for g in range(G):
