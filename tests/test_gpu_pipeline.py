@@ -188,7 +188,8 @@ def test_selfplay_train_loop_single_gpu(overlap):
     assert res["train_steps"] >= 3 and np.isfinite(res["losses"]).all()
     assert res["playouts"] == 4 * 8 * 64 * 16 and res["t_total"] > 0
     if overlap:
-        assert res["weight_swaps"] >= 3 and res["ring_records"] >= res["records"] > 0
+        # nobody waits for the trainer: a swap happens whenever a policy_update had finished at an iteration boundary
+        assert 1 <= res["weight_swaps"] <= 5 and res["ring_records"] >= res["records"] > 0
         assert res["lr_multiplier"] in (1.0, 1.5, 2.25, 3.375, 1 / 1.5, 1 / 2.25, 1 / 3.375, 5.0625, 1 / 5.0625)
     assert not np.array_equal(w0, net.get_policy_param()[0]["conv1_weight"])
     net.close()
