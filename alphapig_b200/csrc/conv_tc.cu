@@ -1450,7 +1450,8 @@ int conv_tc_launch(ap_engine* e, NetState* n, const ConvLayer& L, int n_boards, 
   // auto: CTA pairs where they measured faster on B200 (K = 9*128: conv4, conv5, the residual blocks, the fused-head
   // layer); the memory-bound small layers run the single-CTA kernel
   const bool pair = !L.force_single &&
-                    (n->conv_mode == 2 || (n->conv_mode == 0 && (L.cin_pad == 128 || (head && n->head_pair))));
+                    (n->conv_mode == 2 || (n->conv_mode == 0 && (L.cin_pad == 128 || (head && n->head_pair) ||
+                                                                 (n->pair_cin64 && L.cin_pad == 64 && L.cout == 128))));
   SmemPlan s;
   int grid;
   if (pair) {

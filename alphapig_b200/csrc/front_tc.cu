@@ -47,7 +47,23 @@ struct FrontParams {
   int n_tiles, W, H;
   const int* n_tiles_dev;
   int* errflag;
+#ifdef AP_FRONT_TRACE
+  long long* trace;  // development build: [role][tile][slot] clock64 stamps of CTA 0
+#endif
 };
+
+#ifdef AP_FRONT_TRACE
+// roles: 0 MMA issuer, 1 epilogue warp 4, 2 TMA producer; 64 tiles x 8 slots each
+#define FTRACE(role, t, slot)                                                                   \
+  do {                                                                                          \
+    if (p.trace && blockIdx.x == 0 && (t) < 64 && (threadIdx.x & 31) == 0)                      \
+      p.trace[(((role) * 64) + (t)) * 8 + (slot)] = clock64();                                  \
+  } while (0)
+#else
+#define FTRACE(role, t, slot) \
+  do {                        \
+  } while (0)
+#endif
 
 __device__ __forceinline__ void tmem_ld_wait_regs32(uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -141,8 +157,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
     bool ok = true;
     for (int t = 0; t < my_tiles && ok; ++t) {
       const int s = t & 1, ph = (t >> 1) & 1;
+      FTRACE(2, t, 0);
       ok = __all_sync(AP_FULL, mbar_wait(smem_u32(&f_empty[s]), ph ^ 1, p.errflag));
       if (!ok) break;
+      FTRACE(2, t, 1);
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const long long row0 = NET_PAD_ROWS + (long long)tile * NET_TILE_ROWS - 17;
       if (elect_one()) {
@@ -167,8 +185,11 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
     const uint32_t w2_lo = (smem_u32(smem + OFF_W2) >> 4) | (B_LBO << 16);
     auto conv1 = [&](int t) -> bool {
       const int s = t & 1, ph = (t >> 1) & 1;
+      FTRACE(0, t, 0);
       if (!__all_sync(AP_FULL, mbar_wait(smem_u32(&a1_empty[s]), ph ^ 1, p.errflag))) return false;
+      FTRACE(0, t, 1);
       if (!__all_sync(AP_FULL, mbar_wait(smem_u32(&f_full[s]), ph, p.errflag))) return false;
+      FTRACE(0, t, 2);
       tc_fence_after();
       const uint32_t a_lo = (smem_u32(smem + OFF_SF + s * SLABF_STRIDE) >> 4) | (A_LBO << 16);
       const uint32_t acc = tmem_base + (uint32_t)(s * 128);
@@ -187,12 +208,16 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
         tc_commit(smem_u32(&a1_full[s]));
       }
       __syncwarp();
+      FTRACE(0, t, 3);
       return true;
     };
     auto conv2 = [&](int t) -> bool {
       const int s = t & 1, ph = (t >> 1) & 1;
+      FTRACE(0, t, 4);
       if (!__all_sync(AP_FULL, mbar_wait(smem_u32(&a2_empty[s]), ph ^ 1, p.errflag))) return false;
+      FTRACE(0, t, 5);
       if (!__all_sync(AP_FULL, mbar_wait(smem_u32(&s2_full[s]), ph, p.errflag))) return false;
+      FTRACE(0, t, 6);
       tc_fence_after();
       const uint32_t a_lo = (smem_u32(smem + OFF_S2 + s * SLAB2_BYTES) >> 4) | (A_LBO << 16);
       const uint32_t acc = tmem_base + 256u + (uint32_t)(s * 128);
@@ -214,6 +239,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
         tc_commit(smem_u32(&a2_full[s]));
       }
       __syncwarp();
+      FTRACE(0, t, 7);
       return true;
     };
     if (ok && my_tiles > 0) ok = conv1(0);
@@ -230,8 +256,11 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
     // e1: conv1 accumulator -> conv2 operand slab
     auto epi1 = [&](int t) -> bool {
       const int s = t & 1, ph = (t >> 1) & 1;
+      if (warp == 4) FTRACE(1, t, 0);
       if (!__all_sync(AP_FULL, mbar_wait(smem_u32(&s2_empty[s]), ph ^ 1, p.errflag))) return false;
+      if (warp == 4) FTRACE(1, t, 1);
       if (!__all_sync(AP_FULL, mbar_wait(smem_u32(&a1_full[s]), ph, p.errflag))) return false;
+      if (warp == 4) FTRACE(1, t, 2);
       tc_fence_after();
       uint32_t v[2][32];
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128 + c0);
@@ -254,12 +283,15 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's reads
       mbar_arrive(smem_u32(&s2_full[s]));
+      if (warp == 4) FTRACE(1, t, 3);
       return true;
     };
     // e2: conv2 accumulator -> global activation planes
     auto epi2 = [&](int t) -> bool {
       const int s = t & 1, ph = (t >> 1) & 1;
+      if (warp == 4) FTRACE(1, t, 4);
       if (!__all_sync(AP_FULL, mbar_wait(smem_u32(&a2_full[s]), ph, p.errflag))) return false;
+      if (warp == 4) FTRACE(1, t, 5);
       tc_fence_after();
       uint32_t v[2][32];
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(s * 128 + c0);
@@ -269,6 +301,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
       tmem_ld_wait_regs32(v[1]);
       tc_fence_before();
       mbar_arrive(smem_u32(&a2_empty[s]));
+      if (warp == 4) FTRACE(1, t, 6);
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -281,6 +314,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_front_tc(const __grid_constant
           *reinterpret_cast<uint4*>(p.out + ((long long)((c0 >> 3) + gi) * p.mpad + grow) * 8) = o;
         }
       }
+      if (warp == 4) FTRACE(1, t, 7);
       return true;
     };
     if (my_tiles > 0) ok = epi1(0);
@@ -331,7 +365,33 @@ int front_tc_launch(ap_engine* e, NetState* n, int n_boards, const int* n_boards
   p.H = n->H;
   p.errflag = n->d_err;
   const int grid = n_boards < n->sm_count ? n_boards : n->sm_count;
+#ifdef AP_FRONT_TRACE
+  static long long* d_trace = nullptr;
+  if (!d_trace) cudaMalloc(&d_trace, 3 * 64 * 8 * 8);
+  cudaMemsetAsync(d_trace, 0, 3 * 64 * 8 * 8, e->stream);
+  p.trace = d_trace;
+#endif
   k_front_tc<<<grid, kFThreads, FRONT_SMEM, e->stream>>>(p);
   AP_LAUNCH_CHECK(e);
+#ifdef AP_FRONT_TRACE
+  if (const char* path = getenv("AP_FRONT_TRACE_FILE")) {
+    static long long h[3 * 64 * 8];
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(path, "w")) {
+      long long t0 = h[0];
+      for (int i = 0; i < 3 * 64 * 8; ++i)
+        if (h[i] && h[i] < t0) t0 = h[i];
+      for (int role = 0; role < 3; ++role)
+        for (int t = 0; t < 64; ++t) {
+          if (!h[(role * 64 + t) * 8] && !h[(role * 64 + t) * 8 + 1]) continue;
+          fprintf(f, "%d %d", role, t);
+          for (int sl = 0; sl < 8; ++sl) fprintf(f, " %lld", h[(role * 64 + t) * 8 + sl] ? h[(role * 64 + t) * 8 + sl] - t0 : -1ll);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
+#endif
   return AP_OK;
 }

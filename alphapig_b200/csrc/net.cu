@@ -559,6 +559,7 @@ extern "C" int ap_net_load(ap_engine* e, int32_t arch, int32_t n_blocks, int32_t
   if (const char* m = getenv("AP_CONV4_128")) n->conv4_128 = m[0] - '0';
   if (const char* m = getenv("AP_HEAD_PAIR")) n->head_pair = m[0] != '0';
   if (const char* m = getenv("AP_FRONT_FUSED")) n->front_fused = m[0] != '0';
+  if (const char* m = getenv("AP_PAIR_CIN64")) n->pair_cin64 = m[0] != '0';
   if (const char* m = getenv("AP_HEAD_MODE")) n->head_mode = (m[0] == '0') ? 0 : (m[0] == '1') ? 1 : 2;
   long long total = 0;
   for (int i = 0; i < n_tensors; ++i) {
