@@ -101,7 +101,8 @@ struct NetState {
                       // fused-head layer (AP_CONV4 for A/B timing)
   int conv4_128 = 0;  // 128-channel layers on that kernel too: 1 = cin 64 (conv3), 2 = all (AP_CONV4_128, A/B timing)
   NetHeadW head_w;
-  int pair_cin64 = 0;   // layers with 64 input and 128 output channels (conv3) on the CTA-pair kernel too (AP_PAIR_CIN64, A/B)
+  int pair_cin64 = 1;   // layers with 64 input and 128 output channels (conv3) on the CTA-pair kernel too: 0.116 -> 0.108 ms per
+                        // lock-step on B200 (AP_PAIR_CIN64=0 for A/B)
   int front_fused = 1;  // conv1 + conv2 of the 6-conv net as one kernel (front_tc.cu); AP_FRONT_FUSED=0 runs the two layers
                         // separately (A/B timing and the bit-equality test)
   int head_pair = 1;  // run the fused-head layer on the CTA-pair kernel (measured faster: its double-buffered TMEM hides
