@@ -86,10 +86,13 @@ class _Trainer(object):
 
 def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, c_puct=5, temp=1.0, batch_size=128,
                         epochs=8, learn_rate=4e-4, buffer_size=2198800, n_in_row=5, seed=0, log=None, device_pick=True,
-                        overlap=True, kl_targ=0.02, warmup_iters=0, start_positions=None, prefill=None):
+                        overlap=True, kl_targ=0.02, warmup_iters=0, start_positions=None, prefill=None, trainer_share=0.0):
     """Returns a dict of counters / timings (per rank; wall clock).  ``warmup_iters`` iterations run first and are left
     out of every counter (the timed region then starts at a ply boundary with the pipeline full).
     start_positions: (cells, meta) every slot's first game starts from (default: empty boards).
+    trainer_share (multi-GPU, overlap): the trainer rank plays this fraction FEWER games than the others, so that its
+    plies - slowed down by the policy_update kernels sharing its GPU - take as long as everybody else's and the job is
+    not paced by rank 0 (the job's value is the sum of what all ranks played over the slowest rank's time).
     prefill: callable(ring) run once on the trainer rank before the first iteration - the reference fills its buffer
     from SGF records for the first 4000 batches before any self-play game is trained on (train_mxnet.py:270-273)."""
     import torch
@@ -102,6 +105,10 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
                                  learn_rate, buffer_size, n_in_row, seed, log, device_pick, multi, rank, world)
     from concurrent.futures import ThreadPoolExecutor
     dev = torch.device("cuda", net._device)
+    if multi and rank == 0 and trainer_share > 0:
+        n_games = max(1, int(round(n_games * (1.0 - trainer_share))))
+        if start_positions is not None:
+            start_positions = (start_positions[0][:n_games], start_positions[1][:n_games])
     sp = BatchedSelfPlay(net, n_games, n_playout=n_playout, c_puct=c_puct, temp=temp, n_in_row=n_in_row,
                          seed=seed + 1000 * rank, device_pick=True, device_records=True)
     if start_positions is not None:
@@ -203,7 +210,7 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
     if trainer is not None:
         out.update(train_steps=trainer.steps, ring_records=trainer.records, losses=trainer.losses, kls=trainer.kls,
                    lr_multiplier=trainer.lr_multiplier, early_stops=trainer.early_stops, t_trainer=trainer.seconds)
-    out.update(world=world, weight_swaps=state["swaps"], forced_openings=sp.forced_openings, overlap=True)
+    out.update(world=world, weight_swaps=state["swaps"], forced_openings=sp.forced_openings, overlap=True, n_games=n_games)
     sp.boundary_hook = None
     return out
 

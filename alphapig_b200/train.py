@@ -30,15 +30,15 @@ def trunk_plan(arch, n_blocks):
 
 
 def _bn_train(x, P, gamma, beta, mean_name, var_name, fix_gamma, new_stats):
-    mu = x.mean(dim=(0, 2, 3))
-    var = x.var(dim=(0, 2, 3), unbiased=False)
-    y = (x - mu[None, :, None, None]) / torch.sqrt(var + BN_EPS)[None, :, None, None]
-    if not fix_gamma:
-        y = y * P[gamma][None, :, None, None]
-    y = y + P[beta][None, :, None, None]
+    """BatchNorm in training mode (batch statistics, biased variance, eps 1e-3) through the fused native op -
+    one forward and one backward kernel instead of a dozen element-wise ones - plus the MXNet-style moving statistics
+    (momentum 0.9 on the biased batch variance)."""
+    y = F.batch_norm(x, None, None, weight=None if fix_gamma else P[gamma], bias=P[beta], training=True, momentum=0.0,
+                     eps=BN_EPS)
     with torch.no_grad():
-        new_stats[mean_name] = P[mean_name] * BN_MOMENTUM + mu.detach() * (1 - BN_MOMENTUM)
-        new_stats[var_name] = P[var_name] * BN_MOMENTUM + var.detach() * (1 - BN_MOMENTUM)
+        var, mu = torch.var_mean(x, dim=(0, 2, 3), unbiased=False)
+        new_stats[mean_name] = P[mean_name] * BN_MOMENTUM + mu * (1 - BN_MOMENTUM)
+        new_stats[var_name] = P[var_name] * BN_MOMENTUM + var * (1 - BN_MOMENTUM)
     return y
 
 
@@ -112,19 +112,30 @@ def train_step(arg, aux, opt, states, mcts_probs, winners, lr, arch, n_blocks=0,
     b1, b2, eps = 0.9, 0.999, 1e-8
     lr_t = lr * math.sqrt(1.0 - b2 ** opt.t) / (1.0 - b1 ** opt.t)
     with torch.no_grad():
-        for k, g in zip(names, grads):
-            w = arg[k]
-            g = g * (1.0 / B)
-            if k.endswith("_weight") or k.endswith("_gamma"):
-                g = g + wd * w
-            m = opt.m.get(k)
-            if m is None:
-                m = opt.m[k] = torch.zeros_like(w)
+        # multi-tensor (foreach) form of the per-parameter update: the same element-wise operations in the same
+        # order, ~12 kernel launches instead of ~10 per parameter tensor (on a GPU that is also running the search
+        # every trainer launch is a chance to delay a persistent conv kernel, alphapig_b200/loop.py)
+        ws = [arg[k] for k in names]
+        for k, w in zip(names, ws):
+            if k not in opt.m:
+                opt.m[k] = torch.zeros_like(w)
                 opt.v[k] = torch.zeros_like(w)
-            v = opt.v[k]
-            m.mul_(b1).add_(g, alpha=1 - b1)
-            v.mul_(b2).addcmul_(g, g, value=1 - b2)
-            w.sub_(lr_t * m / (v.sqrt() + eps))
-        for k, t in new_stats.items():
-            aux[k].copy_(t)
+        ms = [opt.m[k] for k in names]
+        vs = [opt.v[k] for k in names]
+        gs = torch._foreach_mul(list(grads), 1.0 / B)
+        decayed = [i for i, k in enumerate(names) if k.endswith("_weight") or k.endswith("_gamma")]
+        if decayed:
+            torch._foreach_add_([gs[i] for i in decayed], [ws[i] for i in decayed], alpha=wd)
+        torch._foreach_mul_(ms, b1)
+        torch._foreach_add_(ms, gs, alpha=1 - b1)
+        torch._foreach_mul_(vs, b2)
+        torch._foreach_addcmul_(vs, gs, gs, value=1 - b2)
+        den = torch._foreach_sqrt(vs)
+        torch._foreach_add_(den, eps)
+        upd = torch._foreach_mul(ms, lr_t)
+        torch._foreach_div_(upd, den)
+        torch._foreach_sub_(ws, upd)
+        stat_names = list(new_stats)
+        if stat_names:
+            torch._foreach_copy_([aux[k] for k in stat_names], [new_stats[k] for k in stat_names])
     return loss.detach(), entropy

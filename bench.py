@@ -654,7 +654,7 @@ def loop_leg(ctx, args, iters, warmup_iters, G, plies=2):
     clocks.start()
     res = selfplay_train_loop(net, G, iters, plies_per_iter=plies, n_playout=N_PLAYOUT, c_puct=C_PUCT, temp=1.0,
                               batch_size=128, epochs=8, seed=7, warmup_iters=warmup_iters, overlap=not args.no_overlap,
-                              start_positions=(cells, meta), prefill=prefill)
+                              start_positions=(cells, meta), prefill=prefill, trainer_share=args.trainer_share)
     clk = clocks.stop()
     t_max, coll_max = ctx.reduce([res["t_total"], res.get("t_collectives", 0.0)])
     playouts, plies_all, games, recs = ctx.reduce([res["playouts"], res["plies"], res["games"], res["records"]], op="sum")
@@ -674,7 +674,7 @@ def loop_leg(ctx, args, iters, warmup_iters, G, plies=2):
                                     "weights, NCCL" if ctx.world > 1 else "none (1 GPU)",
                             "seconds_main_thread_max": coll_max, "weight_broadcasts": res.get("broadcasts"),
                             "bytes_gathered": res.get("bytes_gathered"), "bytes_broadcast": res.get("bytes_broadcast")},
-            "overlap": bool(res.get("overlap")), "clocks": clk,
+            "overlap": bool(res.get("overlap")), "trainer_share": args.trainer_share, "clocks": clk,
             "timing": "wall clock from the ply boundary after the warm-up iterations to the end of the last iteration's "
                       "last search (barrier + synchronize both sides), max over ranks",
             "config": {"workload": "self-play + train loop (configs[4]): %d games per GPU, n_playout=%d, simple net, %d plies per "
@@ -780,6 +780,8 @@ def main():
     ap.add_argument("--device-records", action="store_true",
                     help="selfplay workload with --device-pick: records stay on the device (trajectories + outbox)")
     ap.add_argument("--no-overlap", action="store_true", help="loop workload: the synchronous loop (A/B)")
+    ap.add_argument("--trainer-share", type=float, default=0.0,
+                    help="loop workload, N > 1: the trainer rank plays this fraction fewer games (its GPU also trains)")
     ap.add_argument("--rollout-mode", type=int, default=0, choices=[0, 2],
                     help="pure workload: 0 = permutation rollouts (default), 2 = ply-by-ply rollouts (A/B)")
     ap.add_argument("--net", default="simple", choices=sorted(NETS),
