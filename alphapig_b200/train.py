@@ -33,8 +33,9 @@ def _bn_train(x, P, gamma, beta, mean_name, var_name, fix_gamma, new_stats):
     """BatchNorm in training mode (batch statistics, biased variance, eps 1e-3) through the fused native op -
     one forward and one backward kernel instead of a dozen element-wise ones - plus the MXNet-style moving statistics
     (momentum 0.9 on the biased batch variance)."""
-    y = F.batch_norm(x, None, None, weight=None if fix_gamma else P[gamma], bias=P[beta], training=True, momentum=0.0,
-                     eps=BN_EPS)
+    # fix_gamma: gamma is the constant 1 (an explicit ones vector: cuDNN's backward wants a defined weight tensor)
+    y = F.batch_norm(x, None, None, weight=x.new_ones(x.shape[1]) if fix_gamma else P[gamma], bias=P[beta], training=True,
+                     momentum=0.0, eps=BN_EPS)
     with torch.no_grad():
         var, mu = torch.var_mean(x, dim=(0, 2, 3), unbiased=False)
         new_stats[mean_name] = P[mean_name] * BN_MOMENTUM + mu * (1 - BN_MOMENTUM)
