@@ -123,6 +123,10 @@ struct ap_engine {
   uint64_t net_generation = 0;  // bumped by every weight preparation (kernel-parameter copies of the head weights)
   float last_total_ms = 0.f, last_net_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ap_search_run keeps at most two chunks of lock-steps queued on the stream (the host waits for the event of the
+  // chunk before last): a bottomless launch queue would block every other thread of the process that wants to launch
+  // on this GPU - the trainer of alphapig_b200/loop.py - behind thousands of search kernels
+  cudaEvent_t chunk_ev[3] = {nullptr, nullptr, nullptr};
   // optional per-phase timing of ap_search_run (ap_search_profile): events after every phase of every lock-step
   int profile = 0;
   std::vector<cudaEvent_t> prof_events;

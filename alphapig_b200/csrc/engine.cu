@@ -282,6 +282,8 @@ int ap_engine_destroy(ap_engine* e) {
   if (e->d_stage) cudaFree(e->d_stage);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->chunk_ev)
+    if (ev) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->stream);
@@ -523,9 +525,19 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
   // AP_GRAPH_MAX_GAMES: largest batch that replays the lock-steps as a CUDA graph (default 256; 0 disables)
   static const int graph_max_games = getenv("AP_GRAPH_MAX_GAMES") ? atoi(getenv("AP_GRAPH_MAX_GAMES")) : 256;
   const bool compact = net_can_compact(e);
+  // AP_ENQUEUE_CHUNK: lock-steps per chunk of the bounded launch queue (default 32; 0 = enqueue everything at once)
+  static const int enqueue_chunk = getenv("AP_ENQUEUE_CHUNK") ? atoi(getenv("AP_ENQUEUE_CHUNK")) : 32;
+  bool capturing = false;
   auto enqueue = [&]() -> int {
     AP_CUDA(e, cudaMemsetAsync(e->leaves.n_eval, 0, 4, e->stream));
     for (int it = 0; it < n_playout; ++it) {
+      if (!capturing && enqueue_chunk > 0 && it > 0 && it % enqueue_chunk == 0) {
+        const int c = it / enqueue_chunk;  // chunk about to be enqueued; chunk c - 1 was just completed on the host side
+        if (!e->chunk_ev[0])
+          for (auto& ev : e->chunk_ev) AP_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        AP_CUDA(e, cudaEventRecord(e->chunk_ev[(c - 1) % 3], e->stream));
+        if (c >= 2) AP_CUDA(e, cudaEventSynchronize(e->chunk_ev[(c - 2) % 3]));
+      }
       launch_select(e, compact && !compact_kernel);
       AP_LAUNCH_CHECK(e);
       prof_mark(e);
@@ -546,7 +558,9 @@ int ap_search_run(ap_engine* e, int32_t n_playout) {
     const uint64_t l0 = e->launches;
     cudaGraph_t g = nullptr;
     AP_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
     const int rc = enqueue();
+    capturing = false;
     const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
     if (rc != AP_OK) {
       if (g) cudaGraphDestroy(g);
