@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libalphapig_b200.so")
 AP_OK, AP_ERR_BAD_ARG, AP_ERR_ILLEGAL_MOVE, AP_ERR_POOL_EXHAUSTED = 0, -1, -2, -3
 AP_ERR_CUDA, AP_ERR_NO_NET, AP_ERR_BAD_HANDLE = -4, -5, -6
 AP_META_INTS = 8
+AP_FLAG_HIGH_PRIORITY_STREAM = 1
 AP_ARCH_SIMPLE, AP_ARCH_RESNET, AP_ARCH_INCEPTION = 0, 1, 2
 AP_NET_SPLIT = 0x100  # OR into arch: hi + lo fp16 operand pairs (near-fp32), residual net only
 AP_NET_SPLIT_ACT = 0x200  # OR into arch: hi + lo activations x error-diffusion-rounded fp16 weights, residual net only

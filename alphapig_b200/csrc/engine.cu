@@ -209,7 +209,12 @@ int ap_engine_create(const ap_config* cfg, ap_engine** out) {
     delete e;
     return code;
   };
-  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(AP_ERR_CUDA);
+  {
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const int prio = (cfg->flags & AP_FLAG_HIGH_PRIORITY_STREAM) ? hi : lo;
+    if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio) != cudaSuccess) return fail(AP_ERR_CUDA);
+  }
   const size_t G = g.G;
 #define ALLOC(ptr, bytes) \
   if ((rc = dev_alloc(e, (void**)&(ptr), (bytes))) != AP_OK) return fail(rc)

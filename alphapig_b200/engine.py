@@ -26,14 +26,14 @@ class Engine(object):
     game.py:36-38)."""
 
     def __init__(self, width=8, height=8, n_in_row=5, n_games=1, c_puct=5.0, n_playout=400,
-                 node_capacity=0, device=0):
+                 node_capacity=0, device=0, high_priority=False):
         self.lib = L.load()
         self.width, self.height, self.n_in_row = int(width), int(height), int(n_in_row)
         self.S = self.width * self.height
         self.G = int(n_games)
         self.c_puct = float(c_puct)
         cfg = L.ApConfig(self.width, self.height, self.n_in_row, self.G, int(node_capacity), int(n_playout),
-                         int(device), 0, self.c_puct)
+                         int(device), L.AP_FLAG_HIGH_PRIORITY_STREAM if high_priority else 0, self.c_puct)
         h = C.c_void_p()
         rc = self.lib.ap_engine_create(C.byref(cfg), C.byref(h))
         if rc == L.AP_ERR_BAD_ARG:

@@ -53,7 +53,8 @@ class PolicyValueNetBase(object):
         self._arg_names, self._aux_names = list(arg.keys()), list(aux.keys())
         self._engines = {}
         # the batch engine: forward for policy_value / policy_value_fn, owner of the master weights
-        self._eng = self._make_engine(1, n_in_row, 5.0, 1, arg, aux)
+        # (its stream has the highest priority: policy_value / the replay ring next to a search on the same GPU)
+        self._eng = self._make_engine(1, n_in_row, 5.0, 1, arg, aux, high_priority=True)
         self._torch = None
         self._opt = None
 
@@ -64,9 +65,10 @@ class PolicyValueNetBase(object):
         d.update(aux)
         return d
 
-    def _make_engine(self, n_games, n_in_row, c_puct, n_playout, arg=None, aux=None, node_capacity=0):
+    def _make_engine(self, n_games, n_in_row, c_puct, n_playout, arg=None, aux=None, node_capacity=0, high_priority=False):
         eng = Engine(width=self.board_width, height=self.board_height, n_in_row=n_in_row, n_games=n_games,
-                     c_puct=c_puct, n_playout=n_playout, node_capacity=node_capacity, device=self._device)
+                     c_puct=c_puct, n_playout=n_playout, node_capacity=node_capacity, device=self._device,
+                     high_priority=high_priority)
         if arg is None:
             merged = self._merged_host()
         else:

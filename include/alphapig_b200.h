@@ -51,6 +51,10 @@ typedef struct {
 } ap_config;
 
 #define AP_FLAG_NONE 0
+/* the handle's CUDA stream gets the highest priority: for small latency-sensitive handles (a trainer's batch forward and
+ * replay ring) that share the GPU with another handle's search - their kernels are scheduled as soon as an SM frees up
+ * instead of queueing behind the search's next persistent kernel */
+#define AP_FLAG_HIGH_PRIORITY_STREAM 1
 #define AP_META_INTS 8 /* current_player, last_move, n_stones, hist0..3 (most recent first, -1 = none), start_player */
 
 /* ---- lifecycle ------------------------------------------------------------ */
