@@ -56,6 +56,28 @@ class _Trainer(object):
         self.losses, self.kls = [], []
         self.seconds = 0.0
 
+    def warm(self):
+        """One throw-away train step on copies of the parameters (same shapes, same kernels): cuDNN / cuBLAS handles,
+        algorithm selection and lazy module loading cost seconds the first time and would otherwise land in the first
+        policy_update of the loop."""
+        import torch
+        from collections import OrderedDict
+        from . import train as T
+        net = self.net
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            _, views = net._views()
+            arg = OrderedDict((k, views[k].clone()) for k in net._arg_names)
+            aux = OrderedDict((k, views[k].clone()) for k in net._aux_names)
+            S = net.board_width * net.board_height
+            x = torch.zeros((self.batch_size, net.channelnum, net.board_height, net.board_width), device=self.dev)
+            pi = torch.full((self.batch_size, S), 1.0 / S, device=self.dev)
+            z = torch.zeros((self.batch_size, 1), device=self.dev)
+            for _ in range(2):
+                T.train_step(arg, aux, T.AdamState(), x, pi, z, 1e-3, net.arch,
+                             net._n_blocks if net.arch != "simple" else 0, wd=net.l2_const)
+            net.policy_value(np.zeros((self.batch_size, net.channelnum, net.board_height, net.board_width), np.float32))
+            self.stream.synchronize()
+
     def job(self, gathered):
         """gathered: list of uint8 CUDA tensors of packed records (one per rank)"""
         import torch
@@ -116,9 +138,11 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
     if start_positions is not None:
         sp.load_positions(*start_positions)
     trainer = _Trainer(net, buffer_size, batch_size, epochs, learn_rate, kl_targ) if rank == 0 else None
-    if trainer is not None and prefill is not None:
-        prefill(trainer.ring)
     pool = ThreadPoolExecutor(1) if rank == 0 else None
+    if trainer is not None:
+        pool.submit(trainer.warm).result()
+        if prefill is not None:
+            prefill(trainer.ring)
     if multi:
         apdist.broadcast_weights(net, src=0)  # identical start
     from .nets import _DevView
@@ -158,6 +182,11 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
             done = sp.step()
             if timed:
                 out["games"] += len(done)
+        # both ends of the clock sit right behind a step() (= right behind the launch of the next ply's search): the region
+        # holds n_iters x plies_per_iter whole ply periods and n_iters exchanges
+        if it == warmup_iters - 1:
+            t_start = time.perf_counter()
+        t_end = time.perf_counter()
         recs = state["outbox"]
         state["outbox"] = None
         # ---- exchanges, issued while the next ply's search runs in sp's background thread --------------------------
@@ -194,9 +223,6 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
             out["records"] += int(recs.shape[0])
             out["bytes_gathered"] += sum(int(g.shape[0]) for g in gathered) * int(recs.shape[1])
             out["t_collectives"] += t3 - t0
-        if it == warmup_iters - 1:
-            t_start = time.perf_counter()
-        t_end = time.perf_counter()
         if log and rank == 0:
             log("iter %d: %d games finished so far, ring %d, exchanges %.1f ms on the main thread"
                 % (it, out["games"], trainer.records, 1e3 * (t3 - t0)))
