@@ -92,17 +92,28 @@ def gather_replay(packed, device=None):
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(outs, counts)], axis=0)
 
 
-def gather_records_device(recs, dst=None, group=None):
+def gather_records_device(recs, dst=None, group=None, cpu_group=None):
     """Gather packed records that live on the GPU (a uint8 CUDA tensor [n][width], n differs per rank) straight over
-    NCCL: one tiny all-gather of the counts, then the padded record blocks - to rank ``dst`` only (``dist.gather``,
+    NCCL: an all-gather of the counts, then the padded record blocks - to rank ``dst`` only (``dist.gather``,
     NCCL send/recv underneath: the trainer is the only consumer) or to every rank (dst=None, all-gather).  Returns
-    the list of per-rank tensors trimmed to their counts (empty list on the ranks that receive nothing)."""
+    the list of per-rank tensors trimmed to their counts (empty list on the ranks that receive nothing).
+
+    cpu_group (a gloo group over the same ranks): the counts travel over it as CPU tensors.  That exchange is also the
+    rendezvous: a rank that arrives early waits on the HOST while its GPU keeps searching, and the NCCL kernels that
+    follow start within microseconds of each other on all GPUs.  Without it an early rank's NCCL kernel sits on its
+    SMs spinning for the slowest peer - and the search's persistent conv kernels, which need every SM, stall behind
+    it (measured on 8 x B200: 0.2 s per ply)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     nccl = dist.get_backend(group) == "nccl"
-    n = torch.tensor([recs.shape[0]], dtype=torch.int64, device=recs.device)
-    clist = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(clist, n, group=group)
+    if cpu_group is not None:
+        n = torch.tensor([recs.shape[0]], dtype=torch.int64)
+        clist = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(clist, n, group=cpu_group)
+    else:
+        n = torch.tensor([recs.shape[0]], dtype=torch.int64, device=recs.device)
+        clist = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(clist, n, group=group)
     counts = [int(c.item()) for c in clist]
     mx = max(counts + [1])
     width = recs.shape[1]

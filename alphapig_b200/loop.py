@@ -143,6 +143,9 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
         pool.submit(trainer.warm).result()
         if prefill is not None:
             prefill(trainer.ring)
+    # host-side rendezvous group (gloo): ranks meet on the CPU before any NCCL kernel is launched, see
+    # dist.gather_records_device
+    cpu_group = dist.new_group(backend="gloo") if multi and dist.get_backend() == "nccl" else None
     if multi:
         apdist.broadcast_weights(net, src=0)  # identical start
     from .nets import _DevView
@@ -169,7 +172,7 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
                t_collectives=0.0, iters=0)
     fut = None
     pending = []
-    ready = torch.zeros(1, dtype=torch.int32, device=dev)
+    ready = torch.zeros(1, dtype=torch.int32, device=dev if (multi and cpu_group is None) else "cpu")
     # The timed region starts and ends right behind the launch of a ply's search (no device synchronisation: that would
     # let the search in flight finish off the clock), so it covers n_iters * plies_per_iter whole periods per rank.
     t_start = time.perf_counter()
@@ -191,14 +194,14 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
         state["outbox"] = None
         # ---- exchanges, issued while the next ply's search runs in sp's background thread --------------------------
         t0 = time.perf_counter()
-        gathered = apdist.gather_records_device(recs, dst=0) if multi else [recs]
+        gathered = apdist.gather_records_device(recs, dst=0, cpu_group=cpu_group) if multi else [recs]
         if rank == 0:
             pending.extend(g for g in gathered if g.shape[0])
         # The trainer shares its GPU with rank 0's search and is slowed down by it; nobody waits for it.  Rank 0 tells
         # the others whether a finished policy_update is there to be broadcast; if not, the records just queue up.
         ready[0] = 1 if (rank != 0 or fut is None or fut.done()) else 0
         if multi:
-            dist.broadcast(ready, src=0)
+            dist.broadcast(ready, src=0, group=cpu_group)
         t1 = time.perf_counter()
         if int(ready.item()):
             if rank == 0 and fut is not None:
@@ -231,6 +234,8 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
     torch.cuda.synchronize(dev)
     if multi:
         dist.barrier()
+    if cpu_group is not None:
+        dist.destroy_process_group(cpu_group)
     if fut is not None:
         fut.result()
     if rank == 0 and pending:

@@ -213,6 +213,9 @@ if rank == 0:
     assert np.array_equal(torch.cat(parts0).numpy(), allp)
 else:
     assert parts0 == []
+cg = dist.new_group(backend="gloo")  # the host-side rendezvous group of the loop
+parts1 = D.gather_records_device(t, dst=1, cpu_group=cg)
+assert (np.array_equal(torch.cat(parts1).numpy(), allp) if rank == 1 else parts1 == [])
 bits2, pis2, z2 = D.split_records(allp, S)
 st_u, pi_u, z_u = D.unpack_records(allp, S, 6, 6)
 assert np.array_equal(np.unpackbits(bits2, axis=1)[:, :9 * S].reshape(-1, 9, 6, 6).astype(np.float32), st_u)
