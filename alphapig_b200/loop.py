@@ -31,6 +31,7 @@ The trainer job is the reference's ``TrainPipeline.policy_update`` (train_mxnet.
 ``random.sample`` semantics from the ring, up to ``epochs`` steps on it, early stop at KL > 4 kl_targ, adaptive
 ``lr_multiplier`` (``train_mxnet.kl_and_lr_rule``).
 """
+import os
 import time
 
 import numpy as np
@@ -179,10 +180,13 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
     t_end = t_start
     for it in range(warmup_iters + n_iters):
         timed = it >= warmup_iters
+        detail = []
         for p in range(plies_per_iter):
             if p == plies_per_iter - 1:
                 state["take"] = True
+            ts = time.perf_counter()
             done = sp.step()
+            detail.append(round(time.perf_counter() - ts, 4))
             if timed:
                 out["games"] += len(done)
         # both ends of the clock sit right behind a step() (= right behind the launch of the next ply's search): the region
@@ -194,20 +198,23 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
         state["outbox"] = None
         # ---- exchanges, issued while the next ply's search runs in sp's background thread --------------------------
         t0 = time.perf_counter()
-        gathered = apdist.gather_records_device(recs, dst=0, cpu_group=cpu_group) if multi else [recs]
+        no_coll = os.environ.get("AP_LOOP_NOCOLL") == "1"   # development A/B: every rank keeps its records, no NCCL at all
+        no_train = os.environ.get("AP_LOOP_NOTRAIN") == "1"  # development A/B: exchanges as usual, the trainer job is a no-op
+        gathered = apdist.gather_records_device(recs, dst=0, cpu_group=cpu_group) if (multi and not no_coll) else [recs]
+        tg = time.perf_counter()
         if rank == 0:
             pending.extend(g for g in gathered if g.shape[0])
         # The trainer shares its GPU with rank 0's search and is slowed down by it; nobody waits for it.  Rank 0 tells
         # the others whether a finished policy_update is there to be broadcast; if not, the records just queue up.
         ready[0] = 1 if (rank != 0 or fut is None or fut.done()) else 0
-        if multi:
+        if multi and not no_coll:
             dist.broadcast(ready, src=0, group=cpu_group)
         t1 = time.perf_counter()
         if int(ready.item()):
             if rank == 0 and fut is not None:
                 fut.result()
                 fut = None
-            if multi:
+            if multi and not no_coll:
                 dist.broadcast(flat, src=0)
             staged.copy_(flat)  # the trainer is idle here: a consistent snapshot, swapped in at the next boundary
             torch.cuda.current_stream(dev).synchronize()  # (not the device: the next ply's search is in flight)
@@ -216,9 +223,11 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
                 out["broadcasts"] += 1
                 out["bytes_broadcast"] += flat.numel() * 4 if multi else 0
             if rank == 0:
-                fut = pool.submit(trainer.job, pending)
+                fut = pool.submit(trainer.job, [] if no_train else pending)
                 pending = []
         t3 = time.perf_counter()
+        if timed:
+            out.setdefault("detail", []).append(detail + [round(tg - t0, 4), round(t1 - tg, 4), round(t3 - t1, 4)])
         if timed:
             out["iters"] += 1
             out["plies"] += plies_per_iter * n_games

@@ -656,6 +656,8 @@ def loop_leg(ctx, args, iters, warmup_iters, G, plies=2):
                               batch_size=128, epochs=8, seed=7, warmup_iters=warmup_iters, overlap=not args.no_overlap,
                               start_positions=(cells, meta), prefill=prefill, trainer_share=args.trainer_share)
     clk = clocks.stop()
+    if os.environ.get("AP_LOOP_DETAIL") == "1":  # development: every rank's per-iteration timings
+        sys.stderr.write("rank %d [step s ..., gather, flag, bcast+submit] %s t_total %.3f\n" % (ctx.rank, res.get("detail"), res["t_total"]))
     t_max, coll_max = ctx.reduce([res["t_total"], res.get("t_collectives", 0.0)])
     playouts, plies_all, games, recs = ctx.reduce([res["playouts"], res["plies"], res["games"], res["records"]], op="sum")
     net.close()

@@ -24,6 +24,7 @@ ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--device-pick", action="store_true", help="synchronous loop: sample the self-play moves on the device")
 ap.add_argument("--no-overlap", action="store_true", help="the synchronous loop (host-staged records, engines drained while training)")
 ap.add_argument("--warmup-iters", type=int, default=1)
+ap.add_argument("--detail", action="store_true", help="print every rank's per-iteration timings to stderr")
 a = ap.parse_args()
 
 import torch  # noqa: E402
@@ -49,8 +50,11 @@ cnt = torch.tensor([res["plies"], res["playouts"], res["games"]], dtype=torch.fl
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+if a.detail:
+    print("rank %s detail [step s ..., gather, flag, bcast+submit]: %s host_s %.3f" % (os.environ.get("RANK", "0"), res.get("detail"), 0.0),
+          file=sys.stderr)
 if int(os.environ.get("RANK", "0")) == 0:
-    keep = {k: v for k, v in res.items() if k not in ("losses", "kls")}
+    keep = {k: v for k, v in res.items() if k not in ("losses", "kls", "detail")}
     print(json.dumps({"workload": "self-play + train loop, %s net, %d games/GPU, n_playout %d" % (a.arch, a.games, a.playouts),
                       "n_gpus": world, "moves_per_s": float(cnt[0] / t[0]), "playouts_per_s": float(cnt[1] / t[0]),
                       "games_finished": int(cnt[2]), "seconds_total_max": float(t[0]), "rank0": keep,
