@@ -31,7 +31,6 @@ The trainer job is the reference's ``TrainPipeline.policy_update`` (train_mxnet.
 ``random.sample`` semantics from the ring, up to ``epochs`` steps on it, early stop at KL > 4 kl_targ, adaptive
 ``lr_multiplier`` (``train_mxnet.kl_and_lr_rule``).
 """
-import os
 import time
 
 import numpy as np
@@ -130,6 +129,7 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
                                  learn_rate, buffer_size, n_in_row, seed, log, device_pick, multi, rank, world)
     from concurrent.futures import ThreadPoolExecutor
     dev = torch.device("cuda", net._device)
+    S = net.board_width * net.board_height
     if multi and rank == 0 and trainer_share > 0:
         n_games = max(1, int(round(n_games * (1.0 - trainer_share))))
         if start_positions is not None:
@@ -174,6 +174,14 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
     fut = None
     pending = []
     ready = torch.zeros(1, dtype=torch.int32, device=dev if (multi and cpu_group is None) else "cpu")
+    if multi:
+        # first use of every collective of the loop, off the clock: NCCL sets up its send/recv and broadcast connections
+        # lazily, which costs ~1.5 s on 8 GPUs the first time (the gather to the trainer is grouped point-to-point traffic)
+        apdist.gather_records_device(torch.zeros((1, apdist.record_width(S)), dtype=torch.uint8, device=dev), dst=0,
+                                     cpu_group=cpu_group)
+        dist.broadcast(ready, src=0, group=cpu_group)
+        dist.broadcast(flat, src=0)
+        torch.cuda.synchronize(dev)
     # The timed region starts and ends right behind the launch of a ply's search (no device synchronisation: that would
     # let the search in flight finish off the clock), so it covers n_iters * plies_per_iter whole periods per rank.
     t_start = time.perf_counter()
@@ -198,23 +206,21 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
         state["outbox"] = None
         # ---- exchanges, issued while the next ply's search runs in sp's background thread --------------------------
         t0 = time.perf_counter()
-        no_coll = os.environ.get("AP_LOOP_NOCOLL") == "1"   # development A/B: every rank keeps its records, no NCCL at all
-        no_train = os.environ.get("AP_LOOP_NOTRAIN") == "1"  # development A/B: exchanges as usual, the trainer job is a no-op
-        gathered = apdist.gather_records_device(recs, dst=0, cpu_group=cpu_group) if (multi and not no_coll) else [recs]
+        gathered = apdist.gather_records_device(recs, dst=0, cpu_group=cpu_group) if multi else [recs]
         tg = time.perf_counter()
         if rank == 0:
             pending.extend(g for g in gathered if g.shape[0])
         # The trainer shares its GPU with rank 0's search and is slowed down by it; nobody waits for it.  Rank 0 tells
         # the others whether a finished policy_update is there to be broadcast; if not, the records just queue up.
         ready[0] = 1 if (rank != 0 or fut is None or fut.done()) else 0
-        if multi and not no_coll:
+        if multi:
             dist.broadcast(ready, src=0, group=cpu_group)
         t1 = time.perf_counter()
         if int(ready.item()):
             if rank == 0 and fut is not None:
                 fut.result()
                 fut = None
-            if multi and not no_coll:
+            if multi:
                 dist.broadcast(flat, src=0)
             staged.copy_(flat)  # the trainer is idle here: a consistent snapshot, swapped in at the next boundary
             torch.cuda.current_stream(dev).synchronize()  # (not the device: the next ply's search is in flight)
@@ -223,7 +229,7 @@ def selfplay_train_loop(net, n_games, n_iters, plies_per_iter=4, n_playout=400, 
                 out["broadcasts"] += 1
                 out["bytes_broadcast"] += flat.numel() * 4 if multi else 0
             if rank == 0:
-                fut = pool.submit(trainer.job, [] if no_train else pending)
+                fut = pool.submit(trainer.job, pending)
                 pending = []
         t3 = time.perf_counter()
         if timed:

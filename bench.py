@@ -266,7 +266,10 @@ class Ctx(object):
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            import datetime
+            # a rank that dies must not leave the others in a collective for NCCL's default 10 minutes
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local),
+                                    timeout=datetime.timedelta(seconds=180))
             self.dist = dist
         try:
             self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
