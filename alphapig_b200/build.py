@@ -22,7 +22,11 @@ def _stale():
 
 
 def build(force=False, verbose=False):
+    """Compile every source of csrc/ for sm_100a and link libalphapig_b200.so in-tree.  Prints ONE line saying whether it
+    compiled or re-used an up-to-date library (so a build log shows which it was)."""
     if not force and not _stale():
+        print("[alphapig_b200.build] up to date, re-using %s (newer than every file of csrc/ and the header); "
+              "--force recompiles" % os.path.relpath(LIB))
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("AP_NVCC_EXTRA", "").split()  # development A/B builds, e.g. -DAP_PURE_MINBLK=24
@@ -43,6 +47,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs +
                           ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    print("[alphapig_b200.build] compiled %d sources with %s -gencode arch=compute_100a,code=sm_100a -> %s"
+          % (len(SOURCES), nvcc, os.path.relpath(LIB)))
     return LIB
 
 
