@@ -569,6 +569,20 @@ def pure_leg(ctx, args, steps, warmup, G, cpu=False):
     return out
 
 
+def whole_period_roofline(ctx, playouts_per_s, terminal_frac, what):
+    """Tensor roofline of a leg that is timed by wall clock over whole ply periods (search + tree kernels + sampling +
+    records + exchanges): algorithmic trunk FLOPs of the evaluated leaves per second against the sustained bf16 peak.  The
+    conv-kernel-only fraction is the headline's `roofline`; this one also pays for everything else in the period."""
+    from alphapig_b200.params import flop_per_leaf
+    head_flop = 2 * (256 * 6 * W * H + 4 * (W * H) ** 2 + 2 * W * H)
+    conv_flop_leaf = flop_per_leaf("simple", W, H) - head_flop
+    peak_tf = float(ctx.peaks.get("bf16_tflops_sustained", 1400.0)) * ctx.world
+    ach = playouts_per_s * (1.0 - terminal_frac) * conv_flop_leaf / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "peak_source": ctx.peak_src + " (bf16 sustained x n_gpus)", "traffic": None,
+            "terminal_leaf_frac": terminal_frac, "what": what}
+
+
 # ------------------------------------------------------------------------------------------
 # real self-play plies (BatchedSelfPlay.step: search + move sampling, recording, re-rooting); `--workload selfplay`
 # ------------------------------------------------------------------------------------------
@@ -616,6 +630,13 @@ def selfplay_leg(ctx, args, steps, warmup, G):
     sp.drain()
     dt_max, = ctx.reduce([dt])
     moves_all, games_all = ctx.reduce([moves, games], op="sum")
+    # share of terminal leaves (they never reach the net) over all searches since the last counter reset
+    term_frac = 0.0
+    try:
+        st = [part.eng.search_stats() for part in parts]
+        term_frac = sum(x["terminal_leaves"] for x in st) / float(max(1, sum(x["playouts"] for x in st)))
+    except Exception:
+        pass
     host_ms = 1000 * (sp.host_seconds - host0) / steps
     forced = sum(getattr(part, "forced_openings", 0) for part in parts)
     cap = [part.eng.node_capacity() for part in parts]
@@ -633,6 +654,8 @@ def selfplay_leg(ctx, args, steps, warmup, G):
                         else "host (features + pi copied per ply)"),
             "games_finished": int(games_all), "forced_openings": int(forced),
             "node_capacity": cap, "clocks": clk,
+            "roofline": whole_period_roofline(ctx, moves_all * N_PLAYOUT / dt_max, term_frac,
+                                              "trunk FLOPs of the evaluated leaves over the wall clock of whole self-play plies"),
             "timing": "wall clock over `steps` whole periods of every game's ply (search + sampling + re-root + records; the "
                       "region starts and ends right behind the launch of the next ply's search), max over ranks",
             "config": {"workload": "BatchedSelfPlay.step: %d games per GPU, n_playout=%d, temp=1.0, Dirichlet noise, records kept, "
@@ -760,6 +783,21 @@ def run_gpu(args):
                 legs["inception"] = az_leg(ctx, args, "inception", 3, 2, G, e2e=False)
                 legs["single_game_ms"] = single_game_leg(ctx)
             if ctx.rank == 0:
+                try:  # rooflines of the wall-clock legs (pure arithmetic on numbers already measured)
+                    tf = legs["selfplay"]["roofline"]["terminal_leaf_frac"]
+                    legs["loop"]["roofline"] = whole_period_roofline(
+                        ctx, legs["loop"]["value"], tf, "trunk FLOPs of the evaluated leaves over the wall clock of the self-play + "
+                        "train loop (terminal-leaf share taken from the selfplay leg)")
+                    sg = legs.get("single_game_ms")
+                    if sg:
+                        from alphapig_b200.params import flop_per_leaf
+                        peak = float(ctx.peaks.get("bf16_tflops_sustained", 1400.0))
+                        for key, wb in (("8x8", 8), ("15x15", 15)):
+                            ach = sg[key]["playouts_per_s"] * flop_per_leaf("simple", wb, wb) / 1e12
+                            sg[key]["roofline"] = {"bound": "launch latency (one leaf in flight: ~9 dependent kernels per playout)",
+                                                   "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}
+                except Exception as err:  # never lose the line over a derived number
+                    out["legs_roofline_error"] = repr(err)
                 out["moves_per_s_search_only"] = out["moves_per_s"]
                 out["moves_per_s"] = legs["selfplay"]["value"]
                 out["moves_per_s_note"] = ("played self-play moves per second (the `selfplay` leg: every ply decided by a full "
