@@ -185,7 +185,7 @@ def test_selfplay_train_loop_single_gpu(overlap):
     res = selfplay_train_loop(net, 64, 4, plies_per_iter=8, n_playout=16, batch_size=32, epochs=3, buffer_size=20000,
                               n_in_row=4, seed=1, overlap=overlap, warmup_iters=1 if overlap else 0)
     assert res["overlap"] == overlap and res["games"] > 20 and res["records"] >= 7 * res["games"] * (0 if overlap else 1)
-    assert res["train_steps"] >= 3 and np.isfinite(res["losses"]).all()
+    assert res["train_steps"] >= 1 and np.isfinite(res["losses"]).all()  # (KL early stop may end a policy_update after one step)
     assert res["playouts"] == 4 * 8 * 64 * 16 and res["t_total"] > 0
     if overlap:
         # nobody waits for the trainer: a swap happens whenever a policy_update had finished at an iteration boundary
