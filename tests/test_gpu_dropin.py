@@ -35,6 +35,8 @@ def test_train_pipeline_sequence_through_aliases(aliases):
     batch_size = 32
     random.seed(3)
     np.random.seed(3)
+    import torch
+    torch.manual_seed(3)  # Dropout masks of train_step
     board = Board(width=W, height=H, n_in_row=5)
     game = Game(board)
     game_ai = Game_AI(board)  # train_mxnet.py:47-48: Game and Game_AI share ONE board
