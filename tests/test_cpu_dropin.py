@@ -138,3 +138,34 @@ def test_unmodified_reference_train_script_drives_the_shims(tmp_path):
         print('ok')
     """, cwd=str(tmp_path))
     assert out.strip().endswith("ok")
+
+
+@needs_ref
+def test_reference_train_script_runs_as_main_on_the_aliases(tmp_path):
+    """``python train_mxnet.py`` itself - the reference's ``__main__`` block (train_mxnet.py:286-309: load
+    ./conf/train_config.yaml, build TrainPipeline, run(), send the closing e-mail) - executed with runpy on the aliases
+    from a working directory laid out like the reference's.  Without a GPU it gets through every import, the logging
+    configuration of the reference's own YAML, Board / Game / Game_AI and the SGF directory scan, logs the engine's
+    "no CPU fallback" error through ITS OWN ``except Exception`` handler and ends with the (inert) ``send_mail``."""
+    import shutil
+    (tmp_path / "conf").mkdir()
+    (tmp_path / "sgf_data").mkdir()
+    shutil.copy(os.path.join(REF, "conf", "train_config.yaml"), str(tmp_path / "conf" / "train_config.yaml"))
+    out = _run("""
+        import logging, os, runpy, sys
+        import alphapig_b200
+        alphapig_b200.install()
+        import torch
+        sent = []
+        import utils.send_email as se
+        real = se.send_mail
+        se.send_mail = lambda *a: (sent.append(a), real(*a))[1]
+        runpy.run_path(os.path.join(os.environ['ALPHAPIG_REFERENCE'], 'train_mxnet.py'), run_name='__main__')
+        assert len(sent) == 1, sent                      # the `finally:` of the reference's main block ran
+        assert os.path.isdir('logs')                      # its YAML's file handlers got their directory
+        if not torch.cuda.is_available():
+            log = open(os.path.join('logs', 'error.log')).read()
+            assert 'no CPU fallback' in log, log[-400:]
+        print('ok')
+    """, cwd=str(tmp_path))
+    assert out.strip().endswith("ok")
