@@ -10,7 +10,7 @@ OUT=${1:-gpurun_out}
 mkdir -p $OUT
 rc=0
 i=0
-for cfg in "s 128 0 2 64 1" "p 128 0 2 64 1" "s 384 2 148 256 3" "p 384 2 148 256 3" "p 384 2 148 512 3"; do
+[ -n "$SKIP_REPRO" ] || for cfg in "s 128 0 2 64 1" "p 128 0 2 64 1" "s 384 2 148 256 3" "p 384 2 148 256 3" "p 384 2 148 512 3"; do
   i=$((i+1))
   compute-sanitizer --tool racecheck --print-limit 5 tools/sanitizer_repro/tmem_alloc_pair $cfg > $OUT/sanitize_repro_racecheck_$i.log 2>&1
   echo "repro racecheck [$cfg]: $(grep -c 'Race reported' $OUT/sanitize_repro_racecheck_$i.log) race reports; $(grep -E 'tmem base|RACECHECK SUMMARY' $OUT/sanitize_repro_racecheck_$i.log | tr '\n' ' ')"
