@@ -31,6 +31,11 @@ for arch, nb in (("simple", 0), ("resnet", 2), ("inception", 1)):
     c, a, vis, _, rn = eng.search_root()
     assert int(rn.min()) == 6
 # round-2 kernels: multi-leaf search with virtual loss, device-side trajectories + outbox, packed ring push, pool growth
+# (back on the 6-conv net: the multi-leaf search needs the compacted-batch path the inception variant does not have)
+arg, aux = init_params("simple", 15, 15, seed=0, synthetic_stats=True)
+merged = dict(arg)
+merged.update(aux)
+eng.net_load("simple", merged)
 eng.search_advance(-1)
 eng.search_run_vl(8, 4)
 eng.traj_create(outbox_records=4096)
