@@ -370,3 +370,25 @@ def test_device_rollout_model_reproduces_logged_device_run():
     v, p = outcomes_from_ranks_numpy(full, n_empty, W, H, 5)
     assert "%.1f" % p.mean() == want_plies and "%.4f" % v.mean() == want_value, (p.mean(), v.mean(), line)
     assert int(v.sum()) == 360
+
+
+def test_reference_arm_positions_are_the_gpu_arms():
+    """bench.py --impl reference searches from the GPU arm's own synthetic positions (RandomState(1234 + g),
+    0 - 60 stones, redrawn while the random play already ended the game): the oracle board rebuilt from
+    draw_position's (cells, meta) carries the same stones, side to move, last move and last-four history."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for g in (0, 1, 5, 77, 4095):
+        b = bench.synthetic_position_cpu(g)
+        cells, meta = bench.draw_position(np.random.RandomState(1234 + g))  # first draw of the same stream
+        if not bench.oracle_board_from_position(cells, meta).game_end()[0]:   # (kept unless it had to be redrawn)
+            assert {m: int(cells[m]) for m in np.nonzero(cells)[0]} == b.states and int(meta[1]) == b.last_move
+        assert not b.game_end()[0]
+        assert len(b.states) % 2 == 0 and b.current_player == 1 and len(b.states) <= 60
+        assert sorted(b.availables) == [m for m in range(225) if m not in b.states]
+        if b.states:
+            assert b.last_move == b.history[-1][0] and b.states[b.last_move] == 2
+            assert [m for m, _ in b.history[-4:]] == [m for m, _ in b.history][-4:]
+        st = b.current_state()
+        assert st.shape == (9, 15, 15) and st[8].all()           # even stone count: colour plane all ones
+        assert st[6].sum() + st[7].sum() == len(b.states)         # planes 6 / 7: all stones of both sides
